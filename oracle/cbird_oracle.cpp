@@ -1,0 +1,376 @@
+// TEST INFRASTRUCTURE ONLY — a CPU restatement of cbird's hot path, used as the parity checker.
+// Nothing under cbird_b200/ (the product) may include, link, import or call this file; only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+//
+// Pinning status (see DESIGN.md "Oracle"):
+//   * Hamming radius search  : PINNED against the reference's own vptree.h / radix.h compiled
+//                              unmodified (oracle/_ref/libcbird_ref.so, tests/test_oracle_pinning.py).
+//   * DctVideoIndex          : PINNED the same way for the bucket search; findVideo/findFrame scoring is
+//                              restated from the cited lines and checked with the reference unit test's
+//                              parameter set (unit/testdctvideoindex.cpp:16-24,72-75).
+//   * dctHash64              : reference tests hold no golden hashes (unit/testcvutil.cpp:352-363 never
+//                              compares). Pinned against OpenCV itself (python cv2 4.13; the reference pins
+//                              2.4.13.7) via tests/golden/dcthash_*.npz made by oracle/make_golden.py.
+//                              blur/resize are integer/byte-exact vs cv2; the f32 DCT differs from cv2's
+//                              FFT-based DCT in rounding only — flip rate measured and stated.
+//   * CvFeaturesIndex        : "parity unpinned" vs the reference's LSH (randomised per build);
+//                              exact kNN pinned against cv2.BFMatcher golden vectors.
+//
+// Every function cites the reference lines (under /root/reference/) it follows.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+extern "C" {
+
+// src/hamm.h:24-26
+int orc_hamm64(uint64_t a, uint64_t b) { return __builtin_popcountll(a ^ b); }
+
+// ---------------------------------------------------------------------------------------------
+// dctHash64  — src/cvutil.cpp:435-545
+// ---------------------------------------------------------------------------------------------
+
+// zig-zag order of the 9x9 low-frequency block, src/cvutil.cpp:491-495, generated rather than
+// tabulated: anti-diagonal d is walked bottom-left -> top-right when d is odd, else the other way.
+static void zigzag81(int* zz) {
+  int k = 0;
+  for (int d = 0; d <= 16; ++d) {
+    if (d & 1) {
+      for (int r = std::min(d, 8); r >= 0 && d - r <= 8; --r) zz[k++] = 9 * r + (d - r);
+    } else {
+      for (int r = std::max(0, d - 8); r <= 8 && d - r >= 0; ++r) zz[k++] = 9 * r + (d - r);
+    }
+  }
+}
+
+void orc_zigzag81(int* out) { zigzag81(out); }
+
+// orthonormal DCT-II basis, rows 0..8 (cv::dct semantics, src/cvutil.cpp:477):
+// C[u][x] = a(u) cos((2x+1) u pi / 64), a(0)=sqrt(1/32), a(u>0)=sqrt(2/32)
+static void dct_basis(float C[9][32]) {
+  for (int u = 0; u < 9; ++u) {
+    double a = (u == 0) ? sqrt(1.0 / 32.0) : sqrt(2.0 / 32.0);
+    for (int x = 0; x < 32; ++x) C[u][x] = (float)(a * cos((2 * x + 1) * u * M_PI / 64.0));
+  }
+}
+void orc_dct_basis(float* out) {
+  float C[9][32];
+  dct_basis(C);
+  memcpy(out, C, sizeof(C));
+}
+
+static inline int reflect101(int p, int n) {  // cv::BORDER_REFLECT_101 (default border of cv::blur)
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) {
+    if (p < 0) p = -p;
+    else p = 2 * (n - 1) - p;
+  }
+  return p;
+}
+
+static inline uint8_t round_half_even_u8(float v) {  // saturate_cast<uchar>(float) == cvRound + clamp
+  long r = lrintf(v);                                 // default rounding mode: nearest even
+  return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+// cv::blur(gray, k x k): normalised box filter, centre anchor, BORDER_REFLECT_101 — cvutil.cpp:457-465.
+// u8 result = nearest integer of sum/k^2 (k^2 odd: never a tie).
+static void box_blur(const uint8_t* src, int w, int h, int stride, int k, std::vector<uint8_t>& dst) {
+  dst.resize((size_t)w * h);
+  const int r = k / 2, area = k * k;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int s = 0;
+      for (int dy = -r; dy <= r; ++dy) {
+        const uint8_t* row = src + (size_t)reflect101(y + dy, h) * stride;
+        for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
+      }
+      dst[(size_t)y * w + x] = (uint8_t)((2 * s + area) / (2 * area));
+    }
+}
+
+struct AreaTap {
+  int di, si;
+  float alpha;
+};
+
+// OpenCV's computeResizeAreaTab (imgproc resize.cpp; third-party, restated from its published
+// algorithm): coverage weights of source cells for each destination cell, as f32.
+static void area_taps(int ssize, int dsize, double scale, std::vector<AreaTap>& tab) {
+  tab.clear();
+  for (int dx = 0; dx < dsize; ++dx) {
+    double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    double cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) tab.push_back({dx, sx1 - 1, (float)((sx1 - fsx1) / cell)});
+    for (int sx = sx1; sx < sx2; ++sx) tab.push_back({dx, sx, float(1.0 / cell)});
+    if (fsx2 - sx2 > 1e-3) tab.push_back({dx, sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+  }
+}
+
+// cv::resize(gray, 32x32, INTER_AREA) for downscaling — cvutil.cpp:471.
+// integer factors: (s+2)>>2 for 2x2, else rint(sum * float(1/(fx*fy))); otherwise f32 area weights,
+// rows accumulated in source order, rint (half to even) at the end.
+static int area_resize32(const uint8_t* src, int w, int h, int stride, uint8_t dst[32 * 32]) {
+  if (w < 32 || h < 32) return -1;  // up-scaling uses a different (bilinear-like) OpenCV path: unsupported
+  if (w == 32 && h == 32) {
+    for (int y = 0; y < 32; ++y) memcpy(dst + 32 * y, src + (size_t)y * stride, 32);
+    return 0;
+  }
+  const double sx = w / 32.0, sy = h / 32.0;
+  const int ix = (int)lrint(sx), iy = (int)lrint(sy);
+  const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
+  if (fast) {
+    if (ix == 2 && iy == 2) {
+      for (int y = 0; y < 32; ++y)
+        for (int x = 0; x < 32; ++x) {
+          const uint8_t* a = src + (size_t)(2 * y) * stride + 2 * x;
+          const uint8_t* b = a + stride;
+          dst[32 * y + x] = (uint8_t)((a[0] + a[1] + b[0] + b[1] + 2) >> 2);
+        }
+      return 0;
+    }
+    const float scale = 1.f / (ix * iy);
+    for (int y = 0; y < 32; ++y)
+      for (int x = 0; x < 32; ++x) {
+        int s = 0;
+        for (int dy = 0; dy < iy; ++dy)
+          for (int dx = 0; dx < ix; ++dx) s += src[(size_t)(y * iy + dy) * stride + x * ix + dx];
+        dst[32 * y + x] = round_half_even_u8((float)s * scale);
+      }
+    return 0;
+  }
+  std::vector<AreaTap> xt, yt;
+  area_taps(w, 32, sx, xt);
+  area_taps(h, 32, sy, yt);
+  float buf[32], sum[32];
+  for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+  int prev_dy = yt[0].di;
+  for (size_t j = 0; j < yt.size(); ++j) {
+    const float beta = yt[j].alpha;
+    const int dy = yt[j].di;
+    const uint8_t* S = src + (size_t)yt[j].si * stride;
+    for (int i = 0; i < 32; ++i) buf[i] = 0.f;
+    for (size_t k = 0; k < xt.size(); ++k) buf[xt[k].di] += (float)S[xt[k].si] * xt[k].alpha;
+    if (dy != prev_dy) {
+      for (int i = 0; i < 32; ++i) {
+        dst[32 * prev_dy + i] = round_half_even_u8(sum[i]);
+        sum[i] = beta * buf[i];
+      }
+      prev_dy = dy;
+    } else {
+      for (int i = 0; i < 32; ++i) sum[i] += beta * buf[i];
+    }
+  }
+  for (int i = 0; i < 32; ++i) dst[32 * prev_dy + i] = round_half_even_u8(sum[i]);
+  return 0;
+}
+
+// steps 2-3 only (blur + resize), exposed so they can be pinned byte-exactly against cv2
+int orc_preprocess32(const uint8_t* img, int w, int h, int stride, uint8_t* out32) {
+  const long area = (long)w * h;  // cvutil.cpp:446-455
+  int k = 7;
+  if (area <= 32 * 32) k = 0;
+  else if (area <= 64 * 64) k = 3;
+  else if (area <= 128 * 128) k = 5;
+  if (k) {
+    std::vector<uint8_t> blurred;
+    box_blur(img, w, h, stride, k, blurred);
+    return area_resize32(blurred.data(), w, h, w, out32);
+  }
+  return area_resize32(img, w, h, stride, out32);
+}
+
+// steps 4-9 on a 32x32 u8 tile. The DCT is the separable partial transform C9 * X * C9^T in f32 with a
+// FIXED operation order (even/odd butterfly, then a 16-term fmaf chain in ascending index) that the
+// CUDA kernel follows instruction for instruction, so GPU == this function bit-exactly; the distance
+// of both to cv::dct's FFT-based f32 rounding is measured against cv2 goldens.
+// If coef64 != NULL it receives the 64 selected coefficients, *thresh_out the threshold.
+uint64_t orc_hash_from_tile32(const uint8_t* tile, float* coef64, float* thresh_out) {
+  static float C[9][32];
+  static int zz[81];
+  static bool init = false;
+  if (!init) {
+    dct_basis(C);
+    zigzag81(zz);
+    init = true;
+  }
+  float T[32][9];
+  for (int y = 0; y < 32; ++y) {
+    float s[16], d[16];
+    for (int x = 0; x < 16; ++x) {
+      float a = (float)tile[32 * y + x], b = (float)tile[32 * y + 31 - x];
+      s[x] = a + b;
+      d[x] = a - b;
+    }
+    for (int u = 0; u < 9; ++u) {
+      const float* in = (u & 1) ? d : s;
+      float acc = 0.f;
+      for (int x = 0; x < 16; ++x) acc = fmaf(C[u][x], in[x], acc);
+      T[y][u] = acc;
+    }
+  }
+  float F[81];
+  for (int u = 0; u < 9; ++u) {
+    float s[16], d[16];
+    for (int y = 0; y < 16; ++y) {
+      s[y] = T[y][u] + T[31 - y][u];
+      d[y] = T[y][u] - T[31 - y][u];
+    }
+    for (int v = 0; v < 9; ++v) {
+      const float* in = (v & 1) ? d : s;
+      float acc = 0.f;
+      for (int y = 0; y < 16; ++y) acc = fmaf(C[v][y], in[y], acc);
+      F[9 * v + u] = acc;  // row v = vertical frequency (cv::dct layout), cvutil.cpp:482-485
+    }
+  }
+  float c[64];
+  for (int i = 0; i < 64; ++i) c[i] = F[zz[6 + i]];  // cvutil.cpp:508,513 keep zig-zag positions 6..69
+  // cv::sum accumulates in double (cvutil.cpp:528); order = butterfly tree (matches the warp reduction)
+  double v[32];
+  for (int i = 0; i < 32; ++i) v[i] = (double)c[i] + (double)c[i + 32];
+  for (int off = 16; off >= 1; off >>= 1) {
+    double t[32];
+    for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ off];
+    memcpy(v, t, sizeof(v));
+  }
+  const float thresh = (float)v[0] / 64.f;  // cvutil.cpp:528-529
+  uint64_t hash = 0;
+  for (int i = 1; i < 64; ++i)
+    if (c[i] > thresh) hash |= 1ull << i;  // cvutil.cpp:537-538, bit 0 never set
+  if (hash == 0) hash = 1;                 // cvutil.cpp:542
+  if (coef64) memcpy(coef64, c, sizeof(c));
+  if (thresh_out) *thresh_out = thresh;
+  return hash;
+}
+
+// whole dctHash64 for one 8UC1 image. returns 0 on unsupported geometry (hash 0 == "no hash").
+uint64_t orc_dct_hash64(const uint8_t* img, int w, int h, int stride) {
+  uint8_t tile[32 * 32];
+  if (orc_preprocess32(img, w, h, stride, tile) != 0) return 0;
+  return orc_hash_from_tile32(tile, nullptr, nullptr);
+}
+
+// batch over frames laid out frame_stride bytes apart, `threads` host threads (cpu baseline leg)
+double orc_dct_hash64_batch(const uint8_t* frames, long long n, int w, int h, int stride, long long frame_stride,
+                            uint64_t* out, int threads) {
+  if (threads < 1) threads = 1;
+  {
+    uint8_t zero[32 * 32] = {0};
+    orc_hash_from_tile32(zero, nullptr, nullptr);  // initialise the static tables before threads start
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int wk) {
+    long long lo = n * wk / threads, hi = n * (wk + 1) / threads;
+    for (long long i = lo; i < hi; ++i) out[i] = orc_dct_hash64(frames + i * frame_stride, w, h, stride);
+  };
+  std::vector<std::thread> pool;
+  for (int wk = 1; wk < threads; ++wk) pool.emplace_back(work, wk);
+  work(0);
+  for (auto& th : pool) th.join();
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// DctHashIndex::find — src/dcthashindex.cpp:193-220. The shipped path is the VP tree (exact radius
+// search, strict `<`, src/tree/vptree.h:239,248); an exact radius search is order-insensitive, so the
+// restatement is the brute loop the reference keeps beside it (:209-217), which also drops removed
+// rows (id 0).  Output: every (id, dist) with dist < threshold, in index order.
+// ---------------------------------------------------------------------------------------------
+long long orc_dct_find(const uint64_t* hashes, const uint32_t* ids, long long n, uint64_t target, int threshold,
+                       uint32_t* out_ids, int* out_dist, long long cap) {
+  if (target == 0) return 0;  // dcthashindex.cpp:196-200: no hash for needle
+  long long k = 0;
+  for (long long i = 0; i < n; ++i) {
+    int score = orc_hamm64(target, hashes[i]);
+    if (score < threshold) {
+      uint32_t id = ids[i];
+      if (id != 0) {
+        if (k < cap) {
+          out_ids[k] = id;
+          out_dist[k] = score;
+        }
+        ++k;
+      }
+    }
+  }
+  return k;
+}
+
+// all needles against all rows; triples (needle index, id, dist) in (needle, row) order.
+long long orc_dct_find_batch(const uint64_t* hashes, const uint32_t* ids, long long n, const uint64_t* needles,
+                             long long nq, int threshold, int threads, int* out_q, uint32_t* out_ids,
+                             int* out_dist, long long cap, double* elapsed_ms) {
+  if (threads < 1) threads = 1;
+  std::vector<std::vector<int>> q(threads), d(threads);
+  std::vector<std::vector<uint32_t>> id(threads);
+  std::vector<long long> counts(threads, 0);
+  const bool keep = out_q != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int w) {
+    long long lo = nq * w / threads, hi = nq * (w + 1) / threads;
+    for (long long i = lo; i < hi; ++i) {
+      const uint64_t target = needles[i];
+      if (!target) continue;
+      for (long long j = 0; j < n; ++j) {
+        int score = __builtin_popcountll(target ^ hashes[j]);
+        if (__builtin_expect(score < threshold, 0) && ids[j] != 0) {
+          counts[w]++;
+          if (keep) {
+            q[w].push_back((int)i);
+            id[w].push_back(ids[j]);
+            d[w].push_back(score);
+          }
+        }
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < threads; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& th : pool) th.join();
+  auto t1 = std::chrono::steady_clock::now();
+  if (elapsed_ms) *elapsed_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  long long total = 0, pos = 0;
+  for (int w = 0; w < threads; ++w) {
+    total += counts[w];
+    if (keep)
+      for (size_t k = 0; k < q[w].size() && pos < cap; ++k, ++pos) {
+        out_q[pos] = q[w][k];
+        out_ids[pos] = id[w][k];
+        out_dist[pos] = d[w][k];
+      }
+  }
+  return total;
+}
+
+// Database::searchIndex post-processing — src/database.cpp:1729-1737: sort by score, drop the needle
+// itself when filterSelf, stop at maxMatches.  The reference's std::sort is unstable, so ties are
+// implementation-defined; the contract orders ties by mediaId ascending.
+int orc_search_index_post(uint32_t* ids, int* scores, int n, uint32_t needle_id, int filter_self, int max_matches) {
+  std::vector<std::pair<int, uint32_t>> v(n);
+  for (int i = 0; i < n; ++i) v[i] = {scores[i], ids[i]};
+  std::sort(v.begin(), v.end());
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    if (filter_self && v[i].second == needle_id) continue;
+    if (k >= max_matches) break;
+    ids[k] = v[i].second;
+    scores[k] = v[i].first;
+    ++k;
+  }
+  return k;
+}
+
+}  // extern "C"

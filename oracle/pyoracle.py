@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes loaders for the parity checkers under oracle/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package (cbird_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def build():
+    """compile the restatement (always) and the reference headers (only where /root/reference exists)."""
+    subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(_HERE, "libcbird_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_hamm64.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_zigzag81.argtypes = [_i32p]
+        L.orc_dct_basis.argtypes = [_f32p]
+        L.orc_preprocess32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_hash_from_tile32.argtypes = [_u8p, C.c_void_p, C.c_void_p]
+        L.orc_hash_from_tile32.restype = C.c_uint64
+        L.orc_dct_hash64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_dct_hash64.restype = C.c_uint64
+        L.orc_dct_hash64_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong, _u64p, C.c_int]
+        L.orc_dct_hash64_batch.restype = C.c_double
+        L.orc_dct_find.argtypes = [_u64p, _u32p, C.c_longlong, C.c_uint64, C.c_int, _u32p, _i32p, C.c_longlong]
+        L.orc_dct_find.restype = C.c_longlong
+        L.orc_dct_find_batch.argtypes = [_u64p, _u32p, C.c_longlong, _u64p, C.c_longlong, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+        L.orc_dct_find_batch.restype = C.c_longlong
+        L.orc_search_index_post.argtypes = [_u32p, _i32p, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        _oracle = L
+    return _oracle
+
+
+def ref():
+    """the reference's own vptree.h / radix.h, compiled unmodified (oracle/ref_trees.cpp)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libcbird_ref.so")
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_hamm64.argtypes = [C.c_uint64, C.c_uint64]
+        L.ref_dcttree_create.argtypes = [_u64p, _u32p, C.c_int]
+        L.ref_dcttree_create.restype = C.c_void_p
+        L.ref_dcttree_destroy.argtypes = [C.c_void_p]
+        L.ref_dcttree_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, _u32p, _i32p, C.c_int]
+        L.ref_dcttree_search_batch.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+        L.ref_dcttree_search_batch.restype = C.c_longlong
+        L.ref_radix_create.argtypes = [C.c_uint]
+        L.ref_radix_create.restype = C.c_void_p
+        L.ref_radix_destroy.argtypes = [C.c_void_p]
+        L.ref_radix_index_of.argtypes = [C.c_void_p, C.c_uint64]
+        L.ref_radix_index_of.restype = C.c_ulonglong
+        L.ref_radix_insert.argtypes = [C.c_void_p, _u32p, _i32p, _u64p, C.c_int]
+        L.ref_radix_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, _u32p, _i32p, _u64p, _i32p, C.c_int]
+        L.ref_radix_search_batch_count.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.ref_radix_search_batch_count.restype = C.c_longlong
+        _ref = L
+    return _ref
+
+
+# ---- convenience wrappers -------------------------------------------------------------------------
+
+def dct_hash64(img: np.ndarray) -> int:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    return int(oracle().orc_dct_hash64(img.ctypes.data, w, h, img.strides[0]))
+
+
+def preprocess32(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros((32, 32), np.uint8)
+    rc = oracle().orc_preprocess32(img.ctypes.data, w, h, img.strides[0], out)
+    if rc != 0:
+        raise ValueError("unsupported geometry %dx%d" % (w, h))
+    return out
+
+
+def dct_hash64_batch(frames: np.ndarray, threads=1):
+    """frames: (n, h, w) u8 contiguous -> (hashes u64[n], elapsed ms)"""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, h, w = frames.shape
+    out = np.zeros(n, np.uint64)
+    ms = oracle().orc_dct_hash64_batch(frames.ctypes.data, n, w, h, w, w * h, out, threads)
+    return out, ms
+
+
+def dct_find_batch(hashes, ids, needles, threshold, threads=1, keep=True):
+    """brute radius search -> (q, id, dist) int64 array sorted canonically, total, ms"""
+    hashes = np.ascontiguousarray(hashes, np.uint64)
+    ids = np.ascontiguousarray(ids, np.uint32)
+    needles = np.ascontiguousarray(needles, np.uint64)
+    ms = C.c_double(0)
+    L = oracle()
+    total = L.orc_dct_find_batch(hashes, ids, len(hashes), needles, len(needles), threshold, threads,
+                                 None, None, None, 0, C.byref(ms))
+    if not keep:
+        return None, total, ms.value
+    q = np.zeros(total, np.int32)
+    i = np.zeros(total, np.uint32)
+    d = np.zeros(total, np.int32)
+    L.orc_dct_find_batch(hashes, ids, len(hashes), needles, len(needles), threshold, threads,
+                         q.ctypes.data, i.ctypes.data, d.ctypes.data, total, C.byref(ms))
+    return canonical(q, i, d), total, ms.value
+
+
+def ref_dcttree_find_batch(hashes, ids, needles, threshold, threads=1, keep=True):
+    """the reference's VpTree (what DctHashIndex ships) -> canonical triples, total, search ms"""
+    L = ref()
+    hashes = np.ascontiguousarray(hashes, np.uint64)
+    ids = np.ascontiguousarray(ids, np.uint32)
+    needles = np.ascontiguousarray(needles, np.uint64)
+    t = L.ref_dcttree_create(hashes, ids, len(hashes))
+    try:
+        ms = C.c_double(0)
+        total = L.ref_dcttree_search_batch(t, needles, len(needles), threshold, threads, None, None, None, 0, C.byref(ms))
+        if not keep:
+            return None, total, ms.value
+        q = np.zeros(total, np.int32)
+        i = np.zeros(total, np.uint32)
+        d = np.zeros(total, np.int32)
+        L.ref_dcttree_search_batch(t, needles, len(needles), threshold, threads, q.ctypes.data, i.ctypes.data,
+                                   d.ctypes.data, total, C.byref(ms))
+        return canonical(q, i, d), total, ms.value
+    finally:
+        L.ref_dcttree_destroy(t)
+
+
+def canonical(q, ids, dist):
+    """sorted (needle, id, dist) rows: the multiset form parity is defined on."""
+    a = np.stack([np.asarray(q, np.int64), np.asarray(ids, np.int64), np.asarray(dist, np.int64)], axis=1)
+    if len(a) == 0:
+        return a.reshape(0, 3)
+    order = np.lexsort((a[:, 2], a[:, 1], a[:, 0]))
+    return a[order]
