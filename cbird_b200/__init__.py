@@ -1,0 +1,7 @@
+"""cbird_b200 — B200-native (sm_100a) hot path of cbird behind cbird's Index plugin surface.
+
+The compute lives in libcbird_b200.so (CUDA, C ABI: include/cbird_b200.h); this package is the thin
+host-side mirror of the reference interface.  Importing the package never touches oracle/.
+"""
+from ._lib import CbirdError, LIB_PATH, lib  # noqa: F401
+from .index import DctHashIndex, Match, MatchRange, Media, SearchParams  # noqa: F401

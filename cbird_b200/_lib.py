@@ -1,0 +1,105 @@
+"""ctypes binding of libcbird_b200.so (include/cbird_b200.h). Fails loudly when the CUDA library is
+missing or a call fails: there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcbird_b200.so")
+
+
+class CbirdError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("cbird_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+class cb_match(C.Structure):
+    _fields_ = [("mediaId", C.c_uint32), ("score", C.c_int32), ("srcIn", C.c_int32), ("dstIn", C.c_int32),
+                ("len", C.c_int32)]
+
+
+class cb_params(C.Structure):
+    _fields_ = [("algo", C.c_int32), ("dctThresh", C.c_int32), ("cvThresh", C.c_int32), ("minMatches", C.c_int32),
+                ("maxMatches", C.c_int32), ("skipFrames", C.c_int32), ("minFramesMatched", C.c_int32),
+                ("minFramesNear", C.c_int32), ("videoRadix", C.c_int32), ("maxThresh", C.c_int32),
+                ("filterSelf", C.c_uint8), ("verbose", C.c_uint8), ("pad_", C.c_uint8 * 2), ("target", C.c_uint32)]
+
+
+class cb_stats(C.Structure):
+    _fields_ = [("comparisons", C.c_uint64), ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("frames_hashed", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+HIT_DTYPE = np.dtype([("needle", np.uint32), ("mediaId", np.uint32), ("score", np.int32)])
+PAIR_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("dist", np.uint32), ("pad", np.uint32)])
+MATCH_DTYPE = np.dtype([("mediaId", np.uint32), ("score", np.int32), ("srcIn", np.int32), ("dstIn", np.int32),
+                        ("len", np.int32)])
+
+_lib = None
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); also the list the CPU test checks against include/cbird_b200.h
+SIGNATURES = {
+    "cb_version": (C.c_char_p, []),
+    "cb_last_error": (C.c_char_p, []),
+    "cb_set_device": (C.c_int, [C.c_int]),
+    "cb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cb_params_default": (None, [C.POINTER(cb_params)]),
+    "cb_stats_get": (C.c_int, [C.POINTER(cb_stats)]),
+    "cb_stats_reset": (None, []),
+    "cb_free": (None, [_vp]),
+    "cb_scan64_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
+    "cb_scan64_variant": (C.c_int, [C.c_int]),
+    "cb_scan64_force_variant": (None, [C.c_int]),
+    "cb_dct_index_create": (_vp, []),
+    "cb_dct_index_destroy": (None, [_vp]),
+    "cb_dct_index_load": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "cb_dct_index_is_loaded": (C.c_int, [_vp]),
+    "cb_dct_index_count": (_i64, [_vp]),
+    "cb_dct_index_memory_usage": (C.c_size_t, [_vp]),
+    "cb_dct_index_add": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "cb_dct_index_remove": (C.c_int, [_vp, _vp, _i64]),
+    "cb_dct_index_slice": (_vp, [_vp, _vp, _i64]),
+    "cb_dct_index_media_ids": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "cb_dct_index_find": (C.c_int, [_vp, C.c_uint64, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_dct_index_find_batch_alloc": (C.c_int, [_vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_dct_index_similar_alloc": (C.c_int, [_vp, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_dct_index_similar_shard_alloc": (C.c_int, [_vp, C.POINTER(cb_params), _i64, _i64, C.POINTER(_vp), C.POINTER(_i64)]),
+}
+
+
+def lib():
+    """the loaded shared library; raises if it was not built (python -m cbird_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CbirdError(-1, "%s is missing: build it with `python -m cbird_b200.build` "
+                                 "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise CbirdError(status, lib().cb_last_error().decode("utf-8", "replace"))
+
+
+def take_array(ptr, n, dtype):
+    """copy a library-allocated array into numpy and release it with cb_free."""
+    try:
+        if n == 0 or not ptr:
+            return np.zeros(0, dtype)
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    finally:
+        if ptr:
+            lib().cb_free(ptr)

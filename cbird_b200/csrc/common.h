@@ -1,0 +1,82 @@
+// Shared host-side plumbing of libcbird_b200: status codes, thread-local error text, counters,
+// RAII device buffers.  Product code — must not include anything from oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cbird_b200.h"
+
+namespace cbird {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int current_device();          // device selected by cb_set_device on this thread (default 0)
+int ensure_device();           // CB_OK or CB_ERR_NO_DEVICE; also cudaSetDevice(current_device())
+
+struct Counters {
+  std::atomic<uint64_t> comparisons{0}, hits{0}, launches{0}, frames{0};
+  std::atomic<uint64_t> kernel_us{0};
+};
+Counters& counters();
+
+#define CB_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return ::cbird::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// growable device buffer (never shrinks); not thread-safe, owners lock.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int dev = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  int reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return CB_OK;
+    size_t ncap = cap ? cap : 1024;
+    while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+    T* q = nullptr;
+    CB_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+    if (keep && p && cap) {
+      cudaError_t e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return cuda_fail(e, "DevBuf grow copy", __FILE__, __LINE__);
+      }
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return CB_OK;
+  }
+};
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+struct Scan64Launch {
+  const uint64_t* a;
+  uint32_t n_a;
+  const uint64_t* b;
+  uint32_t n_b;
+  int threshold;
+  int radix_bits;
+  cb_pair* out;
+  unsigned long long cap;
+  unsigned long long* count;
+};
+int scan64_launch(const Scan64Launch& L, cudaStream_t stream);
+int scan64_variant_for(int threshold);
+
+}  // namespace cbird

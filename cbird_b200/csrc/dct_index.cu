@@ -1,0 +1,418 @@
+// DctHashIndex on the device: host-side mirror of src/dcthashindex.{h,cpp} behind the C ABI.
+//
+// The reference keeps flat arrays (uint64 hashes[], uint32 ids[]) plus a VP tree that is rebuilt on
+// every add/remove (dcthashindex.cpp:61-68,158-191).  Here the flat arrays are the whole index: they
+// are mirrored in HBM and every search is a brute-force scan (scan64.cu), so add() is an append and
+// remove() a row rewrite.  Results are exact radius sets, like the VP tree's.
+#include <cub/device/device_merge_sort.cuh>
+
+#include <algorithm>
+#include <unordered_set>
+
+#include "common.h"
+
+namespace cbird {
+
+namespace {
+
+// raw scan hits -> (needle, mediaId, score); rows with id 0 (removed, dcthashindex.cpp:183-186) are
+// dropped like the reference's brute path does (:211-216), and so is the needle itself when asked.
+// swap: the scan ran with A = index rows, B = needles.
+__global__ void hits_to_matches(const cb_pair* __restrict__ pairs, unsigned long long n, int swapped,
+                                const uint32_t* __restrict__ row_ids, uint32_t row_offset,
+                                const uint32_t* __restrict__ needle_ids, uint32_t needle_offset, cb_hit* out,
+                                unsigned long long* n_valid) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cb_pair p = pairs[i];
+  const uint32_t needle = swapped ? p.b : p.a;
+  const uint32_t row = swapped ? p.a : p.b;
+  const uint32_t id = row_ids[row + row_offset];
+  bool keep = id != 0;
+  if (keep && needle_ids && needle_ids[needle + needle_offset] == id) keep = false;
+  cb_hit h;
+  h.needle = keep ? needle + needle_offset : 0xFFFFFFFFu;
+  h.mediaId = id;
+  h.score = int32_t(p.dist);
+  out[i] = h;
+  if (keep) atomicAdd(n_valid, 1ull);
+}
+
+struct HitLess {
+  __device__ __forceinline__ bool operator()(const cb_hit& x, const cb_hit& y) const {
+    if (x.needle != y.needle) return x.needle < y.needle;
+    if (x.score != y.score) return x.score < y.score;
+    return x.mediaId < y.mediaId;
+  }
+};
+
+}  // namespace
+
+struct DctIndex {
+  std::vector<uint64_t> hashes;  // _hashes   (dcthashindex.h)
+  std::vector<uint32_t> ids;     // _mediaId
+  bool loaded = false;
+  int device = 0;
+
+  std::mutex mu;  // find() is called from many host threads (database.cpp:1400,1698)
+  cudaStream_t stream = nullptr;
+  DevBuf<uint64_t> d_hashes;
+  DevBuf<uint32_t> d_ids;
+  size_t d_rows = 0;  // rows valid on the device
+  bool dirty = true;
+  DevBuf<uint64_t> d_needles;
+  DevBuf<cb_pair> d_pairs;
+  DevBuf<cb_hit> d_hits;
+  DevBuf<unsigned char> d_temp;
+  DevBuf<unsigned long long> d_counts;  // [0] scan count, [1] valid count
+  unsigned long long* h_counts = nullptr;  // pinned
+
+  ~DctIndex() {
+    if (h_counts) cudaFreeHost(h_counts);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int init_device() {
+    int rc = ensure_device();
+    if (rc != CB_OK) return rc;
+    device = current_device();
+    if (!stream) CB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!h_counts) CB_CUDA(cudaMallocHost(&h_counts, 2 * sizeof(unsigned long long)));
+    rc = d_counts.reserve(2);
+    return rc;
+  }
+
+  int sync_to_device() {
+    CB_CUDA(cudaSetDevice(device));
+    if (!dirty) return CB_OK;
+    const size_t n = hashes.size();
+    int rc = d_hashes.reserve(n + 2);
+    if (rc == CB_OK) rc = d_ids.reserve(n + 2);
+    if (rc != CB_OK) return rc;
+    if (n) {
+      CB_CUDA(cudaMemcpyAsync(d_hashes.p, hashes.data(), n * 8, cudaMemcpyHostToDevice, stream));
+      CB_CUDA(cudaMemcpyAsync(d_ids.p, ids.data(), n * 4, cudaMemcpyHostToDevice, stream));
+    }
+    d_rows = n;
+    dirty = false;
+    return CB_OK;
+  }
+
+  // Runs the scan of `needles` (device, n_q) against rows [row_begin,row_end) and leaves sorted,
+  // filtered cb_hit records in d_hits; *n_valid_out = number of leading valid records.
+  int search_device(const uint64_t* d_q, uint32_t n_q, uint32_t row_begin, uint32_t row_end, int threshold,
+                    const uint32_t* d_needle_ids, uint32_t needle_offset, unsigned long long* n_valid_out) {
+    *n_valid_out = 0;
+    const uint32_t n_rows = row_end - row_begin;
+    if (!n_q || !n_rows || threshold <= 0) return CB_OK;
+    // the register side of the scan wants the long array
+    const bool swapped = n_q < n_rows;
+    unsigned long long cap = d_pairs.cap ? d_pairs.cap : (1ull << 20);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      int rc = d_pairs.reserve(cap);
+      if (rc != CB_OK) return rc;
+      cap = d_pairs.cap;
+      CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 2 * sizeof(unsigned long long), stream));
+      Scan64Launch L;
+      if (swapped) {
+        L = Scan64Launch{d_hashes.p + row_begin, n_rows, d_q, n_q, threshold, 0, d_pairs.p, cap, d_counts.p};
+      } else {
+        L = Scan64Launch{d_q, n_q, d_hashes.p + row_begin, n_rows, threshold, 0, d_pairs.p, cap, d_counts.p};
+      }
+      rc = scan64_launch(L, stream);
+      if (rc != CB_OK) return rc;
+      CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaStreamSynchronize(stream));
+      if (h_counts[0] <= cap) break;
+      cap = h_counts[0] + h_counts[0] / 8 + 1024;  // overflow: exact size is known now, run again
+      if (attempt == 2) {
+        set_error("scan64: hit list overflow persisted");
+        return CB_ERR_CUDA;
+      }
+    }
+    const unsigned long long n_hits = h_counts[0];
+    counters().hits += n_hits;
+    if (!n_hits) return CB_OK;
+    int rc = d_hits.reserve(n_hits);
+    if (rc != CB_OK) return rc;
+    const unsigned blocks = unsigned((n_hits + 255) / 256);
+    hits_to_matches<<<blocks, 256, 0, stream>>>(d_pairs.p, n_hits, swapped ? 1 : 0, d_ids.p, row_begin, d_needle_ids,
+                                                needle_offset, d_hits.p, d_counts.p + 1);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+    size_t temp_bytes = 0;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)nullptr, temp_bytes, d_hits.p, (long long)n_hits, HitLess(), stream));
+    rc = d_temp.reserve(temp_bytes + 16);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)d_temp.p, temp_bytes, d_hits.p, (long long)n_hits, HitLess(), stream));
+    CB_CUDA(cudaMemcpyAsync(h_counts + 1, d_counts.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    *n_valid_out = h_counts[1];
+    return CB_OK;
+  }
+};
+
+}  // namespace cbird
+
+using namespace cbird;
+
+struct cb_dct_index {
+  DctIndex impl;
+};
+
+extern "C" {
+
+cb_dct_index* cb_dct_index_create(void) { return new (std::nothrow) cb_dct_index; }
+
+void cb_dct_index_destroy(cb_dct_index* ix) {
+  if (!ix) return;
+  if (ix->impl.stream) cudaSetDevice(ix->impl.device);
+  delete ix;
+}
+
+int cb_dct_index_load(cb_dct_index* ix, const uint32_t* ids, const uint64_t* hashes, int64_t n) {
+  if (!ix || n < 0 || (n > 0 && (!ids || !hashes))) {
+    set_error("cb_dct_index_load: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  if (n > 0xFFFFF000ll) {
+    set_error("cb_dct_index_load: %lld rows exceed the 32-bit row index", (long long)n);
+    return CB_ERR_UNSUPPORTED;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  int rc = I.init_device();
+  if (rc != CB_OK) return rc;
+  I.hashes.assign(hashes, hashes + n);
+  I.ids.assign(ids, ids + n);
+  I.loaded = true;
+  I.dirty = true;
+  return I.sync_to_device();
+}
+
+int cb_dct_index_is_loaded(const cb_dct_index* ix) { return ix && ix->impl.loaded ? 1 : 0; }
+int64_t cb_dct_index_count(const cb_dct_index* ix) { return ix ? int64_t(ix->impl.hashes.size()) : 0; }
+size_t cb_dct_index_memory_usage(const cb_dct_index* ix) {
+  return ix ? (sizeof(uint64_t) + sizeof(uint32_t)) * ix->impl.hashes.size() : 0;
+}
+
+int cb_dct_index_add(cb_dct_index* ix, const uint32_t* ids, const uint64_t* hashes, int64_t n) {
+  if (!ix || n < 0 || (n > 0 && (!ids || !hashes))) {
+    set_error("cb_dct_index_add: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (!I.loaded) {
+    set_error("cb_dct_index_add: index is not loaded (src/index.h:234 makes this an error)");
+    return CB_ERR_NOT_LOADED;
+  }
+  I.hashes.insert(I.hashes.end(), hashes, hashes + n);
+  I.ids.insert(I.ids.end(), ids, ids + n);
+  I.dirty = true;
+  return I.sync_to_device();
+}
+
+int cb_dct_index_remove(cb_dct_index* ix, const int32_t* ids, int64_t n) {
+  if (!ix || n < 0 || (n > 0 && !ids)) {
+    set_error("cb_dct_index_remove: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (!I.loaded) return CB_OK;  // dcthashindex.cpp:176
+  std::unordered_set<int32_t> gone(ids, ids + n);
+  for (size_t i = 0; i < I.ids.size(); ++i)
+    if (gone.count(int32_t(I.ids[i]))) {  // nullify rather than compact, :183-186
+      I.ids[i] = 0;
+      I.hashes[i] = 0;
+    }
+  I.dirty = true;
+  return I.sync_to_device();
+}
+
+cb_dct_index* cb_dct_index_slice(const cb_dct_index* ix, const uint32_t* ids, int64_t n) {
+  if (!ix || n < 0 || (n > 0 && !ids)) return nullptr;
+  const DctIndex& S = ix->impl;
+  cb_dct_index* out = new (std::nothrow) cb_dct_index;
+  if (!out) return nullptr;
+  std::unordered_set<uint32_t> want(ids, ids + n);
+  DctIndex& I = out->impl;
+  for (size_t i = 0; i < S.ids.size(); ++i)
+    if (want.count(S.ids[i])) {  // dcthashindex.cpp:232-239, row order preserved
+      I.hashes.push_back(S.hashes[i]);
+      I.ids.push_back(S.ids[i]);
+    }
+  I.loaded = true;
+  I.dirty = true;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (I.init_device() != CB_OK || I.sync_to_device() != CB_OK) {
+    delete out;
+    return nullptr;
+  }
+  return out;
+}
+
+int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, int64_t* n_out) {
+  if (!ix || !n_out) return CB_ERR_INVALID;
+  const DctIndex& I = ix->impl;
+  int64_t k = 0;
+  for (size_t i = 0; i < I.ids.size(); ++i)
+    if (I.hashes[i] != 0) {
+      if (out && k < cap) out[k] = I.ids[i];
+      ++k;
+    }
+  *n_out = k;
+  return (out && k > cap) ? CB_ERR_CAPACITY : CB_OK;
+}
+
+static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int threshold, int64_t row_begin,
+                          int64_t row_end, bool self_needles, bool filter_self, std::vector<cb_hit>& out) {
+  out.clear();
+  if (!I.loaded) {
+    set_error("index not loaded");
+    return CB_ERR_NOT_LOADED;
+  }
+  CB_CUDA(cudaSetDevice(I.device));
+  int rc = I.sync_to_device();
+  if (rc != CB_OK) return rc;
+  const uint64_t* d_q = nullptr;
+  if (self_needles) {
+    d_q = I.d_hashes.p;
+    nq = int64_t(I.d_rows);
+  } else {
+    rc = I.d_needles.reserve(size_t(nq) + 2);
+    if (rc != CB_OK) return rc;
+    if (nq) CB_CUDA(cudaMemcpyAsync(I.d_needles.p, needles, size_t(nq) * 8, cudaMemcpyHostToDevice, I.stream));
+    d_q = I.d_needles.p;
+  }
+  unsigned long long n_valid = 0;
+  rc = I.search_device(d_q, uint32_t(nq), uint32_t(row_begin), uint32_t(row_end), threshold,
+                       (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid);
+  if (rc != CB_OK) return rc;
+  out.resize(n_valid);
+  if (n_valid) {
+    CB_CUDA(cudaMemcpyAsync(out.data(), I.d_hits.p, n_valid * sizeof(cb_hit), cudaMemcpyDeviceToHost, I.stream));
+    CB_CUDA(cudaStreamSynchronize(I.stream));
+  }
+  return CB_OK;
+}
+
+int cb_dct_index_find(cb_dct_index* ix, uint64_t needle_hash, const cb_params* p, cb_match* out, int64_t cap,
+                      int64_t* n_out) {
+  if (!ix || !p || !n_out) {
+    set_error("cb_dct_index_find: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  *n_out = 0;
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (needle_hash == 0) return CB_OK;                // "no hash for needle", dcthashindex.cpp:196-200
+  if (I.loaded && I.hashes.empty()) return CB_OK;    // "empty/null tree", :202-205
+  std::vector<cb_hit> hits;
+  int rc = run_find_batch(I, &needle_hash, 1, p->dctThresh, 0, int64_t(I.hashes.size()), false, false, hits);
+  if (rc != CB_OK) return rc;
+  *n_out = int64_t(hits.size());
+  for (size_t i = 0; i < hits.size() && int64_t(i) < cap; ++i) {
+    out[i].mediaId = hits[i].mediaId;
+    out[i].score = hits[i].score;
+    out[i].srcIn = -1;
+    out[i].dstIn = -1;
+    out[i].len = 0;
+  }
+  return (int64_t(hits.size()) > cap) ? CB_ERR_CAPACITY : CB_OK;
+}
+
+static int export_hits(const std::vector<cb_hit>& hits, cb_hit** out, int64_t* n_out) {
+  *n_out = int64_t(hits.size());
+  *out = static_cast<cb_hit*>(malloc(std::max<size_t>(1, hits.size()) * sizeof(cb_hit)));
+  if (!*out) {
+    set_error("out of host memory");
+    return CB_ERR_INVALID;
+  }
+  if (!hits.empty()) memcpy(*out, hits.data(), hits.size() * sizeof(cb_hit));
+  return CB_OK;
+}
+
+int cb_dct_index_find_batch_alloc(cb_dct_index* ix, const uint64_t* needle_hashes, int64_t n_needles,
+                                  const cb_params* p, cb_hit** out, int64_t* n_out) {
+  if (!ix || !p || !out || !n_out || n_needles < 0 || (n_needles && !needle_hashes)) {
+    set_error("cb_dct_index_find_batch_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  std::vector<cb_hit> hits;
+  int rc = run_find_batch(I, needle_hashes, n_needles, p->dctThresh, 0, int64_t(I.hashes.size()), false, false, hits);
+  if (rc != CB_OK) return rc;
+  // a needle without hash finds nothing (dcthashindex.cpp:196-200)
+  hits.erase(std::remove_if(hits.begin(), hits.end(), [&](const cb_hit& h) { return needle_hashes[h.needle] == 0; }),
+             hits.end());
+  return export_hits(hits, out, n_out);
+}
+
+int cb_dct_index_similar_shard_alloc(cb_dct_index* ix, const cb_params* p, int64_t row_begin, int64_t row_end,
+                                     cb_hit** hits_out, int64_t* n_hits_out) {
+  if (!ix || !p || !hits_out || !n_hits_out) {
+    set_error("cb_dct_index_similar_shard_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  const int64_t n = int64_t(I.hashes.size());
+  if (row_begin < 0 || row_end > n || row_begin > row_end) {
+    set_error("shard rows [%lld,%lld) outside [0,%lld)", (long long)row_begin, (long long)row_end, (long long)n);
+    return CB_ERR_INVALID;
+  }
+  std::vector<cb_hit> hits;
+  int rc = run_find_batch(I, nullptr, 0, p->dctThresh, row_begin, row_end, true, false, hits);
+  if (rc != CB_OK) return rc;
+  hits.erase(std::remove_if(hits.begin(), hits.end(), [&](const cb_hit& h) { return I.hashes[h.needle] == 0; }),
+             hits.end());
+  return export_hits(hits, hits_out, n_hits_out);
+}
+
+int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** offsets_out, cb_hit** hits_out,
+                               int64_t* n_hits_out) {
+  if (!ix || !p || !offsets_out || !hits_out || !n_hits_out) {
+    set_error("cb_dct_index_similar_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  DctIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  const int64_t n = int64_t(I.hashes.size());
+  std::vector<cb_hit> hits;
+  int rc = run_find_batch(I, nullptr, 0, p->dctThresh, 0, n, true, p->filterSelf != 0, hits);
+  if (rc != CB_OK) return rc;
+  // searchIndex post step (database.cpp:1729-1737): hits are already sorted by (needle, score, id);
+  // cut every needle's list at maxMatches. Needles without hash find nothing.
+  int64_t* offsets = static_cast<int64_t*>(malloc(size_t(n + 1) * sizeof(int64_t)));
+  if (!offsets) {
+    set_error("out of host memory");
+    return CB_ERR_INVALID;
+  }
+  const int64_t max_matches = p->maxMatches < 0 ? 0 : p->maxMatches;
+  size_t w = 0, i = 0;
+  for (int64_t row = 0; row < n; ++row) {
+    offsets[row] = int64_t(w);
+    int64_t kept = 0;
+    while (i < hits.size() && int64_t(hits[i].needle) == row) {
+      if (kept < max_matches && I.hashes[row] != 0) {
+        hits[w++] = hits[i];
+        ++kept;
+      }
+      ++i;
+    }
+  }
+  offsets[n] = int64_t(w);
+  hits.resize(w);
+  rc = export_hits(hits, hits_out, n_hits_out);
+  if (rc != CB_OK) {
+    free(offsets);
+    return rc;
+  }
+  *offsets_out = offsets;
+  return CB_OK;
+}
+
+}  // extern "C"

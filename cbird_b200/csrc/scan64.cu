@@ -1,0 +1,242 @@
+// Kernel (b): brute-force 64-bit Hamming radius scan for sm_100a.
+//
+// Replaces the per-needle tree walks of cbird (VpTree::thresholdSearch src/tree/vptree.h:228-255,
+// RadixMap_t::search src/tree/radix.h:187-210) whose primitive is hamm64 (src/hamm.h:24-26) with one
+// dense pass over the A x B pair grid:
+//
+//   * "A side" lives in registers: every thread owns R=8 hashes (16 x b32), a CTA of 256 threads
+//     owns a block of 2048 A rows;
+//   * "B side" is streamed through shared memory in tiles of 2048 hashes (16 KB); all lanes of a warp
+//     read the same address, so one broadcast LDS.128 feeds 2 B rows x 8 A rows = 16 pair tests/lane;
+//   * the integer pipes bound the kernel (measured on B200: POPC 16, LOP3 64 lanes/clk/SM), so the
+//     inner loop is built to minimise POPC issue:
+//        variant 0  exact      popc(lo)+popc(hi) per pair                       2   POPC / pair
+//        variant 1  OR-fold    popc((alo^blo)|(ahi^bhi))      <= distance       1   POPC / pair
+//        variant 2  AND-fold   popc(((alo^b0lo)&(alo^b1lo)) | ((ahi^b0hi)&(ahi^b1hi)))
+//                              <= min(distance to b0, distance to b1)           0.5 POPC / pair
+//     Variants 1 and 2 are LOWER BOUNDS of the distance, so "bound < T" is a necessary condition; the
+//     rare survivors are re-tested exactly (2 POPC) before anything is emitted.  All three variants
+//     therefore emit the identical, exact hit set.  The dispatcher picks the cheapest variant whose
+//     false-positive rate on uniformly random hashes stays negligible for the threshold asked.
+//   * hits are rare: they are appended to a global list with one atomicAdd each; the total is always
+//     counted so the host can detect overflow and re-run with a larger list.
+//
+// Roles are symmetric, so the same kernel serves all-pairs `-similar` (A = B = the index), a few
+// needles against a big index (A = index rows, B = needles) and the radix-bucket filtered video
+// search (extra predicate on the bucket bits, src/tree/radix.h:135-141).
+#include "common.h"
+
+namespace cbird {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kR = 8;                    // A rows per thread
+constexpr int kABlock = kThreads * kR;   // 2048 A rows per CTA
+constexpr int kBTile = 2048;             // B rows per shared-memory tile (16 KB)
+constexpr uint64_t kPadHash = 0xAAAAAAAAAAAAAAAAull;
+
+struct ScanParams {
+  const uint64_t* __restrict__ a;
+  const uint64_t* __restrict__ b;
+  uint32_t n_a, n_b;
+  uint32_t slab;        // B rows per blockIdx.y, multiple of kBTile
+  int threshold;
+  uint32_t radix_mask;  // bucket bits of (h >> 1); 0 = no bucket predicate
+  cb_pair* out;
+  unsigned long long cap;
+  unsigned long long* count;
+};
+
+__device__ __forceinline__ void emit_exact(const ScanParams& P, uint32_t alo, uint32_t ahi, uint32_t blo,
+                                           uint32_t bhi, uint32_t ai, uint32_t bi) {
+  const uint32_t xlo = alo ^ blo;
+  const int d = __popc(xlo) + __popc(ahi ^ bhi);
+  if (d < P.threshold && ai < P.n_a && bi < P.n_b && ((xlo >> 1) & P.radix_mask) == 0) {
+    const unsigned long long pos = atomicAdd(P.count, 1ull);
+    if (pos < P.cap) {
+      uint4 rec = make_uint4(ai, bi, uint32_t(d), 0u);
+      *reinterpret_cast<uint4*>(P.out + pos) = rec;
+    }
+  }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P) {
+  __shared__ uint4 tile[kBTile / 2];
+
+  uint32_t alo[kR], ahi[kR];
+  const uint32_t a_base = blockIdx.x * kABlock + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const uint32_t ai = a_base + r * kThreads;
+    const uint64_t v = ai < P.n_a ? P.a[ai] : ~kPadHash;
+    alo[r] = uint32_t(v);
+    ahi[r] = uint32_t(v >> 32);
+  }
+
+  const int T = P.threshold;
+  const uint32_t slab_begin = blockIdx.y * P.slab;
+  const uint32_t slab_end = min(slab_begin + P.slab, P.n_b);
+
+  for (uint32_t t0 = slab_begin; t0 < slab_end; t0 += kBTile) {
+    __syncthreads();
+    {
+      uint64_t* t64 = reinterpret_cast<uint64_t*>(tile);
+#pragma unroll
+      for (int i = 0; i < kBTile / kThreads; ++i) {
+        const uint32_t k = threadIdx.x + i * kThreads;
+        const uint32_t bi = t0 + k;
+        t64[k] = bi < slab_end ? P.b[bi] : kPadHash;
+      }
+    }
+    __syncthreads();
+    const int pairs = (min(uint32_t(kBTile), slab_end - t0) + 1) >> 1;
+
+#pragma unroll 2
+    for (int j = 0; j < pairs; ++j) {
+      const uint4 d = tile[j];
+      if (VARIANT == 2) {
+        uint32_t p[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const uint32_t w = ((alo[r] ^ d.x) & (alo[r] ^ d.z)) | ((ahi[r] ^ d.y) & (ahi[r] ^ d.w));
+          p[r] = __popc(w);
+        }
+        uint32_t mn = p[0];
+#pragma unroll
+        for (int r = 1; r < kR; ++r) mn = min(mn, p[r]);
+        if (int(mn) < T) {
+          const uint32_t bi = t0 + 2 * j;
+#pragma unroll
+          for (int r = 0; r < kR; ++r)
+            if (int(p[r]) < T) {
+              const uint32_t ai = a_base + r * kThreads;
+              emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
+              emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+            }
+        }
+      } else if (VARIANT == 1) {
+        uint32_t p0[kR], p1[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          p0[r] = __popc((alo[r] ^ d.x) | (ahi[r] ^ d.y));
+          p1[r] = __popc((alo[r] ^ d.z) | (ahi[r] ^ d.w));
+        }
+        uint32_t mn = min(p0[0], p1[0]);
+#pragma unroll
+        for (int r = 1; r < kR; ++r) mn = min(mn, min(p0[r], p1[r]));
+        if (int(mn) < T) {
+          const uint32_t bi = t0 + 2 * j;
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const uint32_t ai = a_base + r * kThreads;
+            if (int(p0[r]) < T) emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
+            if (int(p1[r]) < T) emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+          }
+        }
+      } else {
+        uint32_t p0[kR], p1[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          p0[r] = __popc(alo[r] ^ d.x) + __popc(ahi[r] ^ d.y);
+          p1[r] = __popc(alo[r] ^ d.z) + __popc(ahi[r] ^ d.w);
+        }
+        uint32_t mn = min(p0[0], p1[0]);
+#pragma unroll
+        for (int r = 1; r < kR; ++r) mn = min(mn, min(p0[r], p1[r]));
+        if (int(mn) < T) {
+          const uint32_t bi = t0 + 2 * j;
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const uint32_t ai = a_base + r * kThreads;
+            if (int(p0[r]) < T) emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
+            if (int(p1[r]) < T) emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+          }
+        }
+      }
+    }
+  }
+}
+
+std::atomic<int> g_forced_variant{-1};
+
+}  // namespace
+
+// Variant choice by threshold. The bound of variant 2 is Binomial(32, 7/16) on random data:
+// P(bound < 5) = 1.6e-4 per pair-of-pairs (about 4 % of warp groups take the cheap recheck), but
+// 7e-4 at T=6 and rising fast; variant 1's bound is Binomial(32, 3/4): P(bound < 13) < 1e-6.
+int scan64_variant_for(int threshold) {
+  const int f = g_forced_variant.load();
+  if (f >= 0 && f <= 2) return f;
+  if (threshold <= 5) return 2;
+  if (threshold <= 13) return 1;
+  return 0;
+}
+
+int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
+  if (L.n_a == 0 || L.n_b == 0 || L.threshold <= 0) return CB_OK;  // nothing can match
+  if (!L.a || !L.b || !L.count || (!L.out && L.cap)) {
+    set_error("scan64: null pointer argument");
+    return CB_ERR_INVALID;
+  }
+  if (L.radix_bits < 0 || L.radix_bits > 24) {
+    set_error("scan64: radix_bits %d outside [0,24] (RadixMap_t clamps at 24, src/tree/radix.h:105-112)",
+              L.radix_bits);
+    return CB_ERR_INVALID;
+  }
+  ScanParams P;
+  P.a = L.a;
+  P.b = L.b;
+  P.n_a = L.n_a;
+  P.n_b = L.n_b;
+  P.threshold = L.threshold > 65 ? 65 : L.threshold;
+  P.radix_mask = L.radix_bits ? ((1u << L.radix_bits) - 1u) : 0u;
+  P.out = L.out;
+  P.cap = L.cap;
+  P.count = L.count;
+
+  const uint32_t a_blocks = (L.n_a + kABlock - 1) / kABlock;
+  const uint32_t b_tiles = (L.n_b + kBTile - 1) / kBTile;
+  // enough CTAs for ~24 waves of 148 SMs x 3 resident CTAs when the job is large, never more
+  // slabs than tiles, and gridDim.y <= 65535
+  const uint32_t target_ctas = 148u * 3u * 24u;
+  uint32_t slabs = (target_ctas + a_blocks - 1) / a_blocks;
+  if (slabs > b_tiles) slabs = b_tiles;
+  if (slabs > 65535u) slabs = 65535u;
+  if (slabs < 1) slabs = 1;
+  uint32_t tiles_per_slab = (b_tiles + slabs - 1) / slabs;
+  slabs = (b_tiles + tiles_per_slab - 1) / tiles_per_slab;
+  P.slab = tiles_per_slab * kBTile;
+
+  dim3 grid(a_blocks, slabs), block(kThreads);
+  switch (scan64_variant_for(P.threshold)) {
+    case 2: scan64_kernel<2><<<grid, block, 0, stream>>>(P); break;
+    case 1: scan64_kernel<1><<<grid, block, 0, stream>>>(P); break;
+    default: scan64_kernel<0><<<grid, block, 0, stream>>>(P); break;
+  }
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().comparisons += uint64_t(L.n_a) * uint64_t(L.n_b);
+  return CB_OK;
+}
+
+}  // namespace cbird
+
+using namespace cbird;
+
+extern "C" {
+
+int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
+                  int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, radix_bits, d_out, cap, d_count};
+  return scan64_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+int cb_scan64_variant(int threshold) { return scan64_variant_for(threshold > 65 ? 65 : threshold); }
+
+void cb_scan64_force_variant(int variant) { g_forced_variant.store(variant); }
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+"""Host-side mirror of cbird's Index plugin surface (src/index.h) over the C ABI.
+
+Same names, argument meaning and soft-error behaviour as the reference classes, so the parity tests
+read like unit/testindexbase.cpp: `SearchParams` (src/index.h:35-145), `Match` (src/index.h:157-167),
+`DctHashIndex` (src/dcthashindex.h).  Media objects are reduced to what the indexes read from them
+(src/media.h:243,253,300,417): id, type, dctHash, videoIndex, keyPointDescriptors.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import cb_params, check, lib
+
+
+class SearchParams:
+    """src/index.h:74-121 — only the fields the path reads; defaults identical (cb_params_default)."""
+    AlgoDCT, AlgoDCTFeatures, AlgoCVFeatures, AlgoColor, AlgoVideo = 0, 1, 2, 3, 4
+
+    def __init__(self, **kw):
+        self.algo = self.AlgoDCT
+        self.dctThresh = 5
+        self.cvThresh = 25
+        self.minMatches = 1
+        self.maxMatches = 5
+        self.skipFrames = 300
+        self.minFramesMatched = 30
+        self.minFramesNear = 60
+        self.videoRadix = 10
+        self.maxThresh = 0
+        self.filterSelf = True
+        self.verbose = False
+        self.target = 0
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("SearchParams has no field %r" % k)
+            setattr(self, k, v)
+
+    def to_c(self) -> cb_params:
+        p = cb_params()
+        lib().cb_params_default(C.byref(p))
+        for name in ("algo", "dctThresh", "cvThresh", "minMatches", "maxMatches", "skipFrames", "minFramesMatched",
+                     "minFramesNear", "videoRadix", "maxThresh", "target"):
+            setattr(p, name, int(getattr(self, name)))
+        p.filterSelf = 1 if self.filterSelf else 0
+        p.verbose = 1 if self.verbose else 0
+        return p
+
+
+@dataclass
+class MatchRange:  # src/media.h:62-78
+    srcIn: int = -1
+    dstIn: int = -1
+    len: int = 0
+
+
+@dataclass
+class Match:  # Index::Match, src/index.h:157-167
+    mediaId: int = 0
+    score: int = 0
+    range: MatchRange = field(default_factory=MatchRange)
+
+
+@dataclass
+class Media:
+    """the slice of src/media.h the indexes read."""
+    TypeImage, TypeVideo = 1, 2
+    id: int = 0
+    type: int = 1
+    dctHash: int = 0
+    path: str = ""
+    frames: Optional[np.ndarray] = None        # VideoIndex.frames  (src/videoindex.h:45)
+    hashes: Optional[np.ndarray] = None        # VideoIndex.hashes  (src/videoindex.h:46)
+    descriptors: Optional[np.ndarray] = None   # KeyPointDescriptors, N x 32 u8
+    matchRangeDstIn: int = -1
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _matches_from(arr) -> List[Match]:
+    return [Match(int(m["mediaId"]), int(m["score"]), MatchRange(int(m["srcIn"]), int(m["dstIn"]), int(m["len"])))
+            for m in arr]
+
+
+class DctHashIndex:
+    """Drop-in for src/dcthashindex.{h,cpp}: flat (hash, id) rows searched by exact Hamming radius."""
+
+    def __init__(self, _handle=None):
+        self._L = lib()
+        self._h = _handle if _handle is not None else self._L.cb_dct_index_create()
+        if not self._h:
+            raise _lib.CbirdError(-3, "cb_dct_index_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.cb_dct_index_destroy(h)
+
+    def id(self):
+        return SearchParams.AlgoDCT
+
+    def isLoaded(self) -> bool:
+        return bool(self._L.cb_dct_index_is_loaded(self._h))
+
+    def count(self) -> int:
+        return int(self._L.cb_dct_index_count(self._h))
+
+    def memoryUsage(self) -> int:
+        return int(self._L.cb_dct_index_memory_usage(self._h))
+
+    def load(self, ids, hashes):
+        """load(): takes the (id, phash_dct) rows the reference SELECTs (dcthashindex.cpp:89-106)."""
+        ids, hashes = _u32(ids), _u64(hashes)
+        assert len(ids) == len(hashes)
+        check(self._L.cb_dct_index_load(self._h, ids.ctypes.data, hashes.ctypes.data, len(ids)))
+
+    def save(self):
+        """no-op like the reference (dcthashindex.cpp:116-120)."""
+
+    def add(self, media: List[Media]):
+        ids = _u32([m.id for m in media])
+        hashes = _u64([m.dctHash for m in media])
+        check(self._L.cb_dct_index_add(self._h, ids.ctypes.data, hashes.ctypes.data, len(ids)))
+
+    def remove(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        check(self._L.cb_dct_index_remove(self._h, a.ctypes.data, len(a)))
+
+    def mediaIds(self):
+        n = C.c_int64(0)
+        check(self._L.cb_dct_index_media_ids(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.uint32)
+        check(self._L.cb_dct_index_media_ids(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return set(int(x) for x in out)
+
+    def slice(self, mediaIds) -> "DctHashIndex":
+        a = _u32(sorted(mediaIds))
+        h = self._L.cb_dct_index_slice(self._h, a.ctypes.data, len(a))
+        if not h:
+            raise _lib.CbirdError(-3, "cb_dct_index_slice failed: " + self._L.cb_last_error().decode())
+        return DctHashIndex(_handle=h)
+
+    def find(self, needle: Media, params: SearchParams) -> List[Match]:
+        p = params.to_c()
+        cap = 256
+        while True:
+            out = np.zeros(cap, _lib.MATCH_DTYPE)
+            n = C.c_int64(0)
+            rc = self._L.cb_dct_index_find(self._h, C.c_uint64(int(needle.dctHash)), C.byref(p), out.ctypes.data, cap,
+                                           C.byref(n))
+            if rc == -4:  # CB_ERR_CAPACITY
+                cap = int(n.value)
+                continue
+            check(rc)
+            return _matches_from(out[: n.value])
+
+    # ---- batched entry points (the reference has none: all-pairs is N x find, database.cpp:1400) ----
+    def find_batch(self, needle_hashes, params: SearchParams) -> np.ndarray:
+        """N independent find() calls; structured array (needle, mediaId, score) sorted by those."""
+        q = _u64(needle_hashes)
+        p = params.to_c()
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_dct_index_find_batch_alloc(self._h, q.ctypes.data, len(q), C.byref(p), C.byref(ptr), C.byref(n)))
+        return _lib.take_array(ptr.value, n.value, _lib.HIT_DTYPE)
+
+    def similar(self, params: SearchParams):
+        """`-similar`: every row is a needle + searchIndex post step. Returns (offsets[count+1], hits)."""
+        p = params.to_c()
+        po, ph, n = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_dct_index_similar_alloc(self._h, C.byref(p), C.byref(po), C.byref(ph), C.byref(n)))
+        offsets = _lib.take_array(po.value, self.count() + 1, np.dtype(np.int64))
+        hits = _lib.take_array(ph.value, n.value, _lib.HIT_DTYPE)
+        return offsets, hits
+
+    def similar_shard(self, params: SearchParams, row_begin: int, row_end: int) -> np.ndarray:
+        """all rows as needles against this rank's row shard; unsorted across ranks, no post step."""
+        p = params.to_c()
+        ph, n = C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_dct_index_similar_shard_alloc(self._h, C.byref(p), row_begin, row_end, C.byref(ph), C.byref(n)))
+        return _lib.take_array(ph.value, n.value, _lib.HIT_DTYPE)

@@ -1,0 +1,155 @@
+/* cbird_b200 — C ABI of the B200-native hot path of cbird (scrubbbbs/cbird).
+ *
+ * This is the drop-in boundary: every entry point below is what a cbird build would bind in place of
+ * the CPU code cited beside it (paths are relative to the cbird source tree).  Plain pointers and
+ * sizes only; no C++ / torch / Qt types.  All functions are thread-safe per handle (cbird calls
+ * Index::find concurrently from its Qt pool under a read lock, src/database.cpp:1400,1698) and never
+ * abort: they return CB_OK (0) or a negative cb_status; cb_last_error() gives the message for the
+ * calling thread.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * CB_ERR_NO_DEVICE.
+ *
+ * Pointers named d_* are device pointers, everything else is host memory.
+ */
+#ifndef CBIRD_B200_H
+#define CBIRD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cb_status {
+  CB_OK = 0,
+  CB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+  CB_ERR_CUDA = -2,        /* a CUDA call failed, see cb_last_error() */
+  CB_ERR_INVALID = -3,     /* bad argument */
+  CB_ERR_CAPACITY = -4,    /* caller buffer too small; *n_out holds the required size */
+  CB_ERR_UNSUPPORTED = -5, /* geometry / option outside the implemented range */
+  CB_ERR_NOT_LOADED = -6   /* index not loaded (Index::isLoaded() false) */
+} cb_status;
+
+/* Index::Match (src/index.h:157-167) with MatchRange (src/media.h:62-78) flattened. */
+typedef struct cb_match {
+  uint32_t mediaId; /* unique id of indexed media */
+  int32_t score;    /* lower is better */
+  int32_t srcIn;    /* MatchRange: needle position   (-1 when unused) */
+  int32_t dstIn;    /* MatchRange: matched position  (-1 when unused) */
+  int32_t len;      /* MatchRange: length            ( 0 when unused) */
+} cb_match;
+
+/* The SearchParams fields the path reads (src/index.h:74-121); same names, same defaults. */
+typedef struct cb_params {
+  int32_t algo;             /* AlgoDCT=0, AlgoCVFeatures=2, AlgoVideo=4 (src/index.h:43-50) */
+  int32_t dctThresh;        /* 5   match iff distance <  dctThresh (strict, src/tree/vptree.h:239) */
+  int32_t cvThresh;         /* 25  match iff distance <  cvThresh  (src/cvfeaturesindex.cpp:511) */
+  int32_t minMatches;       /* 1 */
+  int32_t maxMatches;       /* 5   applied by the caller-side post step (src/database.cpp:1737) */
+  int32_t skipFrames;       /* 300 vtrim */
+  int32_t minFramesMatched; /* 30  vfm */
+  int32_t minFramesNear;    /* 60  vfn */
+  int32_t videoRadix;       /* 10  vradix; 0 = one bucket = exact */
+  int32_t maxThresh;        /* 0 */
+  uint8_t filterSelf;       /* 1 */
+  uint8_t verbose;          /* 0 */
+  uint8_t pad_[2];
+  uint32_t target;          /* 0 */
+} cb_params;
+
+/* one radius-search hit of a batched query: (needle index, media id, distance) */
+typedef struct cb_hit {
+  uint32_t needle; /* index into the needle array of the call */
+  uint32_t mediaId;
+  int32_t score;
+} cb_hit;
+
+/* raw device-side hit of the scan kernels: (index on the A side, index on the B side, distance) */
+typedef struct cb_pair {
+  uint32_t a;
+  uint32_t b;
+  uint32_t dist;
+  uint32_t pad_;
+} cb_pair;
+
+typedef struct cb_stats {
+  uint64_t comparisons;     /* pair tests issued by scan kernels since cb_stats_reset */
+  uint64_t hits;            /* pairs under threshold */
+  uint64_t kernel_launches; /* launches of this library's own kernels */
+  uint64_t frames_hashed;
+  double kernel_ms;         /* device time of the last timed call (CUDA events) */
+} cb_stats;
+
+/* ---- library -------------------------------------------------------------------------------- */
+const char* cb_version(void);
+const char* cb_last_error(void);
+/* select the CUDA device used by handles created afterwards on this thread (default 0) */
+int cb_set_device(int device);
+int cb_device_count(int* n_out);
+void cb_params_default(cb_params* p);           /* SearchParams() defaults, src/index.h:74-121 */
+int cb_stats_get(cb_stats* out);
+void cb_stats_reset(void);
+void cb_free(void* p);                           /* frees buffers returned by *_alloc calls */
+
+/* ---- kernel (a): dctHash64, replaces src/cvutil.cpp:435-545 (called from src/scanner.cpp:862 and
+ * src/media.cpp:996) — batched: n 8-bit luma frames of w x h, rows `row_stride` bytes apart, frames
+ * `frame_stride` bytes apart. out[i] is never 0 on success. w,h >= 32; w*h <= 1024*1024. ----------- */
+int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                  uint64_t* out);
+/* device-resident variant on a caller stream (cudaStream_t passed as void*); asynchronous */
+int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                      uint64_t* d_out, void* stream);
+/* the f32 DCT basis rows 0..8 (9*32 floats) and the 81-entry zig-zag table the kernel uses */
+void cb_hash_tables(float* basis_9x32, int32_t* zigzag81);
+
+/* ---- kernel (b): 64-bit Hamming radius scan, replaces hamm64 (src/hamm.h:24-26) driven by
+ * VpTree::search (src/tree/vptree.h:50-69,228-255) / RadixMap_t::search (src/tree/radix.h:187-210).
+ * Emits every (a,b) with popcount(A[a]^B[b]) < threshold and, when radix_bits>0, equal radix bucket
+ * ((h>>1) & (2^radix_bits-1), src/tree/radix.h:135-141).  *d_count receives the total number of hits
+ * (may exceed cap: only the first cap are stored, unordered).  Asynchronous on `stream`. ------------ */
+int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
+                  int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
+/* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
+ * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
+int cb_scan64_variant(int threshold);
+/* force a variant (-1 = automatic); for measurements and parity tests */
+void cb_scan64_force_variant(int variant);
+
+/* ---- DctHashIndex (src/dcthashindex.{h,cpp}) ---------------------------------------------------- */
+typedef struct cb_dct_index cb_dct_index;
+cb_dct_index* cb_dct_index_create(void);                   /* DctHashIndex()            :40-43   */
+void cb_dct_index_destroy(cb_dct_index* ix);               /* ~DctHashIndex/unload      :53-65   */
+/* load(): the (id, phash_dct) rows the reference reads from SQL            :70-114  */
+int cb_dct_index_load(cb_dct_index* ix, const uint32_t* ids, const uint64_t* hashes, int64_t n);
+int cb_dct_index_is_loaded(const cb_dct_index* ix);        /* isLoaded()                         */
+int64_t cb_dct_index_count(const cb_dct_index* ix);        /* count()                            */
+size_t cb_dct_index_memory_usage(const cb_dct_index* ix);  /* memoryUsage() = 12*count  :56-59   */
+int cb_dct_index_add(cb_dct_index* ix, const uint32_t* ids, const uint64_t* hashes, int64_t n); /* :158-173 */
+int cb_dct_index_remove(cb_dct_index* ix, const int32_t* ids, int64_t n);                       /* :175-191 */
+/* slice(): new index holding only the given media ids, caller destroys     :222-250 */
+cb_dct_index* cb_dct_index_slice(const cb_dct_index* ix, const uint32_t* ids, int64_t n);
+/* mediaIds() for a loaded index: ids whose hash != 0                        :128-132 */
+int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, int64_t* n_out);
+/* find(): all rows with distance < p->dctThresh, ascending (score, mediaId); needle hash 0 -> none.
+ * srcIn/dstIn/len are -1/-1/0.                                               :193-220 */
+int cb_dct_index_find(cb_dct_index* ix, uint64_t needle_hash, const cb_params* p, cb_match* out, int64_t cap,
+                      int64_t* n_out);
+/* N independent find() calls in one launch; hits sorted by (needle, score, mediaId). Returns a
+ * library-allocated array in *out (release with cb_free). */
+int cb_dct_index_find_batch_alloc(cb_dct_index* ix, const uint64_t* needle_hashes, int64_t n_needles,
+                                  const cb_params* p, cb_hit** out, int64_t* n_out);
+/* `-similar`: every indexed row is a needle (src/database.cpp:1400-1432), then the searchIndex post
+ * step per needle (sort by score, drop self when filterSelf, cut at maxMatches; :1729-1737).
+ * Result: CSR over rows — offsets[count+1] and hits (needle = row index). Library-allocated. */
+int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** offsets_out, cb_hit** hits_out,
+                               int64_t* n_hits_out);
+/* multi-GPU sharding hook: `-similar` needles are all rows, but only rows [row_begin,row_end) of the
+ * index are searched (this rank's shard); hits carry GLOBAL row indices as `needle`, no post step.
+ * Sorted by (needle, score, mediaId). */
+int cb_dct_index_similar_shard_alloc(cb_dct_index* ix, const cb_params* p, int64_t row_begin, int64_t row_end,
+                                     cb_hit** hits_out, int64_t* n_hits_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBIRD_B200_H */

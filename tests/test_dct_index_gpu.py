@@ -1,0 +1,205 @@
+"""GPU parity: DctHashIndex through the C ABI vs the oracle (and the reference VP tree where the
+prebuilt oracle/_ref is present), bit-exact as sorted (needle, mediaId, distance) multisets.
+Shapes follow unit/testdcthashindex.cpp + unit/testindexbase.cpp and BASELINE cfg1."""
+import numpy as np
+import pytest
+
+from cbird_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def triples(hits):
+    a = np.stack([hits["needle"].astype(np.int64), hits["mediaId"].astype(np.int64), hits["score"].astype(np.int64)], 1)
+    if len(a) == 0:
+        return a.reshape(0, 3)
+    return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    return synth.dct_hashes(10000, seed=1)
+
+
+@pytest.fixture(scope="module")
+def index(cb, cfg1):
+    h, ids = cfg1
+    ix = cb.DctHashIndex()
+    assert not ix.isLoaded() and ix.count() == 0 and ix.memoryUsage() == 0  # baseTestDefaults
+    ix.load(ids, h)
+    assert ix.isLoaded() and ix.count() == len(h)
+    assert ix.memoryUsage() == 12 * ix.count()  # unit/testdcthashindex.cpp:27-30
+    return ix
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2])
+@pytest.mark.parametrize("dht", [1, 5, 9])
+def test_all_pairs_matches_oracle(cb, po, cfg1, index, dht, variant):
+    h, ids = cfg1
+    cb.lib().cb_scan64_force_variant(variant)
+    try:
+        got = index.find_batch(h, cb.SearchParams(dctThresh=dht))
+    finally:
+        cb.lib().cb_scan64_force_variant(-1)
+    want, total, _ = po.dct_find_batch(h, ids, h, dht, threads=8)
+    assert len(got) == total
+    assert np.array_equal(triples(got), want)
+    # sorted by (needle, score, mediaId)
+    key = got["needle"].astype(np.int64) * (1 << 40) + got["score"].astype(np.int64) * (1 << 33) + got["mediaId"]
+    assert np.all(np.diff(key) > 0)
+
+
+def test_all_pairs_matches_reference_vptree(cb, po, cfg1, index):
+    if po.ref() is None:
+        pytest.skip("oracle/_ref not prebuilt")
+    h, ids = cfg1
+    got = index.find_batch(h, cb.SearchParams(dctThresh=5))
+    want, total, _ = po.ref_dcttree_find_batch(h, ids, h, 5, threads=8)
+    assert len(got) == total and np.array_equal(triples(got), want)
+
+
+@pytest.mark.parametrize("dht", [0, -3, 14, 20, 65, 200])
+def test_threshold_range(cb, po, dht):
+    # any int is tolerated: <=0 nothing, >=65 everything (SURVEY §8b parameter ranges)
+    h, ids = synth.dct_hashes(600, seed=11)
+    ix = cb.DctHashIndex()
+    ix.load(ids, h)
+    got = ix.find_batch(h[:50], cb.SearchParams(dctThresh=dht))
+    want, total, _ = po.dct_find_batch(h, ids, h[:50], dht)
+    assert len(got) == total and np.array_equal(triples(got), want)
+    if dht >= 65:
+        assert total == 50 * 600
+
+
+def test_single_find(cb, po, cfg1, index):
+    h, ids = cfg1
+    for row in (0, 17, 8500, 9999):
+        m = index.find(cb.Media(id=int(ids[row]), dctHash=int(h[row])), cb.SearchParams(dctThresh=7))
+        oi = np.zeros(4096, np.uint32)
+        od = np.zeros(4096, np.int32)
+        n = po.oracle().orc_dct_find(h, ids, len(h), int(h[row]), 7, oi, od, 4096)
+        want = sorted(zip(od[:n].tolist(), oi[:n].tolist()))
+        assert [(x.score, x.mediaId) for x in m] == want
+        assert any(x.mediaId == ids[row] and x.score == 0 for x in m)  # finds itself
+        assert all(x.range.srcIn == -1 and x.range.len == 0 for x in m)
+    # needle without hash: warning + empty (dcthashindex.cpp:196-200)
+    assert index.find(cb.Media(id=1, dctHash=0), cb.SearchParams()) == []
+
+
+def test_empty_index(cb):
+    # baseTestEmpty (unit/testindexbase.cpp:82-110)
+    ix = cb.DctHashIndex()
+    ix.load(np.zeros(0, np.uint32), np.zeros(0, np.uint64))
+    assert ix.isLoaded() and ix.count() == 0
+    assert ix.find(cb.Media(id=1, dctHash=0x10), cb.SearchParams()) == []
+    off, hits = ix.similar(cb.SearchParams())
+    assert off.tolist() == [0] and len(hits) == 0
+    ix.add([cb.Media(id=5, dctHash=0xF0)])
+    assert ix.count() == 1
+    assert [(m.mediaId, m.score) for m in ix.find(cb.Media(dctHash=0xF0), cb.SearchParams())] == [(5, 0)]
+    ix.remove([5])
+    assert ix.find(cb.Media(dctHash=0xF0), cb.SearchParams()) == []
+
+
+def test_ragged_sizes(cb, po):
+    # sizes around the 2048-row tile / block edges, odd counts
+    for n, nq in ((1, 1), (2, 3), (2047, 5), (2049, 2049), (4097, 1), (3000, 2500)):
+        h, ids = synth.dct_hashes(n, seed=n, planted_frac=0.3)
+        q = np.concatenate([h[: nq // 2], synth.dct_hashes(nq - nq // 2, seed=nq + 1)[0]])
+        ix = cb.DctHashIndex()
+        ix.load(ids, h)
+        got = ix.find_batch(q, cb.SearchParams(dctThresh=5))
+        want, total, _ = po.dct_find_batch(h, ids, q, 5)
+        assert len(got) == total and np.array_equal(triples(got), want), (n, nq)
+
+
+def test_add_remove_slice(cb, po, cfg1):
+    # baseTestAddRemove (unit/testindexbase.cpp:148-218) + slice (dcthashindex.cpp:222-250)
+    h, ids = cfg1
+    h, ids = h[:3000].copy(), ids[:3000].copy()
+    ix = cb.DctHashIndex()
+    ix.load(ids[:2000], h[:2000])
+    ix.add([cb.Media(id=int(i), dctHash=int(x)) for i, x in zip(ids[2000:], h[2000:])])
+    assert ix.count() == 3000 and ix.memoryUsage() == 36000
+    p = cb.SearchParams(dctThresh=5)
+    before = triples(ix.find_batch(h, p))
+    want, _, _ = po.dct_find_batch(h, ids, h, 5)
+    assert np.array_equal(before, want)
+
+    removed = [int(ids[10]), int(ids[1500]), int(ids[2999])]
+    ix.remove(removed)
+    assert ix.count() == 3000  # rows are nullified, not compacted (dcthashindex.cpp:183-186)
+    h2, ids2 = h.copy(), ids.copy()
+    for r in removed:
+        h2[ids2 == r] = 0
+        ids2[ids2 == r] = 0
+    after = triples(ix.find_batch(h, p))
+    want2, _, _ = po.dct_find_batch(h2, ids2, h, 5)
+    assert np.array_equal(after, want2)
+    assert not set(after[:, 1].tolist()) & set(removed)
+    assert set(removed).isdisjoint(ix.mediaIds())
+
+    ix.add([cb.Media(id=r, dctHash=int(h[ids == r][0])) for r in removed])  # re-add: same groups as before
+    again = triples(ix.find_batch(h, p))
+    assert np.array_equal(again, before)
+
+    keep = set(int(x) for x in ids[::3])
+    sl = ix.slice(keep)
+    mask = np.isin(ids, list(keep))
+    assert sl.isLoaded() and sl.count() == int(mask.sum()) + 0
+    got = triples(sl.find_batch(h[:500], p))
+    want3, _, _ = po.dct_find_batch(h[mask], ids[mask], h[:500], 5)
+    assert np.array_equal(got, want3)
+
+
+@pytest.mark.parametrize("filter_self", [False, True])
+def test_similar_post_step(cb, po, cfg1, index, filter_self):
+    # `-similar` with the searchIndex post step (database.cpp:1729-1737); testdcthashindex shape
+    h, ids = cfg1
+    p = cb.SearchParams(dctThresh=5, maxMatches=5, filterSelf=filter_self)
+    off, hits = index.similar(p)
+    assert len(off) == len(h) + 1 and off[-1] == len(hits)
+    want, _, _ = po.dct_find_batch(h, ids, h, 5, threads=8)
+    O = po.oracle()
+    starts = np.searchsorted(want[:, 0], np.arange(len(h) + 1))
+    for row in list(range(0, 300)) + list(range(8000, 8300)):
+        seg = want[starts[row]:starts[row + 1]]
+        wi = seg[:, 1].astype(np.uint32).copy()
+        ws = seg[:, 2].astype(np.int32).copy()
+        n = O.orc_search_index_post(wi, ws, len(wi), int(ids[row]), int(filter_self), 5)
+        g = hits[off[row]:off[row + 1]]
+        assert g["score"].tolist() == ws[:n].tolist(), row
+        assert g["mediaId"].tolist() == wi[:n].tolist(), row
+        assert np.all(g["needle"] == row)
+    if not filter_self:
+        assert np.all(np.diff(off) >= 1)  # every item matches itself
+
+
+def test_large_property_checks(cb):
+    # full-size property test (no oracle): 2^20 rows, each planted pair must be found symmetrically
+    n = 1 << 20
+    h, ids = synth.dct_hashes_fast(n, seed=3)
+    ix = cb.DctHashIndex()
+    ix.load(ids, h)
+    hits = ix.similar_shard(cb.SearchParams(dctThresh=5), 0, n)
+    # self matches present exactly once
+    self_hits = hits[(hits["mediaId"] == hits["needle"] + 1)]
+    assert len(np.unique(self_hits["needle"])) == n
+    # symmetry: (a,b,d) present iff (b,a,d)
+    a = hits["needle"].astype(np.int64)
+    b = hits["mediaId"].astype(np.int64) - 1
+    fwd = np.sort(a * n + b)
+    rev = np.sort(b * n + a)
+    assert np.array_equal(fwd, rev)
+    # distances recomputed on the host agree
+    x = h[a] ^ h[b]
+    d = np.zeros(len(x), np.int64)
+    for s in range(64):
+        d += ((x >> np.uint64(s)) & np.uint64(1)).astype(np.int64)
+    assert np.array_equal(d, hits["score"].astype(np.int64)) and d.max() < 5
+    # sharded halves give the same multiset (row sharding)
+    h0 = ix.similar_shard(cb.SearchParams(dctThresh=5), 0, n // 2)
+    h1 = ix.similar_shard(cb.SearchParams(dctThresh=5), n // 2, n)
+    both = np.concatenate([h0, h1])
+    assert len(both) == len(hits)
+    assert np.array_equal(np.sort(both, order=["needle", "mediaId", "score"]), np.sort(hits, order=["needle", "mediaId", "score"]))
