@@ -5,3 +5,4 @@ host-side mirror of the reference interface.  Importing the package never touche
 """
 from ._lib import CbirdError, LIB_PATH, lib  # noqa: F401
 from .index import DctHashIndex, Match, MatchRange, Media, SearchParams  # noqa: F401
+from .hashing import dct_hash64, dct_hash64_batch, hash_tables  # noqa: F401,E402

@@ -52,6 +52,9 @@ SIGNATURES = {
     "cb_stats_get": (C.c_int, [C.POINTER(cb_stats)]),
     "cb_stats_reset": (None, []),
     "cb_free": (None, [_vp]),
+    "cb_hash_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
+    "cb_hash_batch_dev": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp]),
+    "cb_hash_tables": (None, [_vp, _vp]),
     "cb_scan64_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),

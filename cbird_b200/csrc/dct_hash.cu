@@ -1,0 +1,436 @@
+// Kernel (a): batched dctHash64 for sm_100a — replaces src/cvutil.cpp:435-545, which cbird calls one
+// image at a time (src/scanner.cpp:862) or one decoded video frame at a time (src/media.cpp:996).
+//
+// Pipeline per frame:
+//   [only when the frame is not already 32x32]
+//     box_blur_kernel     cv::blur k=3/5/7 chosen by input area, BORDER_REFLECT_101, integer exact
+//     area_resize_kernel  cv::resize(32x32, INTER_AREA): (s+2)>>2 for 2x2, rint(sum*f32(1/area)) for
+//                         other integer factors, else OpenCV's f32 coverage-weight accumulation in the
+//                         same order (no FMA contraction), round half to even
+//   dct_hash32_kernel     u8 32x32 tile -> hash.  One CTA = 32 frames, 256 threads:
+//     stage 1  lane = image row: the row (32 B, two LDG.128) stays in registers; 9 lowest DCT outputs
+//              by a decimated butterfly network (61 FADD + 86 FFMA) against the DCT basis in
+//              __constant__ memory (operand straight from the constant bank)
+//              -> T[y][0..8] to shared memory (stride 297 floats per frame: conflict free both ways)
+//     stage 2  thread = (frame, column u): same butterfly + 9 chains down the column -> F[0..8][u]
+//     stage 3  warp = frame: zig-zag gather of the 64 kept coefficients (2 per lane), f64 butterfly
+//              sum for the mean (cv::sum accumulates in double), compare, two ballots = the hash
+//   The operation order is fixed and mirrored by the CPU oracle, so results are bit-identical to it;
+//   vs OpenCV's FFT-based f32 DCT only coefficients tied with the mean to ~1e-4 can flip
+//   (measured rate in DESIGN.md).  HBM traffic: 1 KiB in + 8 B out per frame.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace cbird {
+
+namespace {
+
+__constant__ float c_basis[9][32];  // orthonormal DCT-II rows 0..8
+__constant__ int c_zigzag[81];
+
+float h_basis[9][32];
+int h_zigzag[81];
+std::once_flag g_tables_once;
+std::mutex g_upload_mu;
+bool g_uploaded[64] = {false};
+
+void make_tables() {
+  for (int u = 0; u < 9; ++u) {
+    const double a = (u == 0) ? sqrt(1.0 / 32.0) : sqrt(2.0 / 32.0);
+    for (int x = 0; x < 32; ++x) h_basis[u][x] = (float)(a * cos((2 * x + 1) * u * M_PI / 64.0));
+  }
+  // 9x9 zig-zag (src/cvutil.cpp:491-495): odd anti-diagonals run bottom-left -> top-right
+  int k = 0;
+  for (int d = 0; d <= 16; ++d) {
+    const int rlo = std::max(0, d - 8), rhi = std::min(d, 8);
+    if (d & 1)
+      for (int r = rhi; r >= rlo; --r) h_zigzag[k++] = 9 * r + (d - r);
+    else
+      for (int r = rlo; r <= rhi; ++r) h_zigzag[k++] = 9 * r + (d - r);
+  }
+}
+
+int upload_tables() {
+  std::call_once(g_tables_once, make_tables);
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_upload_mu);
+  if (dev < 64 && g_uploaded[dev]) return CB_OK;
+  CB_CUDA(cudaMemcpyToSymbol(c_basis, h_basis, sizeof(h_basis)));
+  CB_CUDA(cudaMemcpyToSymbol(c_zigzag, h_zigzag, sizeof(h_zigzag)));
+  if (dev < 64) g_uploaded[dev] = true;
+  return CB_OK;
+}
+
+constexpr int kFramesPerCta = 32;
+constexpr int kHashThreads = 256;
+constexpr int kTStride = 297;  // 9*33: (9*frame + 9*y + u) mod 32 is a permutation for 32 consecutive tasks
+
+// acc = 0; acc = fma(C[U][x], v[x], acc) for x ascending — the oracle's order (oracle: chain())
+template <int U, int N>
+__device__ __forceinline__ float chain(const float (&v)[N]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int x = 0; x < N; ++x) acc = __fmaf_rn(c_basis[U][x], v[x], acc);
+  return acc;
+}
+
+// 9 lowest outputs of the 32-point DCT-II as a decimated butterfly network (oracle: dct9_of_32):
+// even outputs come from recursively folded sums/differences, so constant input gives exact zeros for
+// u>0 like cv::dct's FFT butterflies; 61 FADD + 86 FFMA + 1 FMUL per transform.
+__device__ __forceinline__ void dct9_of_32(const float (&in)[32], float (&out)[9]) {
+  float s1[16], d1[16], s2[8], d2[8], s3[4], d3[4], s4[2], d4[2];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    s1[x] = __fadd_rn(in[x], in[31 - x]);
+    d1[x] = __fsub_rn(in[x], in[31 - x]);
+  }
+  out[1] = chain<1, 16>(d1);
+  out[3] = chain<3, 16>(d1);
+  out[5] = chain<5, 16>(d1);
+  out[7] = chain<7, 16>(d1);
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    s2[x] = __fadd_rn(s1[x], s1[15 - x]);
+    d2[x] = __fsub_rn(s1[x], s1[15 - x]);
+  }
+  out[2] = chain<2, 8>(d2);
+  out[6] = chain<6, 8>(d2);
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    s3[x] = __fadd_rn(s2[x], s2[7 - x]);
+    d3[x] = __fsub_rn(s2[x], s2[7 - x]);
+  }
+  out[4] = chain<4, 4>(d3);
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    s4[x] = __fadd_rn(s3[x], s3[3 - x]);
+    d4[x] = __fsub_rn(s3[x], s3[3 - x]);
+  }
+  out[8] = chain<8, 2>(d4);
+  out[0] = __fmul_rn(__fadd_rn(s4[0], s4[1]), c_basis[0][0]);
+}
+
+__device__ __forceinline__ float byte_of(const uint32_t (&w)[8], int x) {
+  return float((w[x >> 2] >> (8 * (x & 3))) & 0xFFu);
+}
+
+__global__ void __launch_bounds__(kHashThreads, 4)
+    dct_hash32_kernel(const uint8_t* __restrict__ frames, long long n, long long row_stride, long long frame_stride,
+                      int aligned16, uint64_t* __restrict__ out) {
+  __shared__ float sT[kFramesPerCta * kTStride];
+  __shared__ float sF[kFramesPerCta * 81];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long f0 = (long long)blockIdx.x * kFramesPerCta;
+  const int nf = int(min((long long)kFramesPerCta, n - f0));
+
+  // ---- stage 1: rows ----
+  for (int fl = warp; fl < nf; fl += kHashThreads / 32) {
+    const uint8_t* row = frames + (f0 + fl) * frame_stride + (long long)lane * row_stride;
+    uint32_t w[8];
+    if (aligned16) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row));
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(row) + 1);
+      w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+      w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w[i] = uint32_t(row[4 * i]) | (uint32_t(row[4 * i + 1]) << 8) | (uint32_t(row[4 * i + 2]) << 16) |
+               (uint32_t(row[4 * i + 3]) << 24);
+    }
+    float px[32], t[9];
+#pragma unroll
+    for (int x = 0; x < 32; ++x) px[x] = byte_of(w, x);
+    dct9_of_32(px, t);
+    float* dst = sT + fl * kTStride + lane * 9;
+#pragma unroll
+    for (int u = 0; u < 9; ++u) dst[u] = t[u];
+  }
+  __syncthreads();
+
+  // ---- stage 2: columns; task = 9*frame + u ----
+  for (int task = threadIdx.x; task < nf * 9; task += kHashThreads) {
+    const int fl = task / 9, u = task - 9 * fl;
+    const float* col = sT + fl * kTStride + u;
+    float cv[32], f[9];
+#pragma unroll
+    for (int y = 0; y < 32; ++y) cv[y] = col[9 * y];
+    dct9_of_32(cv, f);
+    float* dst = sF + fl * 81 + u;
+#pragma unroll
+    for (int v = 0; v < 9; ++v) dst[9 * v] = f[v];  // row v = vertical frequency (cv::dct layout)
+  }
+  __syncthreads();
+
+  // ---- stage 3: threshold at the mean of the 64 kept coefficients ----
+  const int i0 = c_zigzag[6 + lane], i1 = c_zigzag[38 + lane];  // keep zig-zag positions 6..69 (:513)
+  for (int fl = warp; fl < nf; fl += kHashThreads / 32) {
+    const float c0 = sF[fl * 81 + i0], c1 = sF[fl * 81 + i1];
+    double v = double(c0) + double(c1);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    const float thresh = __fdiv_rn(float(v), 64.f);  // :528-529
+    const uint32_t lo = __ballot_sync(0xffffffffu, c0 > thresh) & ~1u;  // bit 0 is never set (:537)
+    const uint32_t hi = __ballot_sync(0xffffffffu, c1 > thresh);
+    if (lane == 0) {
+      uint64_t h = (uint64_t(hi) << 32) | lo;
+      if (h == 0) h = 1;  // 0 means "no hash" (:542)
+      out[f0 + fl] = h;
+    }
+  }
+}
+
+// ---- general geometry: blur + INTER_AREA -------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+__global__ void box_blur_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int w,
+                                int h, int k, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* f = src + (long long)blockIdx.z * frame_stride;
+  const int r = k >> 1, area = k * k;
+  int s = 0;
+  for (int dy = -r; dy <= r; ++dy) {
+    const uint8_t* row = f + (long long)reflect101(y + dy, h) * row_stride;
+    for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
+  }
+  dst[((long long)blockIdx.z * h + y) * w + x] = uint8_t((2 * s + area) / (2 * area));
+}
+
+struct AreaTap {
+  int si;
+  float alpha;
+};
+
+// mode 0: 2x2 integer;  1: integer factors (ix, iy);  2: general f32 taps
+__global__ void __launch_bounds__(1024)
+    area_resize_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int mode, int ix,
+                       int iy, const AreaTap* __restrict__ xt, const int* __restrict__ xofs,
+                       const AreaTap* __restrict__ yt, const int* __restrict__ yofs, uint8_t* __restrict__ dst) {
+  const int dx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const uint8_t* f = src + (long long)blockIdx.x * frame_stride;
+  uint8_t r;
+  if (mode == 0) {
+    const uint8_t* a = f + (long long)(2 * dy) * row_stride + 2 * dx;
+    const uint8_t* b = a + row_stride;
+    r = uint8_t((int(a[0]) + a[1] + b[0] + b[1] + 2) >> 2);
+  } else if (mode == 1) {
+    int s = 0;
+    for (int j = 0; j < iy; ++j) {
+      const uint8_t* row = f + (long long)(dy * iy + j) * row_stride + dx * ix;
+      for (int i = 0; i < ix; ++i) s += row[i];
+    }
+    const float v = __fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)));
+    r = uint8_t(min(255, max(0, __float2int_rn(v))));
+  } else {
+    float sum = 0.f;
+    for (int j = yofs[dy]; j < yofs[dy + 1]; ++j) {
+      const uint8_t* row = f + (long long)yt[j].si * row_stride;
+      float buf = 0.f;
+      for (int k = xofs[dx]; k < xofs[dx + 1]; ++k) buf = __fadd_rn(buf, __fmul_rn(float(row[xt[k].si]), xt[k].alpha));
+      const float t = __fmul_rn(yt[j].alpha, buf);
+      sum = (j == yofs[dy]) ? t : __fadd_rn(sum, t);
+    }
+    r = uint8_t(min(255, max(0, __float2int_rn(sum))));
+  }
+  dst[(long long)blockIdx.x * 1024 + threadIdx.x] = r;
+}
+
+// OpenCV computeResizeAreaTab (third-party imgproc, restated): coverage weights in f32
+void area_taps(int ssize, double scale, std::vector<AreaTap>& tab, std::vector<int>& ofs) {
+  tab.clear();
+  ofs.assign(33, 0);
+  for (int dx = 0; dx < 32; ++dx) {
+    ofs[dx] = int(tab.size());
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = int(ceil(fsx1)), sx2 = int(floor(fsx2));
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) tab.push_back({sx1 - 1, float((sx1 - fsx1) / cell)});
+    for (int sx = sx1; sx < sx2; ++sx) tab.push_back({sx, float(1.0 / cell)});
+    if (fsx2 - sx2 > 1e-3) tab.push_back({sx2, float(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+  }
+  ofs[32] = int(tab.size());
+}
+
+struct HashWorkspace {
+  DevBuf<uint8_t> blurred, tiles;
+  DevBuf<AreaTap> xt, yt;
+  DevBuf<int> xofs, yofs;
+  int tab_w = -1, tab_h = -1;
+};
+
+// frames already on the device. ws may be null only for 32x32 input.
+int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride,
+                       long long frame_stride, uint64_t* d_out, HashWorkspace* ws, cudaStream_t stream) {
+  if (n <= 0) return CB_OK;
+  int rc = upload_tables();
+  if (rc != CB_OK) return rc;
+  const uint8_t* tiles = d_frames;
+  long long t_row = row_stride, t_frame = frame_stride;
+  if (!(w == 32 && h == 32)) {
+    const long long area = (long long)w * h;
+    int k = 7;  // src/cvutil.cpp:446-455
+    if (area <= 32 * 32) k = 0;
+    else if (area <= 64 * 64) k = 3;
+    else if (area <= 128 * 128) k = 5;
+    const uint8_t* src = d_frames;
+    long long s_row = row_stride, s_frame = frame_stride;
+    if (k) {
+      rc = ws->blurred.reserve(size_t(n) * w * h);
+      if (rc != CB_OK) return rc;
+      dim3 grid((w + 127) / 128, h, unsigned(n)), block(128);
+      box_blur_kernel<<<grid, block, 0, stream>>>(d_frames, row_stride, frame_stride, w, h, k, ws->blurred.p);
+      CB_CUDA(cudaGetLastError());
+      counters().launches += 1;
+      src = ws->blurred.p;
+      s_row = w;
+      s_frame = area;
+    }
+    rc = ws->tiles.reserve(size_t(n) * 1024);
+    if (rc != CB_OK) return rc;
+    const double sx = w / 32.0, sy = h / 32.0;
+    const int ix = int(lrint(sx)), iy = int(lrint(sy));
+    const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
+    int mode = 2;
+    if (fast) mode = (ix == 2 && iy == 2) ? 0 : 1;
+    if (mode == 2 && (ws->tab_w != w || ws->tab_h != h)) {
+      std::vector<AreaTap> xt, yt;
+      std::vector<int> xo, yo;
+      area_taps(w, sx, xt, xo);
+      area_taps(h, sy, yt, yo);
+      CB_CUDA(cudaStreamSynchronize(stream));  // previous users of the tables are done
+      if ((rc = ws->xt.reserve(xt.size())) != CB_OK || (rc = ws->yt.reserve(yt.size())) != CB_OK ||
+          (rc = ws->xofs.reserve(33)) != CB_OK || (rc = ws->yofs.reserve(33)) != CB_OK)
+        return rc;
+      CB_CUDA(cudaMemcpy(ws->xt.p, xt.data(), xt.size() * sizeof(AreaTap), cudaMemcpyHostToDevice));
+      CB_CUDA(cudaMemcpy(ws->yt.p, yt.data(), yt.size() * sizeof(AreaTap), cudaMemcpyHostToDevice));
+      CB_CUDA(cudaMemcpy(ws->xofs.p, xo.data(), 33 * sizeof(int), cudaMemcpyHostToDevice));
+      CB_CUDA(cudaMemcpy(ws->yofs.p, yo.data(), 33 * sizeof(int), cudaMemcpyHostToDevice));
+      ws->tab_w = w;
+      ws->tab_h = h;
+    }
+    area_resize_kernel<<<unsigned(n), 1024, 0, stream>>>(src, s_row, s_frame, mode, ix, iy, ws->xt.p, ws->xofs.p,
+                                                          ws->yt.p, ws->yofs.p, ws->tiles.p);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+    tiles = ws->tiles.p;
+    t_row = 32;
+    t_frame = 1024;
+  }
+  const int aligned16 = ((reinterpret_cast<uintptr_t>(tiles) | uintptr_t(t_row) | uintptr_t(t_frame)) & 15) == 0;
+  const unsigned blocks = unsigned((n + kFramesPerCta - 1) / kFramesPerCta);
+  dct_hash32_kernel<<<blocks, kHashThreads, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().frames += uint64_t(n);
+  return CB_OK;
+}
+
+int check_geometry(int w, int h, long long n, long long row_stride, long long frame_stride) {
+  if (n < 0 || w <= 0 || h <= 0 || row_stride < w || (n > 1 && frame_stride < (long long)(h - 1) * row_stride + w)) {
+    set_error("cb_hash_batch: invalid geometry n=%lld w=%d h=%d row_stride=%lld frame_stride=%lld", n, w, h, row_stride,
+              frame_stride);
+    return CB_ERR_INVALID;
+  }
+  if (w < 32 || h < 32) {
+    set_error("cb_hash_batch: %dx%d is smaller than 32x32; INTER_AREA up-scaling is not implemented", w, h);
+    return CB_ERR_UNSUPPORTED;
+  }
+  if ((long long)w * h > 4096ll * 4096ll) {
+    set_error("cb_hash_batch: %dx%d frames are larger than the supported 4096x4096", w, h);
+    return CB_ERR_UNSUPPORTED;
+  }
+  return CB_OK;
+}
+
+struct HostHashContext {
+  std::mutex mu;
+  HashWorkspace ws;
+  DevBuf<uint8_t> d_in;
+  DevBuf<uint64_t> d_out;
+  cudaStream_t stream = nullptr;
+};
+HostHashContext g_ctx[16];
+thread_local HashWorkspace tl_ws;  // for the _dev entry point (tables per calling thread)
+
+}  // namespace
+}  // namespace cbird
+
+using namespace cbird;
+
+extern "C" {
+
+void cb_hash_tables(float* basis_9x32, int32_t* zigzag81) {
+  std::call_once(g_tables_once, make_tables);
+  if (basis_9x32) memcpy(basis_9x32, h_basis, sizeof(h_basis));
+  if (zigzag81)
+    for (int i = 0; i < 81; ++i) zigzag81[i] = h_zigzag[i];
+}
+
+int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                      uint64_t* d_out, void* stream) {
+  int rc = check_geometry(w, h, n, row_stride, frame_stride);
+  if (rc != CB_OK) return rc;
+  if (n == 0) return CB_OK;
+  if (!d_frames || !d_out) {
+    set_error("cb_hash_batch_dev: null pointer");
+    return CB_ERR_INVALID;
+  }
+  rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  return hash_frames_device(d_frames, n, w, h, row_stride, frame_stride, d_out, &tl_ws,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                  uint64_t* out) {
+  int rc = check_geometry(w, h, n, row_stride, frame_stride);
+  if (rc != CB_OK) return rc;
+  if (n == 0) return CB_OK;
+  if (!frames || !out) {
+    set_error("cb_hash_batch: null pointer");
+    return CB_ERR_INVALID;
+  }
+  rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  HostHashContext& ctx = g_ctx[current_device() & 15];
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  if (!ctx.stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  // chunks of <= 256 MiB of pixels: copy in, hash, copy the hashes out; the stream keeps H2D of the
+  // next chunk queued behind the kernels of the previous one
+  const long long frame_bytes = (long long)(h - 1) * row_stride + w;
+  const bool dense = (frame_stride == (long long)h * row_stride);
+  const long long per_frame = dense ? frame_stride : frame_bytes;
+  long long chunk = std::max(1ll, (256ll << 20) / std::max(1ll, per_frame));
+  chunk = std::min<long long>(chunk, n);
+  rc = ctx.d_in.reserve(size_t(chunk) * per_frame + 16);
+  if (rc == CB_OK) rc = ctx.d_out.reserve(size_t(chunk));
+  if (rc != CB_OK) return rc;
+  for (long long i0 = 0; i0 < n; i0 += chunk) {
+    const long long m = std::min(chunk, n - i0);
+    if (dense) {
+      CB_CUDA(cudaMemcpyAsync(ctx.d_in.p, frames + i0 * frame_stride, size_t(m) * frame_stride - (frame_stride - frame_bytes),
+                              cudaMemcpyHostToDevice, ctx.stream));
+    } else {
+      CB_CUDA(cudaMemcpy2DAsync(ctx.d_in.p, per_frame, frames + i0 * frame_stride, frame_stride, frame_bytes, m,
+                                cudaMemcpyHostToDevice, ctx.stream));
+    }
+    rc = hash_frames_device(ctx.d_in.p, m, w, h, row_stride, per_frame, ctx.d_out.p, &ctx.ws, ctx.stream);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    CB_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: one process per GPU, index rows sharded contiguously, needles replicated,
+per-shard hit lists merged with an all-gather.  torch.distributed is used only as the
+transport (NCCL over NVLink on GPUs, gloo in the CPU tests); the scan itself is the C-ABI kernel.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib
+
+
+def shard_rows(n_rows: int, rank: int, world: int, align: int = 2):
+    """contiguous row range [begin, end) of `rank`; boundaries aligned so shards keep 16-byte alignment."""
+    per = (n_rows + world - 1) // world
+    per = (per + align - 1) // align * align
+    begin = min(n_rows, rank * per)
+    end = min(n_rows, begin + per)
+    return begin, end
+
+
+def allgather_hits(local: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather variable-length hit lists.  local: [m, k] integer tensor on this rank's device.
+    Two collectives per batch: counts, then payloads padded to the longest list; returns the
+    concatenation in rank order (every rank gets the full merged list)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    m = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(counts, m, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts)
+    if mx == 0:
+        return local[:0]
+    padded = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+class ShardedSimilar:
+    """`-similar` all-pairs over an index sharded by row across the ranks of the default process group.
+
+    Every rank holds all hashes (they are also the needles: 8 B each), scans only its own row shard
+    with the C-ABI scan kernel, and the (needle, row, distance) lists are merged with allgather_hits.
+    """
+
+    def __init__(self, n_rows: int, device: torch.device, cap: int = 1 << 22):
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_rows = n_rows
+        self.device = device
+        self.begin, self.end = shard_rows(n_rows, self.rank, self.world)
+        self.cap = cap
+        self.pairs = torch.empty((cap, 4), dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+        self._L = lib()
+
+    def scan_local(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
+        """this rank's shard: needles = all rows (A side), rows [begin,end) on the B side.
+        Returns [m,4] int32 (needle, GLOBAL row, dist, 0) on the device."""
+        assert d_hashes.dtype == torch.int64 and d_hashes.is_cuda and d_hashes.numel() == self.n_rows
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        while True:
+            self.count.zero_()
+            n_b = self.end - self.begin
+            if n_b > 0:
+                check(self._L.cb_scan64_dev(d_hashes.data_ptr(), self.n_rows, d_hashes.data_ptr() + 8 * self.begin, n_b,
+                                            int(threshold), 0, self.pairs.data_ptr(), self.cap, self.count.data_ptr(),
+                                            C.c_void_p(stream)))
+            m = int(self.count.item())
+            if m <= self.cap:
+                break
+            self.cap = m + m // 8 + 1024  # overflow: the exact size is known now
+            self.pairs = torch.empty((self.cap, 4), dtype=torch.int32, device=self.device)
+        out = self.pairs[:m]
+        if self.begin:
+            out[:, 1] += self.begin
+        return out
+
+    def similar(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
+        return allgather_hits(self.scan_local(d_hashes, threshold))

@@ -191,10 +191,36 @@ int orc_preprocess32(const uint8_t* img, int w, int h, int stride, uint8_t* out3
   return area_resize32(img, w, h, stride, out32);
 }
 
-// steps 4-9 on a 32x32 u8 tile. The DCT is the separable partial transform C9 * X * C9^T in f32 with a
-// FIXED operation order (even/odd butterfly, then a 16-term fmaf chain in ascending index) that the
-// CUDA kernel follows instruction for instruction, so GPU == this function bit-exactly; the distance
-// of both to cv::dct's FFT-based f32 rounding is measured against cv2 goldens.
+// 9 lowest outputs of the 32-point orthonormal DCT-II in f32, as a decimated butterfly network:
+// every even-index output is computed from sums/differences of mirrored inputs, recursively, so a
+// constant input gives EXACTLY zero for u>0 (as cv::dct's FFT butterflies do) instead of rounding
+// noise.  basis symmetry: C[u][N-1-x] = (-1)^(u/(64/ (2N))) C[u][x] on the folded length N.
+// The operation order below is fixed; the CUDA kernel follows it instruction for instruction.
+static inline float chain(const float* c, const float* v, int n) {
+  float acc = 0.f;
+  for (int x = 0; x < n; ++x) acc = fmaf(c[x], v[x], acc);
+  return acc;
+}
+static void dct9_of_32(const float C[9][32], const float in[32], float out[9]) {
+  float s1[16], d1[16], s2[8], d2[8], s3[4], d3[4], s4[2], d4[2];
+  for (int x = 0; x < 16; ++x) { s1[x] = in[x] + in[31 - x]; d1[x] = in[x] - in[31 - x]; }
+  out[1] = chain(C[1], d1, 16);
+  out[3] = chain(C[3], d1, 16);
+  out[5] = chain(C[5], d1, 16);
+  out[7] = chain(C[7], d1, 16);
+  for (int x = 0; x < 8; ++x) { s2[x] = s1[x] + s1[15 - x]; d2[x] = s1[x] - s1[15 - x]; }
+  out[2] = chain(C[2], d2, 8);
+  out[6] = chain(C[6], d2, 8);
+  for (int x = 0; x < 4; ++x) { s3[x] = s2[x] + s2[7 - x]; d3[x] = s2[x] - s2[7 - x]; }
+  out[4] = chain(C[4], d3, 4);
+  for (int x = 0; x < 2; ++x) { s4[x] = s3[x] + s3[3 - x]; d4[x] = s3[x] - s3[3 - x]; }
+  out[8] = chain(C[8], d4, 2);
+  out[0] = (s4[0] + s4[1]) * C[0][0];
+}
+
+// steps 4-9 on a 32x32 u8 tile: separable partial transform C9 * X * C9^T in f32 (rows, then
+// columns), zig-zag selection, mean threshold.  GPU == this function bit-exactly; the distance of both
+// to cv::dct's own f32 rounding is measured against cv2 goldens (tests/test_dct_hash_oracle.py).
 // If coef64 != NULL it receives the 64 selected coefficients, *thresh_out the threshold.
 uint64_t orc_hash_from_tile32(const uint8_t* tile, float* coef64, float* thresh_out) {
   static float C[9][32];
@@ -207,32 +233,16 @@ uint64_t orc_hash_from_tile32(const uint8_t* tile, float* coef64, float* thresh_
   }
   float T[32][9];
   for (int y = 0; y < 32; ++y) {
-    float s[16], d[16];
-    for (int x = 0; x < 16; ++x) {
-      float a = (float)tile[32 * y + x], b = (float)tile[32 * y + 31 - x];
-      s[x] = a + b;
-      d[x] = a - b;
-    }
-    for (int u = 0; u < 9; ++u) {
-      const float* in = (u & 1) ? d : s;
-      float acc = 0.f;
-      for (int x = 0; x < 16; ++x) acc = fmaf(C[u][x], in[x], acc);
-      T[y][u] = acc;
-    }
+    float row[32];
+    for (int x = 0; x < 32; ++x) row[x] = (float)tile[32 * y + x];
+    dct9_of_32(C, row, T[y]);
   }
   float F[81];
   for (int u = 0; u < 9; ++u) {
-    float s[16], d[16];
-    for (int y = 0; y < 16; ++y) {
-      s[y] = T[y][u] + T[31 - y][u];
-      d[y] = T[y][u] - T[31 - y][u];
-    }
-    for (int v = 0; v < 9; ++v) {
-      const float* in = (v & 1) ? d : s;
-      float acc = 0.f;
-      for (int y = 0; y < 16; ++y) acc = fmaf(C[v][y], in[y], acc);
-      F[9 * v + u] = acc;  // row v = vertical frequency (cv::dct layout), cvutil.cpp:482-485
-    }
+    float col[32], f[9];
+    for (int y = 0; y < 32; ++y) col[y] = T[y][u];
+    dct9_of_32(C, col, f);
+    for (int v = 0; v < 9; ++v) F[9 * v + u] = f[v];  // row v = vertical frequency (cv::dct layout), cvutil.cpp:482-485
   }
   float c[64];
   for (int i = 0; i < 64; ++i) c[i] = F[zz[6 + i]];  // cvutil.cpp:508,513 keep zig-zag positions 6..69

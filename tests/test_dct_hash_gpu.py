@@ -1,0 +1,85 @@
+"""GPU parity: cb_hash_batch vs the CPU oracle (bit-exact: same f32 operation order) and vs the
+cv2 golden fixtures (only near-tie bits may flip; rate stated)."""
+import os
+
+import numpy as np
+import pytest
+
+from cbird_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GEOMS = ["32x32", "64x64", "128x72", "100x75", "128x128", "160x120", "96x64", "33x47"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "dcthash_cv2.npz"))
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_golden_vs_cv2_and_oracle(cb, po, gold, geom):
+    frames, want = gold["frames_" + geom], gold["hash_" + geom]
+    coef, thresh = gold["coef_" + geom], gold["thresh_" + geom]
+    got = cb.dct_hash64_batch(frames)
+    orc, _ = po.dct_hash64_batch(frames)
+    assert np.array_equal(got, orc)  # bit-exact vs the restatement
+    diff = got ^ want
+    flipped = 0
+    for i in np.nonzero(diff)[0]:
+        for b in range(64):
+            if int(diff[i]) >> b & 1:
+                flipped += 1
+                assert abs(float(coef[i][b]) - float(thresh[i])) <= 2e-3 * max(1.0, abs(float(thresh[i])))
+    assert flipped <= 2
+
+
+def test_cfg2_frames_bit_exact_vs_oracle(cb, po):
+    # BASELINE cfg2 distribution, 65,536 frames (the oracle hashes them in ~0.3 s on 8 threads)
+    fr = synth.luma_frames(65536, seed=2)
+    got = cb.dct_hash64_batch(fr)
+    want, _ = po.dct_hash64_batch(fr, threads=8)
+    assert np.array_equal(got, want)
+    assert np.all(got != 0) and np.all((got & np.uint64(1)) == 0)
+    # exact duplicates hash identically; +-1 LSB copies land within a small radius
+    assert len(np.unique(got)) < len(got)
+
+
+def test_ragged_and_strided(cb, po):
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 31, 32, 33, 100):
+        fr = rng.integers(0, 256, size=(n, 32, 32), dtype=np.uint8)
+        assert np.array_equal(cb.dct_hash64_batch(fr), po.dct_hash64_batch(fr)[0])
+    big = rng.integers(0, 256, size=(5, 40, 48), dtype=np.uint8)
+    view = big[:, 3:35, 7:39]  # 32x32 windows with row stride 48, frame stride 1920 (unaligned rows)
+    assert np.array_equal(cb.dct_hash64_batch(view), po.dct_hash64_batch(np.ascontiguousarray(view))[0])
+    assert cb.dct_hash64_batch(np.zeros((0, 32, 32), np.uint8)).shape == (0,)
+    assert cb.dct_hash64(np.zeros((32, 32), np.uint8)) == 1  # hash 0 is remapped (cvutil.cpp:542)
+    assert cb.dct_hash64(np.full((90, 70), 9, np.uint8)) == 1
+
+
+def test_video_sized_frames(cb, po):
+    # decoded video frames arrive <=128x128 gray (src/scanner.cpp:1045-1048): k=5 blur + area resize
+    rng = np.random.default_rng(4)
+    for (w, h) in ((128, 72), (128, 96), (72, 128), (128, 128), (64, 48), (127, 53), (320, 240)):
+        base = rng.integers(0, 256, size=(12, h // 6 + 1, w // 6 + 1)).astype(np.float32)
+        fr = np.stack([np.kron(b, np.ones((6, 6), np.float32))[:h, :w] for b in base])
+        fr = np.clip(fr + rng.normal(0, 5, fr.shape), 0, 255).astype(np.uint8)
+        assert np.array_equal(cb.dct_hash64_batch(fr), po.dct_hash64_batch(fr)[0]), (w, h)
+
+
+def test_unsupported_geometry_fails_loudly(cb):
+    with pytest.raises(cb.CbirdError) as e:
+        cb.dct_hash64_batch(np.zeros((1, 16, 64), np.uint8))
+    assert e.value.status == -5
+
+
+def test_full_size_properties(cb):
+    # cfg2 full size: 2^20 frames. Properties: deterministic, duplicates collide, never 0, bit 0 clear.
+    fr = synth.luma_frames(1 << 20, seed=2)
+    a = cb.dct_hash64_batch(fr)
+    b = cb.dct_hash64_batch(fr)
+    assert np.array_equal(a, b)
+    assert np.all(a != 0) and np.all((a & np.uint64(1)) == 0)
+    perm = np.random.default_rng(1).permutation(len(fr))[:4096]
+    assert np.array_equal(cb.dct_hash64_batch(fr[perm]), a[perm])  # batch position does not matter
