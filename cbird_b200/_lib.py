@@ -56,6 +56,7 @@ SIGNATURES = {
     "cb_hash_batch_dev": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp]),
     "cb_hash_tables": (None, [_vp, _vp]),
     "cb_scan64_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
+    "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),
     "cb_dct_index_create": (_vp, []),
@@ -72,6 +73,19 @@ SIGNATURES = {
     "cb_dct_index_find_batch_alloc": (C.c_int, [_vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_dct_index_similar_alloc": (C.c_int, [_vp, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_dct_index_similar_shard_alloc": (C.c_int, [_vp, C.POINTER(cb_params), _i64, _i64, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_video_index_create": (_vp, []),
+    "cb_video_index_destroy": (None, [_vp]),
+    "cb_video_index_load": (C.c_int, [_vp, _vp, _i64]),
+    "cb_video_index_set_video": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _i64]),
+    "cb_video_index_is_loaded": (C.c_int, [_vp]),
+    "cb_video_index_count": (_i64, [_vp]),
+    "cb_video_index_memory_usage": (C.c_size_t, [_vp]),
+    "cb_video_index_add": (C.c_int, [_vp, _vp, _i64]),
+    "cb_video_index_remove": (C.c_int, [_vp, _vp, _i64]),
+    "cb_video_index_slice": (_vp, [_vp, _vp, _i64]),
+    "cb_video_index_find_video": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_video_index_find_videos_alloc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_video_index_find_frame": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
 }
 
 

@@ -77,6 +77,8 @@ struct Scan64Launch {
   unsigned long long* count;
 };
 int scan64_launch(const Scan64Launch& L, cudaStream_t stream);
+int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, uint64_t pair_tests,
+                        cudaStream_t stream);
 int scan64_variant_for(int threshold);
 
 }  // namespace cbird

@@ -48,11 +48,20 @@ struct ScanParams {
   unsigned long long* count;
 };
 
-__device__ __forceinline__ void emit_exact(const ScanParams& P, uint32_t alo, uint32_t ahi, uint32_t blo,
-                                           uint32_t bhi, uint32_t ai, uint32_t bi) {
+struct TileBounds {
+  uint32_t a_base;   // A row of thread 0, register 0
+  uint32_t a_limit;  // first invalid A row
+  uint32_t b_begin, b_end;
+};
+
+__device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds& B, uint32_t alo, uint32_t ahi,
+                                           uint32_t blo, uint32_t bhi, uint32_t ai, uint32_t bi) {
+  // opaque copies: without them the compiler shares the XORs of this rare path with the pre-filter
+  // and the hot loop grows from 3 to 6 LOP3 per pair of pairs (seen in SASS / ncu: ALU pipe 92 %)
+  asm volatile("" : "+r"(alo), "+r"(ahi));
   const uint32_t xlo = alo ^ blo;
   const int d = __popc(xlo) + __popc(ahi ^ bhi);
-  if (d < P.threshold && ai < P.n_a && bi < P.n_b && ((xlo >> 1) & P.radix_mask) == 0) {
+  if (d < P.threshold && ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
     const unsigned long long pos = atomicAdd(P.count, 1ull);
     if (pos < P.cap) {
       uint4 rec = make_uint4(ai, bi, uint32_t(d), 0u);
@@ -61,23 +70,23 @@ __device__ __forceinline__ void emit_exact(const ScanParams& P, uint32_t alo, ui
   }
 }
 
+// one CTA-level tile: A rows [B.a_base + tid + r*256) held in registers against B rows [b_begin,b_end)
+// streamed through `tile`.
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P) {
-  __shared__ uint4 tile[kBTile / 2];
-
+__device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds& B, uint4* tile) {
   uint32_t alo[kR], ahi[kR];
-  const uint32_t a_base = blockIdx.x * kABlock + threadIdx.x;
+  const uint32_t a_base = B.a_base + threadIdx.x;
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
     const uint32_t ai = a_base + r * kThreads;
-    const uint64_t v = ai < P.n_a ? P.a[ai] : ~kPadHash;
+    const uint64_t v = ai < B.a_limit ? P.a[ai] : ~kPadHash;
     alo[r] = uint32_t(v);
     ahi[r] = uint32_t(v >> 32);
   }
 
   const int T = P.threshold;
-  const uint32_t slab_begin = blockIdx.y * P.slab;
-  const uint32_t slab_end = min(slab_begin + P.slab, P.n_b);
+  const uint32_t slab_begin = B.b_begin;
+  const uint32_t slab_end = B.b_end;
 
   for (uint32_t t0 = slab_begin; t0 < slab_end; t0 += kBTile) {
     __syncthreads();
@@ -112,8 +121,8 @@ __global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P)
           for (int r = 0; r < kR; ++r)
             if (int(p[r]) < T) {
               const uint32_t ai = a_base + r * kThreads;
-              emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
-              emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+              emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
+              emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
             }
         }
       } else if (VARIANT == 1) {
@@ -131,8 +140,8 @@ __global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P)
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
-            if (int(p1[r]) < T) emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
           }
         }
       } else {
@@ -150,13 +159,40 @@ __global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P)
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact(P, alo[r], ahi[r], d.x, d.y, ai, bi);
-            if (int(p1[r]) < T) emit_exact(P, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
           }
         }
       }
     }
   }
+}
+
+// dense grid: blockIdx.x = block of 2048 A rows, blockIdx.y = slab of B rows
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P) {
+  __shared__ uint4 tile[kBTile / 2];
+  TileBounds B;
+  B.a_base = blockIdx.x * kABlock;
+  B.a_limit = P.n_a;
+  B.b_begin = blockIdx.y * P.slab;
+  B.b_end = min(B.b_begin + P.slab, P.n_b);
+  scan_tile<VARIANT>(P, B, tile);
+}
+
+// tile list: one CTA per (<=2048 A rows) x (B range) work item — the radix-bucket search of
+// DctVideoIndex (a bucket's index rows against the needle frames that fall into the same bucket)
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, 3)
+    scan64_tiles_kernel(const ScanParams P, const cb_scan_tile* __restrict__ tiles) {
+  __shared__ uint4 tile[kBTile / 2];
+  const cb_scan_tile t = tiles[blockIdx.x];
+  TileBounds B;
+  B.a_base = t.a_begin;
+  B.a_limit = t.a_begin + t.a_count;
+  B.b_begin = t.b_begin;
+  B.b_end = t.b_begin + t.b_count;
+  scan_tile<VARIANT>(P, B, tile);
 }
 
 std::atomic<int> g_forced_variant{-1};
@@ -221,11 +257,49 @@ int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
   return CB_OK;
 }
 
+int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, uint64_t pair_tests,
+                        cudaStream_t stream) {
+  if (n_tiles == 0 || L.threshold <= 0) return CB_OK;
+  if (!L.a || !L.b || !L.count || !d_tiles || (!L.out && L.cap)) {
+    set_error("scan64_tiles: null pointer argument");
+    return CB_ERR_INVALID;
+  }
+  ScanParams P;
+  P.a = L.a;
+  P.b = L.b;
+  P.n_a = L.n_a;
+  P.n_b = L.n_b;
+  P.slab = 0;
+  P.threshold = L.threshold > 65 ? 65 : L.threshold;
+  P.radix_mask = L.radix_bits ? ((1u << L.radix_bits) - 1u) : 0u;
+  P.out = L.out;
+  P.cap = L.cap;
+  P.count = L.count;
+  switch (scan64_variant_for(P.threshold)) {
+    case 2: scan64_tiles_kernel<2><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
+    case 1: scan64_tiles_kernel<1><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
+    default: scan64_tiles_kernel<0><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
+  }
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().comparisons += pair_tests;
+  return CB_OK;
+}
+
 }  // namespace cbird
 
 using namespace cbird;
 
 extern "C" {
+
+int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, const cb_scan_tile* d_tiles,
+                        uint32_t n_tiles, int threshold, cb_pair* d_out, uint64_t cap, unsigned long long* d_count,
+                        void* stream) {
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, 0, d_out, cap, d_count};
+  return scan64_tiles_launch(L, d_tiles, n_tiles, 0, static_cast<cudaStream_t>(stream));
+}
 
 int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
                   int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {

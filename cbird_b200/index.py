@@ -186,3 +186,116 @@ class DctHashIndex:
         ph, n = C.c_void_p(), C.c_int64(0)
         check(self._L.cb_dct_index_similar_shard_alloc(self._h, C.byref(p), row_begin, row_end, C.byref(ph), C.byref(n)))
         return _lib.take_array(ph.value, n.value, _lib.HIT_DTYPE)
+
+
+class DctVideoIndex:
+    """Drop-in for src/dctvideoindex.{h,cpp}: per-video frame-hash tables searched per needle frame."""
+
+    def __init__(self, _handle=None):
+        self._L = lib()
+        self._h = _handle if _handle is not None else self._L.cb_video_index_create()
+        if not self._h:
+            raise _lib.CbirdError(-3, "cb_video_index_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.cb_video_index_destroy(h)
+
+    def id(self):
+        return SearchParams.AlgoVideo
+
+    def isLoaded(self) -> bool:
+        return bool(self._L.cb_video_index_is_loaded(self._h))
+
+    def count(self) -> int:
+        return int(self._L.cb_video_index_count(self._h))
+
+    def memoryUsage(self) -> int:
+        return int(self._L.cb_video_index_memory_usage(self._h))
+
+    def load(self, ids, tables=None):
+        """load(): ids of the indexed videos (ordered by id); tables: {id: (frames, hashes)} = the
+        contents of <dataPath>/<id>.vdx (dctvideoindex.cpp:64-72,172-211)."""
+        a = _u32(ids)
+        check(self._L.cb_video_index_load(self._h, a.ctypes.data, len(a)))
+        for vid, (frames, hashes) in (tables or {}).items():
+            self.setVideo(vid, frames, hashes)
+
+    def setVideo(self, media_id, frames, hashes):
+        f = np.ascontiguousarray(frames, dtype=np.int32)
+        h = _u64(hashes)
+        assert len(f) == len(h)
+        check(self._L.cb_video_index_set_video(self._h, int(media_id), f.ctypes.data, h.ctypes.data, len(f)))
+
+    def save(self):
+        """no-op like the reference (dctvideoindex.cpp:213-216)."""
+
+    def add(self, media: List[Media]):
+        a = _u32([m.id for m in media])
+        check(self._L.cb_video_index_add(self._h, a.ctypes.data, len(a)))
+        for m in media:
+            if m.frames is not None and m.hashes is not None:
+                self.setVideo(m.id, m.frames, m.hashes)
+
+    def remove(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        check(self._L.cb_video_index_remove(self._h, a.ctypes.data, len(a)))
+
+    def slice(self, mediaIds) -> "DctVideoIndex":
+        a = _u32(sorted(mediaIds))
+        h = self._L.cb_video_index_slice(self._h, a.ctypes.data, len(a))
+        if not h:
+            raise _lib.CbirdError(-3, "cb_video_index_slice failed")
+        return DctVideoIndex(_handle=h)
+
+    def find(self, needle: Media, params: SearchParams) -> List[Match]:
+        """find(): image needle -> findFrame, video needle -> findVideo (dctvideoindex.cpp:282-289)."""
+        p = params.to_c()
+        cap = 1024
+        while True:
+            out = np.zeros(cap, _lib.MATCH_DTYPE)
+            n = C.c_int64(0)
+            if needle.type == Media.TypeImage:
+                rc = self._L.cb_video_index_find_frame(self._h, C.c_uint64(int(needle.dctHash)), int(needle.matchRangeDstIn),
+                                                       C.byref(p), out.ctypes.data, cap, C.byref(n))
+            elif needle.type == Media.TypeVideo:
+                if needle.frames is not None:
+                    f = np.ascontiguousarray(needle.frames, dtype=np.int32)
+                    h = _u64(needle.hashes)
+                    rc = self._L.cb_video_index_find_video(self._h, f.ctypes.data, h.ctypes.data, len(f), int(needle.id),
+                                                           C.byref(p), out.ctypes.data, cap, C.byref(n))
+                else:
+                    rc = self._L.cb_video_index_find_video(self._h, None, None, 0, int(needle.id), C.byref(p),
+                                                           out.ctypes.data, cap, C.byref(n))
+            else:
+                return []
+            if rc == -4:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return _matches_from(out[: n.value])
+
+    def find_videos(self, needles: List[Media], params: SearchParams):
+        """many needle videos in one launch; returns a list of match lists (one per needle)."""
+        p = params.to_c()
+        offs = [0]
+        fr, hs = [], []
+        for m in needles:
+            if m.frames is not None:
+                fr.append(np.asarray(m.frames, np.int32))
+                hs.append(np.asarray(m.hashes, np.uint64))
+                offs.append(offs[-1] + len(m.frames))
+            else:
+                offs.append(offs[-1])
+        frames = np.ascontiguousarray(np.concatenate(fr) if fr else np.zeros(0, np.int32), dtype=np.int32)
+        hashes = _u64(np.concatenate(hs) if hs else np.zeros(0, np.uint64))
+        offsets = np.ascontiguousarray(offs, dtype=np.int64)
+        ids = _u32([m.id for m in needles])
+        po, pm, n = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_video_index_find_videos_alloc(self._h, offsets.ctypes.data, frames.ctypes.data, hashes.ctypes.data,
+                                                       ids.ctypes.data, len(needles), C.byref(p), C.byref(po), C.byref(pm),
+                                                       C.byref(n)))
+        ro = _lib.take_array(po.value, len(needles) + 1, np.dtype(np.int64))
+        mm = _lib.take_array(pm.value, n.value, _lib.MATCH_DTYPE)
+        return [_matches_from(mm[ro[k]:ro[k + 1]]) for k in range(len(needles))]

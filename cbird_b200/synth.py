@@ -75,3 +75,41 @@ def luma_frames(n, seed, w=32, h=32, dup_frac=0.01, lsb_frac=0.01):
         src += rng.integers(-1, 2, size=src.shape, dtype=np.int16)
         frames[dst] = np.clip(src, 0, 255).astype(np.uint8)
     return frames
+
+
+def video_tables(n_videos, frames_per_video, seed, first_id=1):
+    """cfg4-style haystack: per-video random-walk frame hashes (each frame = previous with 0-3 bits of
+    1..63 flipped) and strictly increasing frame numbers starting at 0 with gaps 1-30.
+    Returns (ids u32[n], {id: (frames i32, hashes u64)})."""
+    rng = np.random.default_rng(seed)
+    ids = np.arange(first_id, first_id + n_videos, dtype=np.uint32)
+    start = rng.integers(0, 2 ** 63, size=n_videos, dtype=np.uint64) << _U64(1)
+    nflip = rng.integers(0, 4, size=(n_videos, frames_per_video))
+    bits = rng.integers(1, 64, size=(n_videos, frames_per_video, 3)).astype(np.uint64)
+    delta = np.zeros((n_videos, frames_per_video), np.uint64)
+    for k in range(3):
+        delta ^= np.where(nflip > k, _U64(1) << bits[:, :, k], _U64(0)).astype(np.uint64)
+    delta[:, 0] = start
+    hashes = np.bitwise_xor.accumulate(delta, axis=1)
+    gaps = rng.integers(1, 31, size=(n_videos, frames_per_video)).astype(np.int64)
+    gaps[:, 0] = 0
+    frames = np.cumsum(gaps, axis=1).astype(np.int32)
+    tables = {int(i): (frames[k].copy(), hashes[k].copy()) for k, i in enumerate(ids)}
+    return ids, tables
+
+
+def video_needles(ids, tables, n_copies, n_unrelated, frames_per_video, seed):
+    """needle videos: re-timed copies of haystack videos (every 2nd frame kept) + unrelated random walks.
+    Returns list of (needle_id, frames, hashes, source_id or 0); needle ids are 0 (not in the index)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    src = rng.choice(ids, size=min(n_copies, len(ids)), replace=False)
+    for s in src:
+        f, h = tables[int(s)]
+        out.append((0, f[::2].copy(), h[::2].copy(), int(s)))
+    if n_unrelated:
+        _, other = video_tables(n_unrelated, frames_per_video, seed + 1000, first_id=1)
+        for k in other:
+            f, h = other[k]
+            out.append((0, f, h, 0))
+    return out

@@ -72,6 +72,12 @@ typedef struct cb_pair {
   uint32_t pad_;
 } cb_pair;
 
+/* one work item of the tile-list scan: A rows [a_begin, a_begin+a_count), a_count <= 2048, against
+ * B rows [b_begin, b_begin+b_count) */
+typedef struct cb_scan_tile {
+  uint32_t a_begin, a_count, b_begin, b_count;
+} cb_scan_tile;
+
 typedef struct cb_stats {
   uint64_t comparisons;     /* pair tests issued by scan kernels since cb_stats_reset */
   uint64_t hits;            /* pairs under threshold */
@@ -106,9 +112,15 @@ void cb_hash_tables(float* basis_9x32, int32_t* zigzag81);
  * VpTree::search (src/tree/vptree.h:50-69,228-255) / RadixMap_t::search (src/tree/radix.h:187-210).
  * Emits every (a,b) with popcount(A[a]^B[b]) < threshold and, when radix_bits>0, equal radix bucket
  * ((h>>1) & (2^radix_bits-1), src/tree/radix.h:135-141).  *d_count receives the total number of hits
- * (may exceed cap: only the first cap are stored, unordered).  Asynchronous on `stream`. ------------ */
+ * (may exceed cap: only the first cap are stored, unordered); it ACCUMULATES, the caller zeroes it.
+ * Asynchronous on `stream`. ---------------------------------------------------------------------- */
 int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
                   int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
+/* same inner loop over an explicit list of (A block, B range) work items, one CTA each — the
+ * radix-bucket search of DctVideoIndex (src/tree/radix.h:187-210 scans one bucket per needle frame) */
+int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b,
+                        const cb_scan_tile* d_tiles, uint32_t n_tiles, int threshold, cb_pair* d_out, uint64_t cap,
+                        unsigned long long* d_count, void* stream);
 /* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
  * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
 int cb_scan64_variant(int threshold);
@@ -148,6 +160,41 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
  * Sorted by (needle, score, mediaId). */
 int cb_dct_index_similar_shard_alloc(cb_dct_index* ix, const cb_params* p, int64_t row_begin, int64_t row_end,
                                      cb_hit** hits_out, int64_t* n_hits_out);
+
+/* ---- DctVideoIndex (src/dctvideoindex.{h,cpp}) --------------------------------------------------
+ * The per-video frame-hash tables the reference reads from "<dataPath>/<mediaId>.vdx"
+ * (src/dctvideoindex.cpp:64-72) are handed over with cb_video_index_set_video (or read from .vdx files
+ * with cb_vdx_load below).  The bucket "tree" is built lazily by the first search and rebuilt whenever
+ * videoRadix / skipFrames / the contents change. */
+typedef struct cb_video_index cb_video_index;
+cb_video_index* cb_video_index_create(void);
+void cb_video_index_destroy(cb_video_index* ix);
+/* load(): media ids of type=video ordered by id; at most 2^24 are kept       :172-211 */
+int cb_video_index_load(cb_video_index* ix, const uint32_t* ids, int64_t n);
+/* VideoIndex{frames[], hashes[]} of one video (src/videoindex.h:45-46) */
+int cb_video_index_set_video(cb_video_index* ix, uint32_t media_id, const int32_t* frames, const uint64_t* hashes,
+                             int64_t n);
+int cb_video_index_is_loaded(const cb_video_index* ix);
+int64_t cb_video_index_count(const cb_video_index* ix);          /* count() = number of videos :49-53 */
+size_t cb_video_index_memory_usage(const cb_video_index* ix);    /* 0 until the tree is built  :57-59 */
+int cb_video_index_add(cb_video_index* ix, const uint32_t* ids, int64_t n);     /* :256-260 */
+int cb_video_index_remove(cb_video_index* ix, const int32_t* ids, int64_t n);   /* :262-280 */
+cb_video_index* cb_video_index_slice(const cb_video_index* ix, const uint32_t* ids, int64_t n); /* :389-397 */
+/* findVideo(): needle = one video's (frames, hashes); frames==NULL && needle_id!=0 uses the stored
+ * table of needle_id.  One match per similar video: score = 100 - percentNear, range = (srcIn, dstIn,
+ * len), ascending mediaId.                                                     :399-657 */
+int cb_video_index_find_video(cb_video_index* ix, const int32_t* frames, const uint64_t* hashes, int64_t n,
+                              uint32_t needle_id, const cb_params* p, cb_match* out, int64_t cap, int64_t* n_out);
+/* many needle videos in one launch: needle k owns frames/hashes[needle_offsets[k] .. needle_offsets[k+1]);
+ * result CSR (result_offsets[n_needles+1], matches) is library-allocated (cb_free). */
+int cb_video_index_find_videos_alloc(cb_video_index* ix, const int64_t* needle_offsets, const int32_t* frames,
+                                     const uint64_t* hashes, const uint32_t* needle_ids, int64_t n_needles,
+                                     const cb_params* p, int64_t** result_offsets, cb_match** matches,
+                                     int64_t* n_matches);
+/* findFrame(): needle = one image hash; nearest frame per video: score = distance,
+ * range = (needle_dst_in<0 ? 0 : needle_dst_in, matched frame, 1), ascending video index.  :291-387 */
+int cb_video_index_find_frame(cb_video_index* ix, uint64_t hash, int32_t needle_dst_in, const cb_params* p,
+                              cb_match* out, int64_t cap, int64_t* n_out);
 
 #ifdef __cplusplus
 }

@@ -383,4 +383,241 @@ int orc_search_index_post(uint32_t* ids, int* scores, int n, uint32_t needle_id,
   return k;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// DctVideoIndex — src/dctvideoindex.cpp.  The .vdx tables are handed in by the caller (the reference
+// reads "<dataPath>/<mediaId>.vdx", :64-72); everything else follows the cited lines.
+// ---------------------------------------------------------------------------------------------
+struct OrcVideoTable {
+  std::vector<int> frames;         // VideoIndex::frames  (src/videoindex.h:45)
+  std::vector<uint64_t> hashes;    // VideoIndex::hashes  (src/videoindex.h:46)
+};
+struct OrcBucketItem {
+  uint64_t hash;
+  uint32_t idx;  // index into mediaId[], VideoTreeIndex::idx (src/dctvideoindex.h:41)
+  int frame;     // VideoTreeIndex::frame
+};
+struct OrcVideoIndex {
+  std::vector<uint32_t> mediaId;
+  std::map<uint32_t, OrcVideoTable> tables;
+  std::vector<std::vector<OrcBucketItem>> buckets;  // RadixMap_t (src/tree/radix.h): bucket = (hash>>1)&mask
+  uint64_t mask = 0;
+  bool built = false;
+  int built_radix = -1, built_skip = -1;
+};
+
+static uint64_t radix_mask_for(int radix) {
+  // RadixMap_t ctor clamps the radix (src/tree/radix.h:105-112: 30 - ceil(log2(sizeof(Bucket)+8)) = 24)
+  if (radix < 0) radix = 0;
+  if (radix > 24) radix = 24;
+  uint64_t m = 0;
+  for (int i = 0; i < radix; ++i) m |= 1ull << i;
+  return m;
+}
+
+// DctVideoIndex::insertHashes, src/dctvideoindex.cpp:61-111
+static void orc_insert_hashes(OrcVideoIndex* ix, uint32_t mediaIndex, int skipFrames) {
+  auto it = ix->tables.find(ix->mediaId[mediaIndex]);
+  if (it == ix->tables.end()) return;  // "index file missing" :65-68
+  const OrcVideoTable& t = it->second;
+  if (t.frames.empty()) return;
+  const int lastFrame = t.frames[t.frames.size() - 1];
+  const int skip = skipFrames;
+  for (size_t j = 0; j < t.hashes.size(); ++j) {
+    const uint64_t hash = t.hashes[j];
+    if (orc_hamm64(hash, 0) < 5 || orc_hamm64(hash, 0xFFFFFFFFFFFFFFFFull) < 5) continue;  // :89
+    const int frame = t.frames[j];
+    if (skip && lastFrame / 2 > skip) {  // :93-95
+      if (frame < skip || frame > lastFrame - skip) continue;
+    }
+    ix->buckets[(hash >> 1) & ix->mask].push_back({hash, mediaIndex, frame});  // radix.h:135-155
+  }
+}
+
+// DctVideoIndex::buildTree, src/dctvideoindex.cpp:113-170. The reference builds once with the
+// parameters of the first query; the restatement (and the product) rebuild whenever vradix/vtrim or
+// the contents change so that results never depend on query history — documented divergence.
+static void orc_build_tree(OrcVideoIndex* ix, int videoRadix, int skipFrames) {
+  if (ix->built && ix->built_radix == videoRadix && ix->built_skip == skipFrames) return;
+  ix->built_radix = videoRadix;
+  ix->built_skip = skipFrames;
+  ix->mask = radix_mask_for(videoRadix);
+  ix->buckets.assign(size_t(ix->mask + 1), std::vector<OrcBucketItem>());
+  for (size_t i = 0; i < ix->mediaId.size(); ++i) orc_insert_hashes(ix, uint32_t(i), skipFrames);
+  ix->built = true;
+}
+
+struct OrcMatch {  // Index::Match + MatchRange flattened (src/index.h:157-167, src/media.h:62-78)
+  uint32_t mediaId;
+  int32_t score, srcIn, dstIn, len;
+};
+
+void* orc_video_create() { return new OrcVideoIndex; }
+void orc_video_destroy(void* p) { delete static_cast<OrcVideoIndex*>(p); }
+// load(): ids of type=video ordered by id, src/dctvideoindex.cpp:172-211
+void orc_video_load(void* p, const uint32_t* ids, long long n) {
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  ix->mediaId.assign(ids, ids + n);
+  ix->built = false;
+}
+void orc_video_set_video(void* p, uint32_t id, const int* frames, const uint64_t* hashes, long long n) {
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  OrcVideoTable& t = ix->tables[id];
+  t.frames.assign(frames, frames + n);
+  t.hashes.assign(hashes, hashes + n);
+  ix->built = false;
+}
+void orc_video_add(void* p, const uint32_t* ids, long long n) {  // :256-260
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  for (long long i = 0; i < n; ++i) ix->mediaId.push_back(ids[i]);
+  ix->built = false;
+}
+void orc_video_remove(void* p, const int* ids, long long n) {  // :262-280
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  std::vector<uint32_t> copy;
+  for (uint32_t id : ix->mediaId) {
+    bool gone = false;
+    for (long long i = 0; i < n; ++i) gone |= (int(id) == ids[i]);
+    if (!gone) copy.push_back(id);
+  }
+  ix->mediaId = copy;
+  ix->built = false;
+}
+long long orc_video_count(void* p) { return (long long)static_cast<OrcVideoIndex*>(p)->mediaId.size(); }
+
+// DctVideoIndex::findVideo, src/dctvideoindex.cpp:399-657.
+// needle table given explicitly; if frames==NULL the stored table of needle_id is used (:411-414).
+long long orc_video_find_video(void* p, const int* nframes, const uint64_t* nhashes, long long nn, uint32_t needle_id,
+                               int dctThresh, int skipFrames, int minFramesMatched, int minFramesNear, int videoRadix,
+                               int filterSelf, OrcMatch* out, long long cap) {
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  orc_build_tree(ix, videoRadix, skipFrames);
+  OrcVideoTable stored;
+  if (!nframes) {
+    auto it = ix->tables.find(needle_id);
+    if (it == ix->tables.end()) return 0;
+    stored = it->second;
+    nframes = stored.frames.data();
+    nhashes = stored.hashes.data();
+    nn = (long long)stored.frames.size();
+  }
+  if (nn == 0) return 0;  // "needle video index is empty" :416-419
+  int thr = dctThresh;    // RadixMap_t::distance_t is char (radix.h:44); the boundary clamps to [0,65]
+  if (thr < 0) thr = 0;
+  if (thr > 65) thr = 65;
+
+  struct Src { int frame; uint64_t hash; };
+  std::vector<Src> srcData;
+  const int lastFrame = nframes[nn - 1];
+  for (long long i = 0; i < nn; ++i) {
+    const int srcFrame = nframes[i];
+    if (srcFrame < skipFrames || srcFrame > (lastFrame - skipFrames)) continue;  // :431
+    srcData.push_back({srcFrame, nhashes[i]});  // (the bucket pre-sort :436-450 only changes visiting order)
+  }
+
+  std::map<uint32_t, std::vector<std::pair<int, int>>> cand;  // mediaId -> (srcIn, dstIn), QMap order :463
+  std::unordered_map<uint32_t, std::pair<int, int>> closest;  // mediaId -> (score, frame)  :469
+  for (const Src& q : srcData) {
+    closest.clear();
+    const std::vector<OrcBucketItem>& b = ix->buckets[(q.hash >> 1) & ix->mask];  // radix.h:187-190
+    for (const OrcBucketItem& it : b) {                                           // insertion order
+      const int d = orc_hamm64(q.hash, it.hash);
+      if (!(d < thr)) continue;                                                   // radix.h:196 strict
+      const uint32_t id = ix->mediaId[it.idx];
+      if (id == needle_id && filterSelf) continue;                                // :493-496
+      auto c = closest.find(id);
+      if (c == closest.end() || d < c->second.first) closest[id] = {d, it.frame};  // first wins ties :499-501
+    }
+    for (auto& c : closest) cand[c.first].push_back({q.frame, c.second.second});  // :505-507
+  }
+
+  long long k = 0;
+  const int frameMargin = 15;  // :592
+  for (auto& kv : cand) {
+    auto& ranges = kv.second;
+    std::sort(ranges.begin(), ranges.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      return a.first < b.first;  // MatchRange::operator< compares srcIn only (src/media.h:77)
+    });
+    int numAdjacent = 0, last = 0;
+    for (auto& r : ranges) {  // :607-613
+      if (abs(r.second - last) < frameMargin) numAdjacent++;
+      last = r.second;
+    }
+    const int num = int(ranges.size());
+    const int percentNear = numAdjacent * 100 / num;  // :616
+    if (num < minFramesMatched) continue;             // :619-624
+    if (percentNear < minFramesNear) continue;        // :637-641
+    OrcMatch m;
+    m.mediaId = kv.first;
+    m.score = 100 - percentNear;  // :645
+    m.srcIn = ranges.front().first;
+    m.dstIn = ranges.front().second;
+    const int srcLen = ranges.back().first - m.srcIn;
+    const int dstLen = ranges.back().second - m.dstIn;
+    m.len = std::max(srcLen, dstLen);  // :649-651
+    if (k < cap) out[k] = m;
+    ++k;
+  }
+  return k;
+}
+
+// DctVideoIndex::findFrame, src/dctvideoindex.cpp:291-387 (params.target: only the video with the
+// first id >= target, as std::lower_bound picks it :307-310)
+long long orc_video_find_frame(void* p, uint64_t hash, int needle_dst_in, int dctThresh, int skipFrames, int videoRadix,
+                               uint32_t target, OrcMatch* out, long long cap) {
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  orc_build_tree(ix, videoRadix, skipFrames);
+  if (hash == 0) return 0;  // :331-335
+  int thr = dctThresh;
+  if (thr < 0) thr = 0;
+  if (thr > 65) thr = 65;
+  long long only = -1;
+  if (target != 0) {
+    auto it = std::lower_bound(ix->mediaId.begin(), ix->mediaId.end(), target);
+    if (it == ix->mediaId.end()) return 0;  // "unable to find the requested target id" :316-318
+    only = it - ix->mediaId.begin();
+  }
+  std::map<uint32_t, std::pair<int, int>> nearest;  // mediaIndex -> (distance, frame)  :353
+  for (const OrcBucketItem& it : ix->buckets[(hash >> 1) & ix->mask]) {
+    if (only >= 0 && (long long)it.idx != only) continue;
+    const int d = orc_hamm64(hash, it.hash);
+    if (!(d < thr)) continue;
+    auto f = nearest.find(it.idx);
+    if (f == nearest.end()) nearest[it.idx] = {d, it.frame};
+    else if (d < f->second.first) f->second = {d, it.frame};  // :360-363
+  }
+  long long k = 0;
+  for (auto& kv : nearest) {  // :366-384
+    OrcMatch m;
+    m.mediaId = ix->mediaId[kv.first];
+    m.score = kv.second.first;
+    m.srcIn = needle_dst_in < 0 ? 0 : needle_dst_in;
+    m.dstIn = kv.second.second;
+    m.len = 1;
+    if (k < cap) out[k] = m;
+    ++k;
+  }
+  return k;
+}
+
+// raw bucket search of the restated tree (for pinning against the reference radix.h)
+long long orc_video_bucket_search(void* p, uint64_t hash, int thr, int skipFrames, int videoRadix, uint32_t* out_idx,
+                                  int* out_frame, int* out_dist, long long cap) {
+  OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
+  orc_build_tree(ix, videoRadix, skipFrames);
+  long long k = 0;
+  for (const OrcBucketItem& it : ix->buckets[(hash >> 1) & ix->mask]) {
+    const int d = orc_hamm64(hash, it.hash);
+    if (d < thr) {
+      if (k < cap) {
+        out_idx[k] = it.idx;
+        out_frame[k] = it.frame;
+        out_dist[k] = d;
+      }
+      ++k;
+    }
+  }
+  return k;
+}
+
 }  // extern "C"

@@ -49,6 +49,23 @@ def oracle():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
         L.orc_dct_find_batch.restype = C.c_longlong
         L.orc_search_index_post.argtypes = [_u32p, _i32p, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        L.orc_video_create.restype = C.c_void_p
+        L.orc_video_destroy.argtypes = [C.c_void_p]
+        L.orc_video_load.argtypes = [C.c_void_p, _u32p, C.c_longlong]
+        L.orc_video_set_video.argtypes = [C.c_void_p, C.c_uint32, _i32p, _u64p, C.c_longlong]
+        L.orc_video_add.argtypes = [C.c_void_p, _u32p, C.c_longlong]
+        L.orc_video_remove.argtypes = [C.c_void_p, _i32p, C.c_longlong]
+        L.orc_video_count.argtypes = [C.c_void_p]
+        L.orc_video_count.restype = C.c_longlong
+        L.orc_video_find_video.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint32, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+        L.orc_video_find_video.restype = C.c_longlong
+        L.orc_video_find_frame.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                           C.c_void_p, C.c_longlong]
+        L.orc_video_find_frame.restype = C.c_longlong
+        L.orc_video_bucket_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, _u32p, _i32p, _i32p,
+                                              C.c_longlong]
+        L.orc_video_bucket_search.restype = C.c_longlong
         _oracle = L
     return _oracle
 
@@ -159,3 +176,66 @@ def canonical(q, ids, dist):
         return a.reshape(0, 3)
     order = np.lexsort((a[:, 2], a[:, 1], a[:, 0]))
     return a[order]
+
+
+ORC_MATCH = np.dtype([("mediaId", np.uint32), ("score", np.int32), ("srcIn", np.int32), ("dstIn", np.int32),
+                      ("len", np.int32)])
+
+
+class OracleVideoIndex:
+    """restated DctVideoIndex (oracle/cbird_oracle.cpp, src/dctvideoindex.cpp)."""
+
+    def __init__(self):
+        self.L = oracle()
+        self.h = self.L.orc_video_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_video_destroy(self.h)
+            self.h = None
+
+    def load(self, ids, tables=None):
+        self.L.orc_video_load(self.h, np.ascontiguousarray(ids, np.uint32), len(ids))
+        for vid, (f, h) in (tables or {}).items():
+            self.set_video(vid, f, h)
+
+    def set_video(self, vid, frames, hashes):
+        self.L.orc_video_set_video(self.h, int(vid), np.ascontiguousarray(frames, np.int32),
+                                   np.ascontiguousarray(hashes, np.uint64), len(frames))
+
+    def add(self, ids):
+        self.L.orc_video_add(self.h, np.ascontiguousarray(ids, np.uint32), len(ids))
+
+    def remove(self, ids):
+        self.L.orc_video_remove(self.h, np.ascontiguousarray(ids, np.int32), len(ids))
+
+    def count(self):
+        return int(self.L.orc_video_count(self.h))
+
+    def find_video(self, frames, hashes, needle_id, dht=5, skip=300, vfm=30, vfn=60, vradix=10, filter_self=True):
+        out = np.zeros(4096, ORC_MATCH)
+        if frames is None:
+            n = self.L.orc_video_find_video(self.h, None, None, 0, int(needle_id), dht, skip, vfm, vfn, vradix,
+                                            int(filter_self), out.ctypes.data, len(out))
+        else:
+            f = np.ascontiguousarray(frames, np.int32)
+            h = np.ascontiguousarray(hashes, np.uint64)
+            n = self.L.orc_video_find_video(self.h, f.ctypes.data, h.ctypes.data, len(f), int(needle_id), dht, skip, vfm,
+                                            vfn, vradix, int(filter_self), out.ctypes.data, len(out))
+        assert n <= len(out)
+        return out[:n].copy()
+
+    def find_frame(self, hash_, dst_in=-1, dht=5, skip=300, vradix=10, target=0):
+        out = np.zeros(65536, ORC_MATCH)
+        n = self.L.orc_video_find_frame(self.h, int(hash_), int(dst_in), dht, skip, vradix, int(target), out.ctypes.data,
+                                        len(out))
+        assert n <= len(out)
+        return out[:n].copy()
+
+    def bucket_search(self, hash_, thr, skip, vradix, cap=1 << 16):
+        idx = np.zeros(cap, np.uint32)
+        fr = np.zeros(cap, np.int32)
+        d = np.zeros(cap, np.int32)
+        n = self.L.orc_video_bucket_search(self.h, int(hash_), thr, skip, vradix, idx, fr, d, cap)
+        assert n <= cap
+        return idx[:n], fr[:n], d[:n]
