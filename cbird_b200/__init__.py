@@ -4,5 +4,5 @@ The compute lives in libcbird_b200.so (CUDA, C ABI: include/cbird_b200.h); this 
 host-side mirror of the reference interface.  Importing the package never touches oracle/.
 """
 from ._lib import CbirdError, LIB_PATH, lib  # noqa: F401
-from .index import DctHashIndex, DctVideoIndex, Match, MatchRange, Media, SearchParams  # noqa: F401
+from .index import CvFeaturesIndex, DctHashIndex, DctVideoIndex, Match, MatchRange, Media, SearchParams  # noqa: F401
 from .hashing import dct_hash64, dct_hash64_batch, hash_tables  # noqa: F401,E402

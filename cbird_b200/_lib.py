@@ -86,6 +86,18 @@ SIGNATURES = {
     "cb_video_index_find_video": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
     "cb_video_index_find_videos_alloc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_video_index_find_frame": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_orb_index_create": (_vp, []),
+    "cb_orb_index_destroy": (None, [_vp]),
+    "cb_orb_index_load": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "cb_orb_index_add": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "cb_orb_index_remove": (C.c_int, [_vp, _vp, _i64]),
+    "cb_orb_index_is_loaded": (C.c_int, [_vp]),
+    "cb_orb_index_count": (_i64, [_vp]),
+    "cb_orb_index_memory_usage": (C.c_size_t, [_vp]),
+    "cb_orb_index_slice": (_vp, [_vp, _vp, _i64]),
+    "cb_orb_index_descriptors": (C.c_int, [_vp, C.c_uint32, _vp, _i64, C.POINTER(_i64)]),
+    "cb_orb_index_find": (C.c_int, [_vp, _vp, _i64, C.c_uint32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_orb_index_knn_alloc": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
 }
 
 

@@ -1,0 +1,490 @@
+// Kernel (c): 256-bit ORB descriptor matcher for sm_100a + CvFeaturesIndex behind the C ABI.
+//
+// Replaces cv::flann::Index(LSH)::knnSearch(k=10) in CvFeaturesIndex::find
+// (src/cvfeaturesindex.cpp:497) — an approximate, per-build randomised search — with an EXACT scan.
+// find() only keeps neighbours with distance < cvThresh (:511), so the k nearest under the threshold
+// are all that matter: the kernel is a radius scan (like scan64) and the top-k cut happens on the
+// (tiny) hit list afterwards.
+//
+//   * A side = index rows in registers: 4 rows x 8 words per thread, 1024 rows per CTA, every row is
+//     read from HBM once per query slab (32 B/row, two LDG.128 per row);
+//   * B side = needle descriptors in shared memory (512 per 16 KB tile), read as broadcast LDS.128;
+//   * the exact distance costs 8 POPC per pair (the binding pipe: 16 lanes/clk/SM). The pre-filter
+//     ORs the 8 XOR words down to G words first (G = 1, 2 or 4; one 3-input LOP3 per word, the XOR is
+//     fused) and popcounts those: popc(OR) <= distance, so "bound < T" is necessary; survivors are
+//     re-tested exactly.  G is chosen from the threshold so that the bound stays far above T on
+//     random descriptors (G=1 saturates at ~32, G=2 at ~60, G=4 at ~96); G=8 is the exact kernel.
+#include <cub/device/device_merge_sort.cuh>
+
+#include <algorithm>
+#include <map>
+#include <unordered_set>
+
+#include "common.h"
+
+namespace cbird {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kR = 4;
+constexpr int kABlock = kThreads * kR;  // 1024 rows
+constexpr int kQTile = 512;             // queries per smem tile (16 KB)
+
+struct KnnParams {
+  const uint4* __restrict__ db;  // rows x 2 uint4
+  const uint4* __restrict__ q;   // queries x 2 uint4
+  uint32_t n_db, n_q;
+  uint32_t slab;  // queries per blockIdx.y (multiple of kQTile)
+  int threshold;
+  cb_pair* out;
+  unsigned long long cap;
+  unsigned long long* count;
+};
+
+__device__ __forceinline__ void emit256(const KnnParams& P, const uint32_t (&a)[8], const uint4& b0, const uint4& b1,
+                                        uint32_t row, uint32_t qi) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = a[i];
+    asm volatile("" : "+r"(x[i]));  // opaque copy: keep this rare path's XORs out of the hot loop's CSE
+  }
+  const int d = __popc(x[0] ^ b0.x) + __popc(x[1] ^ b0.y) + __popc(x[2] ^ b0.z) + __popc(x[3] ^ b0.w) +
+                __popc(x[4] ^ b1.x) + __popc(x[5] ^ b1.y) + __popc(x[6] ^ b1.z) + __popc(x[7] ^ b1.w);
+  if (d < P.threshold && row < P.n_db && qi < P.n_q) {
+    const unsigned long long pos = atomicAdd(P.count, 1ull);
+    if (pos < P.cap) *reinterpret_cast<uint4*>(P.out + pos) = make_uint4(row, qi, uint32_t(d), 0u);
+  }
+}
+
+template <int G>
+__device__ __forceinline__ uint32_t bound256(const uint32_t (&a)[8], const uint4& b0, const uint4& b1) {
+  if (G == 1) {
+    uint32_t w = a[0] ^ b0.x;
+    w |= a[1] ^ b0.y;
+    w |= a[2] ^ b0.z;
+    w |= a[3] ^ b0.w;
+    w |= a[4] ^ b1.x;
+    w |= a[5] ^ b1.y;
+    w |= a[6] ^ b1.z;
+    w |= a[7] ^ b1.w;
+    return __popc(w);
+  } else if (G == 2) {
+    uint32_t w0 = a[0] ^ b0.x, w1 = a[4] ^ b1.x;
+    w0 |= a[1] ^ b0.y;
+    w1 |= a[5] ^ b1.y;
+    w0 |= a[2] ^ b0.z;
+    w1 |= a[6] ^ b1.z;
+    w0 |= a[3] ^ b0.w;
+    w1 |= a[7] ^ b1.w;
+    return __popc(w0) + __popc(w1);
+  } else if (G == 4) {
+    return __popc((a[0] ^ b0.x) | (a[1] ^ b0.y)) + __popc((a[2] ^ b0.z) | (a[3] ^ b0.w)) +
+           __popc((a[4] ^ b1.x) | (a[5] ^ b1.y)) + __popc((a[6] ^ b1.z) | (a[7] ^ b1.w));
+  } else {
+    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
+           __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads, 3) scan256_kernel(const KnnParams P) {
+  __shared__ uint4 tile[kQTile * 2];
+  uint32_t a[kR][8];
+  const uint32_t row0 = blockIdx.x * kABlock + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const uint32_t row = row0 + r * kThreads;
+    uint4 v0 = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u), v1 = v0;
+    if (row < P.n_db) {
+      v0 = __ldg(P.db + 2 * size_t(row));
+      v1 = __ldg(P.db + 2 * size_t(row) + 1);
+    }
+    a[r][0] = v0.x; a[r][1] = v0.y; a[r][2] = v0.z; a[r][3] = v0.w;
+    a[r][4] = v1.x; a[r][5] = v1.y; a[r][6] = v1.z; a[r][7] = v1.w;
+  }
+  const int T = P.threshold;
+  const uint32_t q_begin = blockIdx.y * P.slab;
+  const uint32_t q_end = min(q_begin + P.slab, P.n_q);
+  for (uint32_t t0 = q_begin; t0 < q_end; t0 += kQTile) {
+    const uint32_t nq = min(uint32_t(kQTile), q_end - t0);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nq * 2; i += kThreads) tile[i] = P.q[2 * size_t(t0) + i];
+    __syncthreads();
+#pragma unroll 2
+    for (uint32_t j = 0; j < nq; ++j) {
+      const uint4 b0 = tile[2 * j], b1 = tile[2 * j + 1];
+      uint32_t p[kR];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) p[r] = bound256<G>(a[r], b0, b1);
+      uint32_t mn = p[0];
+#pragma unroll
+      for (int r = 1; r < kR; ++r) mn = min(mn, p[r]);
+      if (int(mn) < T) {
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+          if (int(p[r]) < T) emit256(P, a[r], b0, b1, row0 + r * kThreads, t0 + j);
+      }
+    }
+  }
+}
+
+int fold_for(int threshold) {
+  if (threshold <= 26) return 1;
+  if (threshold <= 50) return 2;
+  if (threshold <= 80) return 4;
+  return 8;
+}
+
+int scan256_launch(const uint8_t* d_db, uint32_t n_db, const uint8_t* d_q, uint32_t n_q, int threshold, cb_pair* out,
+                   unsigned long long cap, unsigned long long* count, cudaStream_t stream) {
+  if (!n_db || !n_q || threshold <= 0) return CB_OK;
+  KnnParams P;
+  P.db = reinterpret_cast<const uint4*>(d_db);
+  P.q = reinterpret_cast<const uint4*>(d_q);
+  P.n_db = n_db;
+  P.n_q = n_q;
+  P.threshold = threshold > 257 ? 257 : threshold;
+  P.out = out;
+  P.cap = cap;
+  P.count = count;
+  const uint32_t a_blocks = (n_db + kABlock - 1) / kABlock;
+  const uint32_t q_tiles = (n_q + kQTile - 1) / kQTile;
+  uint32_t slabs = (148u * 3u * 8u + a_blocks - 1) / a_blocks;
+  slabs = std::max(1u, std::min(std::min(slabs, q_tiles), 65535u));
+  const uint32_t tiles_per_slab = (q_tiles + slabs - 1) / slabs;
+  slabs = (q_tiles + tiles_per_slab - 1) / tiles_per_slab;
+  P.slab = tiles_per_slab * kQTile;
+  dim3 grid(a_blocks, slabs);
+  switch (fold_for(P.threshold)) {
+    case 1: scan256_kernel<1><<<grid, kThreads, 0, stream>>>(P); break;
+    case 2: scan256_kernel<2><<<grid, kThreads, 0, stream>>>(P); break;
+    case 4: scan256_kernel<4><<<grid, kThreads, 0, stream>>>(P); break;
+    default: scan256_kernel<8><<<grid, kThreads, 0, stream>>>(P); break;
+  }
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().comparisons += uint64_t(n_db) * n_q;
+  return CB_OK;
+}
+
+struct KHitLess {  // (query, dist, row)
+  __device__ __forceinline__ bool operator()(const cb_pair& x, const cb_pair& y) const {
+    if (x.b != y.b) return x.b < y.b;
+    if (x.dist != y.dist) return x.dist < y.dist;
+    return x.a < y.a;
+  }
+};
+
+}  // namespace
+
+struct OrbIndex {
+  std::vector<uint8_t> desc;                 // _descriptors: rows x 32
+  std::vector<uint32_t> first_row, media;    // _indexMap as sorted arrays: block start -> mediaId (0 = removed)
+  std::map<uint32_t, std::pair<uint32_t, uint32_t>> id_map;  // _idMap: mediaId -> (first row, rows)
+  bool loaded = false;
+  int device = 0;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> d_desc, d_q;
+  size_t d_rows = 0;
+  DevBuf<cb_pair> d_pairs;
+  DevBuf<unsigned char> d_temp;
+  DevBuf<unsigned long long> d_counts;
+  unsigned long long* h_counts = nullptr;
+
+  ~OrbIndex() {
+    if (h_counts) cudaFreeHost(h_counts);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  uint32_t rows() const { return uint32_t(desc.size() / 32); }
+
+  int init_device() {
+    int rc = ensure_device();
+    if (rc != CB_OK) return rc;
+    if (!stream) {
+      device = current_device();
+      CB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    if (!h_counts) CB_CUDA(cudaMallocHost(&h_counts, 2 * sizeof(unsigned long long)));
+    return d_counts.reserve(2);
+  }
+
+  // append rows of the device mirror (load / add)
+  int sync_to_device() {
+    int rc = init_device();
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaSetDevice(device));
+    const size_t n = rows();
+    if (n < d_rows) d_rows = 0;
+    if (n == d_rows) return CB_OK;
+    rc = d_desc.reserve(n * 32 + 32, true, stream);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(d_desc.p + d_rows * 32, desc.data() + d_rows * 32, (n - d_rows) * 32, cudaMemcpyHostToDevice, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    d_rows = n;
+    return CB_OK;
+  }
+
+  void append(const uint32_t* ids, const int64_t* offs, const uint8_t* d, int64_t n_media, bool strict) {
+    uint32_t last = 0;
+    for (int64_t m = 0; m < n_media; ++m) {
+      const int64_t r0 = offs[m], r1 = offs[m + 1];
+      if (r1 <= r0) continue;                   // empty descriptors are skipped (:207-209, :127-132)
+      if (strict && last >= ids[m]) continue;   // load(): ids must be strictly increasing (:212-219)
+      const uint32_t first = rows();
+      desc.insert(desc.end(), d + r0 * 32, d + r1 * 32);
+      first_row.push_back(first);
+      media.push_back(ids[m]);
+      id_map[ids[m]] = {first, uint32_t(r1 - r0)};
+      last = ids[m];
+    }
+  }
+
+  uint32_t media_of_row(uint32_t row) const {  // prev(_indexMap.upper_bound(row)) (:514-516)
+    auto it = std::upper_bound(first_row.begin(), first_row.end(), row);
+    if (it == first_row.begin()) return 0;
+    return media[size_t(it - first_row.begin()) - 1];
+  }
+
+  // exact neighbours with distance < threshold for every query, sorted by (query, dist, row);
+  // at most k per query are kept when k > 0.
+  int knn(const uint8_t* q, int64_t nq, int threshold, int k, std::vector<cb_pair>& out) {
+    out.clear();
+    int rc = sync_to_device();
+    if (rc != CB_OK) return rc;
+    if (!nq || !d_rows || threshold <= 0) return CB_OK;
+    rc = d_q.reserve(size_t(nq) * 32 + 32);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(d_q.p, q, size_t(nq) * 32, cudaMemcpyHostToDevice, stream));
+    unsigned long long cap = d_pairs.cap ? d_pairs.cap : (1ull << 18);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      rc = d_pairs.reserve(cap);
+      if (rc != CB_OK) return rc;
+      cap = d_pairs.cap;
+      CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 2 * sizeof(unsigned long long), stream));
+      rc = scan256_launch(d_desc.p, uint32_t(d_rows), d_q.p, uint32_t(nq), threshold, d_pairs.p, cap, d_counts.p, stream);
+      if (rc != CB_OK) return rc;
+      CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaStreamSynchronize(stream));
+      if (h_counts[0] <= cap) break;
+      cap = h_counts[0] + h_counts[0] / 8 + 1024;
+      if (attempt == 2) {
+        set_error("scan256: hit list overflow persisted");
+        return CB_ERR_CUDA;
+      }
+    }
+    const unsigned long long n = h_counts[0];
+    counters().hits += n;
+    if (!n) return CB_OK;
+    size_t tb = 0;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)nullptr, tb, d_pairs.p, (long long)n, KHitLess(), stream));
+    rc = d_temp.reserve(tb + 16);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)d_temp.p, tb, d_pairs.p, (long long)n, KHitLess(), stream));
+    std::vector<cb_pair> all(n);
+    CB_CUDA(cudaMemcpyAsync(all.data(), d_pairs.p, n * sizeof(cb_pair), cudaMemcpyDeviceToHost, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    if (k <= 0) {
+      out.swap(all);
+      return CB_OK;
+    }
+    size_t i = 0;
+    while (i < all.size()) {
+      size_t j = i;
+      while (j < all.size() && all[j].b == all[i].b) ++j;
+      for (size_t t = i; t < j && t < i + size_t(k); ++t) out.push_back(all[t]);
+      i = j;
+    }
+    return CB_OK;
+  }
+};
+
+}  // namespace cbird
+
+using namespace cbird;
+
+struct cb_orb_index {
+  OrbIndex impl;
+};
+
+extern "C" {
+
+cb_orb_index* cb_orb_index_create(void) { return new (std::nothrow) cb_orb_index; }
+
+void cb_orb_index_destroy(cb_orb_index* ix) {
+  if (!ix) return;
+  if (ix->impl.stream) cudaSetDevice(ix->impl.device);
+  delete ix;
+}
+
+static int check_media_args(const char* fn, const void* ix, const uint32_t* ids, const int64_t* offs, const uint8_t* d,
+                            int64_t n) {
+  if (!ix || n < 0 || (n && (!ids || !offs)) || (n && offs[n] > offs[0] && !d)) {
+    set_error("%s: invalid argument", fn);
+    return CB_ERR_INVALID;
+  }
+  return CB_OK;
+}
+
+int cb_orb_index_load(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
+                      int64_t n_media) {
+  int rc = check_media_args("cb_orb_index_load", ix, media_ids, row_offsets, desc, n_media);
+  if (rc != CB_OK) return rc;
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  I.desc.clear();
+  I.first_row.clear();
+  I.media.clear();
+  I.id_map.clear();
+  I.d_rows = 0;
+  I.append(media_ids, row_offsets, desc, n_media, true);
+  if (I.rows() > 0xFFFFF000u) {
+    set_error("cb_orb_index_load: too many descriptors");
+    return CB_ERR_UNSUPPORTED;
+  }
+  I.loaded = true;
+  return I.sync_to_device();
+}
+
+int cb_orb_index_add(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
+                     int64_t n_media) {
+  int rc = check_media_args("cb_orb_index_add", ix, media_ids, row_offsets, desc, n_media);
+  if (rc != CB_OK) return rc;
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  I.append(media_ids, row_offsets, desc, n_media, false);  // :122-152
+  I.loaded = true;
+  return I.sync_to_device();
+}
+
+int cb_orb_index_remove(cb_orb_index* ix, const int32_t* ids, int64_t n) {
+  if (!ix || n < 0 || (n && !ids)) {
+    set_error("cb_orb_index_remove: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  for (int64_t i = 0; i < n; ++i) {  // rows stay, their block maps to media 0 (:154-165)
+    auto it = I.id_map.find(uint32_t(ids[i]));
+    if (it == I.id_map.end()) continue;
+    auto b = std::lower_bound(I.first_row.begin(), I.first_row.end(), it->second.first);
+    if (b != I.first_row.end() && *b == it->second.first) I.media[size_t(b - I.first_row.begin())] = 0;
+  }
+  return CB_OK;
+}
+
+/* isLoaded(): `_index != nullptr`, i.e. a search structure exists: loaded and at least one row (:102, :320-323) */
+int cb_orb_index_is_loaded(const cb_orb_index* ix) { return ix && ix->impl.loaded && ix->impl.rows() > 0 ? 1 : 0; }
+int64_t cb_orb_index_count(const cb_orb_index* ix) { return ix ? int64_t(ix->impl.rows()) : 0; }  // :104
+size_t cb_orb_index_memory_usage(const cb_orb_index* ix) {                                          // :106-120
+  return ix ? size_t(ix->impl.rows()) * 32 * 2 : 0;
+}
+
+int cb_orb_index_descriptors(const cb_orb_index* ix, uint32_t media_id, uint8_t* out, int64_t cap_rows, int64_t* n_rows) {
+  if (!ix || !n_rows) return CB_ERR_INVALID;
+  const OrbIndex& I = ix->impl;
+  *n_rows = 0;
+  auto it = I.id_map.find(media_id);
+  if (it == I.id_map.end()) return CB_OK;  // empty Mat (:421-423)
+  *n_rows = it->second.second;
+  if (out) {
+    if (cap_rows < *n_rows) return CB_ERR_CAPACITY;
+    memcpy(out, I.desc.data() + size_t(it->second.first) * 32, size_t(it->second.second) * 32);
+  }
+  return CB_OK;
+}
+
+cb_orb_index* cb_orb_index_slice(const cb_orb_index* ix, const uint32_t* ids, int64_t n) {
+  if (!ix || n < 0 || (n && !ids)) return nullptr;
+  cb_orb_index* out = new (std::nothrow) cb_orb_index;
+  if (!out) return nullptr;
+  const OrbIndex& S = ix->impl;
+  OrbIndex& I = out->impl;
+  std::vector<uint32_t> values(ids, ids + n);
+  std::sort(values.begin(), values.end());  // :291-292
+  values.erase(std::unique(values.begin(), values.end()), values.end());
+  for (uint32_t id : values) {
+    auto it = S.id_map.find(id);
+    if (it == S.id_map.end() || it->second.second == 0) continue;
+    const int64_t offs[2] = {0, int64_t(it->second.second)};
+    I.append(&id, offs, S.desc.data() + size_t(it->second.first) * 32, 1, false);
+  }
+  I.loaded = true;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (I.sync_to_device() != CB_OK) {
+    delete out;
+    return nullptr;
+  }
+  return out;
+}
+
+int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, int k, int threshold, cb_pair** out,
+                           int64_t* n_out) {
+  if (!ix || !out || !n_out || n_rows < 0 || (n_rows && !desc)) {
+    set_error("cb_orb_index_knn_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  std::vector<cb_pair> hits;
+  int rc = I.knn(desc, n_rows, threshold, k, hits);
+  if (rc != CB_OK) return rc;
+  for (auto& h : hits) h.pad_ = I.media_of_row(h.a);  // media id of the row travels in the 4th word
+  *n_out = int64_t(hits.size());
+  *out = static_cast<cb_pair*>(malloc(std::max<size_t>(1, hits.size()) * sizeof(cb_pair)));
+  if (!*out) {
+    set_error("out of host memory");
+    return CB_ERR_INVALID;
+  }
+  if (!hits.empty()) memcpy(*out, hits.data(), hits.size() * sizeof(cb_pair));
+  return CB_OK;
+}
+
+int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uint32_t needle_id, const cb_params* p,
+                      cb_match* out, int64_t cap, int64_t* n_out) {
+  if (!ix || !p || !n_out || n_rows < 0) {
+    set_error("cb_orb_index_find: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  *n_out = 0;
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  std::vector<uint8_t> own;
+  if (!desc || n_rows <= 0) {  // descriptorsForMediaId(needle.id()) (:442-444)
+    auto it = I.id_map.find(needle_id);
+    if (it == I.id_map.end()) return CB_OK;  // "needle has no descriptors" (:446-449)
+    own.assign(I.desc.begin() + size_t(it->second.first) * 32,
+               I.desc.begin() + size_t(it->second.first + it->second.second) * 32);
+    desc = own.data();
+    n_rows = it->second.second;
+  }
+  if (n_rows <= 0 || I.rows() == 0) return CB_OK;  // "empty index" (:451-454)
+  std::vector<cb_pair> hits;
+  int rc = I.knn(desc, n_rows, p->cvThresh, 10, hits);  // k = 10 (:497), distance < cvThresh (:511)
+  if (rc != CB_OK) return rc;
+  std::map<uint32_t, std::vector<int>> matches;
+  for (const cb_pair& h : hits) {
+    const uint32_t mediaId = I.media_of_row(h.a);
+    if (!mediaId) continue;  // removed item (:519)
+    matches[mediaId].push_back(int(h.dist));
+  }
+  int64_t k = 0;
+  for (auto& kv : matches) {  // median score x1000 / count (:571-596)
+    std::vector<int>& s = kv.second;
+    std::sort(s.begin(), s.end());
+    int score;
+    const size_t mid = s.size() / 2;
+    if (s.size() < 2) score = s[0];
+    else if (s.size() % 2 == 0) score = (s[mid - 1] + s[mid]) / 2;
+    else score = s[mid];
+    score = score * 1000 / int(s.size());
+    if (k < cap) out[k] = cb_match{kv.first, score, -1, -1, 0};
+    ++k;
+  }
+  *n_out = k;
+  return k > cap ? CB_ERR_CAPACITY : CB_OK;
+}
+
+}  // extern "C"

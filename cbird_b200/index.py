@@ -299,3 +299,98 @@ class DctVideoIndex:
         ro = _lib.take_array(po.value, len(needles) + 1, np.dtype(np.int64))
         mm = _lib.take_array(pm.value, n.value, _lib.MATCH_DTYPE)
         return [_matches_from(mm[ro[k]:ro[k + 1]]) for k in range(len(needles))]
+
+
+def _pack_descriptors(ids, descs):
+    offs = np.zeros(len(ids) + 1, np.int64)
+    for i, d in enumerate(descs):
+        offs[i + 1] = offs[i] + (0 if d is None else len(d))
+    parts = [np.asarray(d, np.uint8).reshape(-1, 32) for d in descs if d is not None and len(d)]
+    flat = np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros((0, 32), np.uint8))
+    return _u32(ids), offs, flat
+
+
+class CvFeaturesIndex:
+    """Drop-in for src/cvfeaturesindex.{h,cpp}: 256-bit ORB descriptors, exact k=10 search under odt."""
+
+    def __init__(self, _handle=None):
+        self._L = lib()
+        self._h = _handle if _handle is not None else self._L.cb_orb_index_create()
+        if not self._h:
+            raise _lib.CbirdError(-3, "cb_orb_index_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.cb_orb_index_destroy(h)
+
+    def id(self):
+        return SearchParams.AlgoCVFeatures
+
+    def isLoaded(self) -> bool:
+        return bool(self._L.cb_orb_index_is_loaded(self._h))
+
+    def count(self) -> int:
+        return int(self._L.cb_orb_index_count(self._h))
+
+    def memoryUsage(self) -> int:
+        return int(self._L.cb_orb_index_memory_usage(self._h))
+
+    def load(self, ids, descriptors):
+        """load(): the (media_id, matrix) rows the reference SELECTs ordered by media_id (:189)."""
+        i, o, f = _pack_descriptors(ids, descriptors)
+        check(self._L.cb_orb_index_load(self._h, i.ctypes.data, o.ctypes.data, f.ctypes.data, len(i)))
+
+    def save(self):
+        """cache files are out of scope; nothing to do."""
+
+    def add(self, media: List[Media]):
+        i, o, f = _pack_descriptors([m.id for m in media], [m.descriptors for m in media])
+        check(self._L.cb_orb_index_add(self._h, i.ctypes.data, o.ctypes.data, f.ctypes.data, len(i)))
+
+    def remove(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        check(self._L.cb_orb_index_remove(self._h, a.ctypes.data, len(a)))
+
+    def slice(self, mediaIds) -> "CvFeaturesIndex":
+        a = _u32(sorted(mediaIds))
+        h = self._L.cb_orb_index_slice(self._h, a.ctypes.data, len(a))
+        if not h:
+            raise _lib.CbirdError(-3, "cb_orb_index_slice failed")
+        return CvFeaturesIndex(_handle=h)
+
+    def findIndexData(self, m: Media) -> bool:
+        """findIndexData(): populate the descriptors stored in the index for m.id (:96-100)."""
+        n = C.c_int64(0)
+        check(self._L.cb_orb_index_descriptors(self._h, int(m.id), None, 0, C.byref(n)))
+        if n.value <= 0:
+            return False
+        out = np.zeros((n.value, 32), np.uint8)
+        check(self._L.cb_orb_index_descriptors(self._h, int(m.id), out.ctypes.data, n.value, C.byref(n)))
+        m.descriptors = out
+        return True
+
+    def find(self, needle: Media, params: SearchParams) -> List[Match]:
+        p = params.to_c()
+        cap = 1024
+        d = None
+        if needle.descriptors is not None and len(needle.descriptors):
+            d = np.ascontiguousarray(needle.descriptors, dtype=np.uint8).reshape(-1, 32)
+        while True:
+            out = np.zeros(cap, _lib.MATCH_DTYPE)
+            n = C.c_int64(0)
+            rc = self._L.cb_orb_index_find(self._h, d.ctypes.data if d is not None else None, len(d) if d is not None else 0,
+                                           int(needle.id), C.byref(p), out.ctypes.data, cap, C.byref(n))
+            if rc == -4:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return _matches_from(out[: n.value])
+
+    def knn(self, descriptors, k=10, threshold=25) -> np.ndarray:
+        """exact k nearest rows under the threshold per needle row: structured (a=row, b=needle row, dist,
+        pad=media id), sorted by (needle row, dist, row)."""
+        d = np.ascontiguousarray(descriptors, dtype=np.uint8).reshape(-1, 32)
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_orb_index_knn_alloc(self._h, d.ctypes.data, len(d), int(k), int(threshold), C.byref(ptr), C.byref(n)))
+        return _lib.take_array(ptr.value, n.value, _lib.PAIR_DTYPE)

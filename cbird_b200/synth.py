@@ -113,3 +113,24 @@ def video_needles(ids, tables, n_copies, n_unrelated, frames_per_video, seed):
             f, h = other[k]
             out.append((0, f, h, 0))
     return out
+
+
+def orb_descriptors(n_media, rows_per_media, seed, planted_frac=0.05, max_flips=24, first_id=1):
+    """cfg5-style ORB index: n_media x rows_per_media uniform random 256-bit descriptors, a fraction
+    planted as near-copies (<= max_flips flipped bits) of other rows.  Returns (ids, [desc u8[r,32]...])."""
+    rng = np.random.default_rng(seed)
+    n = n_media * rows_per_media
+    d = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    n_plant = int(n * planted_frac)
+    if n_plant and n > 1:
+        dst = rng.choice(n, size=n_plant, replace=False)
+        src = rng.integers(0, n, size=n_plant)
+        v = d[src].copy()
+        flips = rng.integers(0, max_flips + 1, size=n_plant)
+        for k in range(max_flips):
+            bit = rng.integers(0, 256, size=n_plant)
+            on = flips > k
+            v[np.arange(n_plant)[on], bit[on] >> 3] ^= (1 << (bit[on] & 7)).astype(np.uint8)
+        d[dst] = v
+    ids = np.arange(first_id, first_id + n_media, dtype=np.uint32)
+    return ids, [d[i * rows_per_media:(i + 1) * rows_per_media] for i in range(n_media)]

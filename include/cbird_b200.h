@@ -196,6 +196,37 @@ int cb_video_index_find_videos_alloc(cb_video_index* ix, const int64_t* needle_o
 int cb_video_index_find_frame(cb_video_index* ix, uint64_t hash, int32_t needle_dst_in, const cb_params* p,
                               cb_match* out, int64_t cap, int64_t* n_out);
 
+/* ---- CvFeaturesIndex (src/cvfeaturesindex.{h,cpp}): 256-bit ORB descriptors, kernel (c) ----------
+ * Descriptors are rows of 32 bytes (cv::Mat N x 32 CV_8U); media m owns rows
+ * [row_offsets[m], row_offsets[m+1]) of `desc`.  The reference's flann LSH knnSearch(k=10) (:497) is
+ * replaced by an exact search; everything else (row->media maps, removal, threshold, median score)
+ * follows the cited lines. */
+typedef struct cb_orb_index cb_orb_index;
+cb_orb_index* cb_orb_index_create(void);
+void cb_orb_index_destroy(cb_orb_index* ix);
+/* load(): media in ascending id order, empty or out-of-order entries are ignored      :167-250 */
+int cb_orb_index_load(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
+                      int64_t n_media);
+int cb_orb_index_add(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
+                     int64_t n_media);                                          /* :122-152 */
+int cb_orb_index_remove(cb_orb_index* ix, const int32_t* ids, int64_t n);       /* :154-165 */
+int cb_orb_index_is_loaded(const cb_orb_index* ix);                              /* :102     */
+int64_t cb_orb_index_count(const cb_orb_index* ix);       /* count() = number of descriptors :104 */
+size_t cb_orb_index_memory_usage(const cb_orb_index* ix); /* 2 x rows x 32            :106-120 */
+cb_orb_index* cb_orb_index_slice(const cb_orb_index* ix, const uint32_t* ids, int64_t n);   /* :285-309 */
+/* descriptorsForMediaId() / findIndexData(): rows of one media                     :421-436 */
+int cb_orb_index_descriptors(const cb_orb_index* ix, uint32_t media_id, uint8_t* out, int64_t cap_rows,
+                             int64_t* n_rows);
+/* find(): needle = n_rows descriptors (or desc==NULL: the indexed descriptors of needle_id).
+ * One match per media: score = median(distances) * 1000 / count, ascending mediaId.   :438-604 */
+int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uint32_t needle_id, const cb_params* p,
+                      cb_match* out, int64_t cap, int64_t* n_out);
+/* the exact k nearest rows with distance < threshold of every needle row: cb_pair{a = row, b = needle
+ * row, dist, pad_ = media id of the row (0 = removed)}, sorted by (needle row, dist, row); k<=0 = all.
+ * Building block for sharded search: per-shard lists are merged by (dist, row) and cut at k. */
+int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, int k, int threshold,
+                           cb_pair** out, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

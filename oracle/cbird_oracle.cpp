@@ -620,4 +620,140 @@ long long orc_video_bucket_search(void* p, uint64_t hash, int thr, int skipFrame
   return k;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CvFeaturesIndex — src/cvfeaturesindex.cpp.  The reference answers knnSearch (:497) with an
+// OpenCV flann LSH index (approximate, randomised per build: unpinnable); the restatement
+// answers it EXACTLY (brute force, ties by ascending row) and keeps everything else — row->media
+// maps, removal semantics, threshold, median scoring — as the cited lines have it.
+// ---------------------------------------------------------------------------------------------
+struct OrcOrbIndex {
+  std::vector<uint8_t> desc;            // _descriptors, rows x 32 (cv::Mat CV_8U)
+  std::map<uint32_t, uint32_t> idMap;   // mediaId -> first row   (:226-227)
+  std::map<uint32_t, uint32_t> indexMap;  // first row -> mediaId (0 = removed)
+  std::map<uint32_t, uint32_t> rowsOf;  // mediaId -> row count (descriptorsForMediaId without the
+                                        // "next key" trick, which breaks after add() of a smaller id)
+  uint32_t rows() const { return uint32_t(desc.size() / 32); }
+};
+
+static inline int hamm256(const uint8_t* a, const uint8_t* b) {
+  const uint64_t* x = reinterpret_cast<const uint64_t*>(a);
+  const uint64_t* y = reinterpret_cast<const uint64_t*>(b);
+  uint64_t v[4];
+  memcpy(v, x, 32);
+  uint64_t w[4];
+  memcpy(w, y, 32);
+  return __builtin_popcountll(v[0] ^ w[0]) + __builtin_popcountll(v[1] ^ w[1]) + __builtin_popcountll(v[2] ^ w[2]) +
+         __builtin_popcountll(v[3] ^ w[3]);
+}
+
+void* orc_orb_create() { return new OrcOrbIndex; }
+void orc_orb_destroy(void* p) { delete static_cast<OrcOrbIndex*>(p); }
+
+// load() (:167-250) and add() (:122-152) share the append step; `strict` enforces load()'s
+// "ids strictly increasing, rows > 0" rule (:212-219)
+static void orb_append(OrcOrbIndex* ix, const uint32_t* ids, const long long* row_offsets, const uint8_t* desc,
+                       long long n_media, bool strict) {
+  uint32_t lastId = 0;
+  for (long long m = 0; m < n_media; ++m) {
+    const long long r0 = row_offsets[m], r1 = row_offsets[m + 1];
+    if (r1 <= r0) continue;  // "skip empty descriptors" :207-209 / "no descriptors for" :127-132
+    if (strict && lastId >= ids[m]) continue;
+    const uint32_t first = ix->rows();
+    ix->desc.insert(ix->desc.end(), desc + r0 * 32, desc + r1 * 32);
+    ix->idMap[ids[m]] = first;
+    ix->indexMap[first] = ids[m];
+    ix->rowsOf[ids[m]] = uint32_t(r1 - r0);
+    lastId = ids[m];
+  }
+  ix->idMap[UINT32_MAX] = ix->rows();  // trailing values :244-245 / :139-140
+  ix->indexMap[ix->rows()] = 0;
+}
+void orc_orb_load(void* p, const uint32_t* ids, const long long* row_offsets, const uint8_t* desc, long long n_media) {
+  OrcOrbIndex* ix = static_cast<OrcOrbIndex*>(p);
+  ix->desc.clear();
+  ix->idMap.clear();
+  ix->indexMap.clear();
+  ix->rowsOf.clear();
+  orb_append(ix, ids, row_offsets, desc, n_media, true);
+}
+void orc_orb_add(void* p, const uint32_t* ids, const long long* row_offsets, const uint8_t* desc, long long n_media) {
+  OrcOrbIndex* ix = static_cast<OrcOrbIndex*>(p);
+  if (ix->indexMap.count(ix->rows()) && ix->indexMap[ix->rows()] == 0) ix->indexMap.erase(ix->rows());
+  orb_append(ix, ids, row_offsets, desc, n_media, false);
+}
+void orc_orb_remove(void* p, const int* ids, long long n) {  // :154-165
+  OrcOrbIndex* ix = static_cast<OrcOrbIndex*>(p);
+  for (long long i = 0; i < n; ++i) {
+    auto it = ix->idMap.find(uint32_t(ids[i]));
+    if (it != ix->idMap.end()) {
+      auto it2 = ix->indexMap.find(it->second);
+      if (it2 != ix->indexMap.end()) it2->second = 0;
+    }
+  }
+}
+long long orc_orb_count(void* p) { return static_cast<OrcOrbIndex*>(p)->rows(); }
+
+// exact k nearest rows of every query (ties: ascending row), -1 padding like flann (:502-506)
+void orc_knn256(const uint8_t* db, long long n_db, const uint8_t* q, long long n_q, int k, int* out_idx, int* out_dist) {
+  std::vector<std::pair<int, int>> all;
+  for (long long i = 0; i < n_q; ++i) {
+    all.clear();
+    for (long long r = 0; r < n_db; ++r) all.push_back({hamm256(q + i * 32, db + r * 32), int(r)});
+    const size_t kk = std::min<size_t>(k, all.size());
+    std::partial_sort(all.begin(), all.begin() + kk, all.end());
+    for (int j = 0; j < k; ++j) {
+      out_idx[i * k + j] = j < int(kk) ? all[j].second : -1;
+      out_dist[i * k + j] = j < int(kk) ? all[j].first : 0;
+    }
+  }
+}
+
+// find() :438-604. needle descriptors given explicitly, or (desc==NULL) taken from the index by
+// needle_id (descriptorsForMediaId :421-436).
+long long orc_orb_find(void* p, const uint8_t* desc, long long n_rows, uint32_t needle_id, int cvThresh, OrcMatch* out,
+                       long long cap) {
+  OrcOrbIndex* ix = static_cast<OrcOrbIndex*>(p);
+  std::vector<uint8_t> own;
+  if (!desc || n_rows <= 0) {
+    auto it = ix->idMap.find(needle_id);
+    if (it == ix->idMap.end() || needle_id == UINT32_MAX) return 0;  // "needle has no descriptors" :446-449
+    const uint32_t first = it->second, cnt = ix->rowsOf[needle_id];
+    own.assign(ix->desc.begin() + size_t(first) * 32, ix->desc.begin() + size_t(first + cnt) * 32);
+    desc = own.data();
+    n_rows = cnt;
+  }
+  if (n_rows <= 0 || ix->rows() == 0) return 0;  // "empty index" :451-454
+  const int K = 10;                               // :497
+  std::vector<int> idx(size_t(n_rows) * K), dist(size_t(n_rows) * K);
+  orc_knn256(ix->desc.data(), ix->rows(), desc, n_rows, K, idx.data(), dist.data());
+  std::map<uint32_t, std::vector<int>> matches;  // QMap<uint32_t, Match_> :485
+  for (long long i = 0; i < n_rows; ++i)
+    for (int j = 0; j < K; ++j) {
+      const int index = idx[i * K + j];
+      if (index < 0) continue;                  // :502-506
+      const int distance = dist[i * K + j];
+      if (distance >= cvThresh) continue;       // :511
+      auto it = ix->indexMap.upper_bound(uint32_t(index));  // :514-516
+      --it;
+      const uint32_t mediaId = it->second;
+      if (!mediaId) continue;                   // removed item :519
+      matches[mediaId].push_back(distance);
+    }
+  long long k = 0;
+  for (auto& kv : matches) {  // :571-596
+    std::vector<int>& scores = kv.second;
+    std::sort(scores.begin(), scores.end());
+    int score;
+    const size_t middle = scores.size() / 2;
+    if (scores.size() < 2) score = scores[0];
+    else if (scores.size() % 2 == 0) score = (scores[middle - 1] + scores[middle]) / 2;
+    else score = scores[middle];
+    score = score * 1000 / int(scores.size());  // :592
+    if (k < cap) out[k] = OrcMatch{kv.first, score, -1, -1, 0};
+    ++k;
+  }
+  return k;
+}
+
 }  // extern "C"

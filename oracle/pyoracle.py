@@ -66,6 +66,16 @@ def oracle():
         L.orc_video_bucket_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, _u32p, _i32p, _i32p,
                                               C.c_longlong]
         L.orc_video_bucket_search.restype = C.c_longlong
+        L.orc_orb_create.restype = C.c_void_p
+        L.orc_orb_destroy.argtypes = [C.c_void_p]
+        L.orc_orb_load.argtypes = [C.c_void_p, _u32p, C.c_void_p, C.c_void_p, C.c_longlong]
+        L.orc_orb_add.argtypes = [C.c_void_p, _u32p, C.c_void_p, C.c_void_p, C.c_longlong]
+        L.orc_orb_remove.argtypes = [C.c_void_p, _i32p, C.c_longlong]
+        L.orc_orb_count.argtypes = [C.c_void_p]
+        L.orc_orb_count.restype = C.c_longlong
+        L.orc_knn256.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, _i32p, _i32p]
+        L.orc_orb_find.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint32, C.c_int, C.c_void_p, C.c_longlong]
+        L.orc_orb_find.restype = C.c_longlong
         _oracle = L
     return _oracle
 
@@ -239,3 +249,58 @@ class OracleVideoIndex:
         n = self.L.orc_video_bucket_search(self.h, int(hash_), thr, skip, vradix, idx, fr, d, cap)
         assert n <= cap
         return idx[:n], fr[:n], d[:n]
+
+
+def knn256(db, q, k=10):
+    db = np.ascontiguousarray(db, np.uint8)
+    q = np.ascontiguousarray(q, np.uint8)
+    idx = np.zeros(len(q) * k, np.int32)
+    dist = np.zeros(len(q) * k, np.int32)
+    oracle().orc_knn256(db.ctypes.data, len(db), q.ctypes.data, len(q), k, idx, dist)
+    return idx.reshape(len(q), k), dist.reshape(len(q), k)
+
+
+class OracleOrbIndex:
+    """restated CvFeaturesIndex with exact kNN (oracle/cbird_oracle.cpp, src/cvfeaturesindex.cpp)."""
+
+    def __init__(self):
+        self.L = oracle()
+        self.h = self.L.orc_orb_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_orb_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _pack(ids, descs):
+        offs = np.zeros(len(ids) + 1, np.int64)
+        for i, d in enumerate(descs):
+            offs[i + 1] = offs[i] + len(d)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(d, np.uint8).reshape(-1, 32) for d in descs])
+                                    if len(descs) else np.zeros((0, 32), np.uint8))
+        return np.ascontiguousarray(ids, np.uint32), offs, flat
+
+    def load(self, ids, descs):
+        i, o, f = self._pack(ids, descs)
+        self.L.orc_orb_load(self.h, i, o.ctypes.data, f.ctypes.data, len(i))
+
+    def add(self, ids, descs):
+        i, o, f = self._pack(ids, descs)
+        self.L.orc_orb_add(self.h, i, o.ctypes.data, f.ctypes.data, len(i))
+
+    def remove(self, ids):
+        self.L.orc_orb_remove(self.h, np.ascontiguousarray(ids, np.int32), len(ids))
+
+    def count(self):
+        return int(self.L.orc_orb_count(self.h))
+
+    def find(self, desc, needle_id=0, odt=25):
+        out = np.zeros(1 << 16, ORC_MATCH)
+        if desc is None:
+            n = self.L.orc_orb_find(self.h, None, 0, int(needle_id), odt, out.ctypes.data, len(out))
+        else:
+            d = np.ascontiguousarray(desc, np.uint8)
+            n = self.L.orc_orb_find(self.h, d.ctypes.data, len(d), int(needle_id), odt, out.ctypes.data, len(out))
+        assert n <= len(out)
+        return out[:n].copy()

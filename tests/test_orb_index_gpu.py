@@ -1,0 +1,135 @@
+"""GPU parity: CvFeaturesIndex through the C ABI (kernel (c): exact 256-bit matcher).
+ * exact kNN == cv2.BFMatcher golden vectors (distances and rows);
+ * find() == the oracle's restated find() (same maps/threshold/median arithmetic), BASELINE cfg5 shape
+   at a size the oracle finishes in seconds;
+ * every prefilter fold width gives the same hit set."""
+import os
+
+import numpy as np
+import pytest
+
+from cbird_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rows_of(matches):
+    return [(m.mediaId, m.score, m.range.srcIn, m.range.dstIn, m.range.len) for m in matches]
+
+
+def orc_rows(arr):
+    return [(int(m["mediaId"]), int(m["score"]), int(m["srcIn"]), int(m["dstIn"]), int(m["len"])) for m in arr]
+
+
+def test_knn_equals_bfmatcher_golden(cb):
+    g = np.load(os.path.join(GOLD, "knn256_cv2.npz"))
+    db, q = g["db"], g["q"]
+    ix = cb.CvFeaturesIndex()
+    assert not ix.isLoaded() and ix.count() == 0 and ix.memoryUsage() == 0
+    ix.load([1], [db])
+    assert ix.isLoaded() and ix.count() == len(db) and ix.memoryUsage() == 2 * 32 * len(db)
+    for thr in (26, 40, 70, 257):  # fold widths 1, 2, 4, exact
+        hits = ix.knn(q, k=10, threshold=thr)
+        for i in range(len(q)):
+            want = [(int(r), int(d)) for r, d in zip(g["idx"][i], g["dist"][i]) if d < thr]
+            got = [(int(h["a"]), int(h["dist"])) for h in hits[hits["b"] == i]]
+            assert got == want, (thr, i)
+    assert len(ix.knn(q, k=10, threshold=0)) == 0
+
+
+@pytest.fixture(scope="module")
+def orb(cb, po):
+    ids, descs = synth.orb_descriptors(300, 100, seed=5)
+    gx, ox = cb.CvFeaturesIndex(), po.OracleOrbIndex()
+    gx.load(ids, descs)
+    ox.load(ids, descs)
+    return ids, descs, gx, ox
+
+
+@pytest.mark.parametrize("odt", [25, 10, 45, 90])
+def test_find_matches_oracle(cb, orb, odt):
+    ids, descs, gx, ox = orb
+    rng = np.random.default_rng(odt)
+    nonempty = 0
+    for k in range(12):
+        src = descs[int(rng.integers(0, len(descs)))]
+        needle = src.copy()
+        for r in range(len(needle)):  # perturbed copy of an indexed image
+            for b in rng.integers(0, 256, size=int(rng.integers(0, 20))):
+                needle[r, b >> 3] ^= np.uint8(1 << (b & 7))
+        got = rows_of(gx.find(cb.Media(id=0, descriptors=needle), cb.SearchParams(cvThresh=odt)))
+        want = orc_rows(ox.find(needle, 0, odt=odt))
+        assert got == want
+        nonempty += bool(got)
+    assert nonempty >= 10
+    unrelated = np.random.default_rng(99).integers(0, 256, size=(50, 32), dtype=np.uint8)
+    assert rows_of(gx.find(cb.Media(descriptors=unrelated), cb.SearchParams(cvThresh=odt))) == orc_rows(ox.find(unrelated, 0, odt=odt))
+
+
+def test_indexed_needle_add_remove_slice(cb, po):
+    ids, descs = synth.orb_descriptors(60, 40, seed=8)
+    gx, ox = cb.CvFeaturesIndex(), po.OracleOrbIndex()
+    gx.load(ids[:50], descs[:50])
+    ox.load(ids[:50], descs[:50])
+    gx.add([cb.Media(id=int(i), descriptors=d) for i, d in zip(ids[50:], descs[50:])])
+    ox.add(ids[50:], descs[50:])
+    assert gx.count() == ox.count() == 60 * 40
+    sp = cb.SearchParams(cvThresh=25)
+    for vid in (int(ids[0]), int(ids[33]), int(ids[55])):
+        got = rows_of(gx.find(cb.Media(id=vid), sp))  # descriptors come from the index (:442-444)
+        assert got == orc_rows(ox.find(None, vid, odt=25))
+        assert (vid, 0, -1, -1, 0) in got  # an indexed image matches itself with score 0
+        m = cb.Media(id=vid)
+        assert gx.findIndexData(m) and np.array_equal(m.descriptors, descs[list(ids).index(vid)])
+    assert gx.find(cb.Media(id=123456), sp) == []  # "needle has no descriptors"
+    gone = [int(ids[33]), int(ids[55])]
+    gx.remove(gone)
+    ox.remove(gone)
+    assert gx.count() == 60 * 40  # rows stay, their media id becomes 0 (:154-165)
+    for vid in (int(ids[0]), int(ids[33])):
+        got = rows_of(gx.find(cb.Media(id=vid), sp))
+        assert got == orc_rows(ox.find(None, vid, odt=25))
+        assert not {g[0] for g in got} & set(gone)
+    sl = gx.slice([int(x) for x in ids[:10]])
+    assert sl.isLoaded() and sl.count() == 400
+    got = rows_of(sl.find(cb.Media(descriptors=descs[3]), sp))
+    assert (int(ids[3]), 0, -1, -1, 0) in got and all(g[0] <= int(ids[9]) for g in got)
+    # media without descriptors are skipped, ids out of order ignored by load() (:207-219)
+    g2, o2 = cb.CvFeaturesIndex(), po.OracleOrbIndex()
+    g2.load([5, 3, 9, 12], [descs[0], descs[1], descs[2][:0], descs[3]])
+    o2.load([5, 3, 9, 12], [descs[0], descs[1], descs[2][:0], descs[3]])
+    assert g2.count() == o2.count() == 80
+    assert rows_of(g2.find(cb.Media(descriptors=descs[1]), sp)) == orc_rows(o2.find(descs[1], 0, odt=25))
+
+
+def test_empty(cb):
+    ix = cb.CvFeaturesIndex()
+    ix.load([], [])
+    assert not ix.isLoaded() and ix.count() == 0
+    d = np.zeros((4, 32), np.uint8)
+    assert ix.find(cb.Media(descriptors=d), cb.SearchParams()) == []
+    ix.add([cb.Media(id=7, descriptors=d)])
+    assert ix.isLoaded() and [m.mediaId for m in ix.find(cb.Media(descriptors=d), cb.SearchParams())] == [7]
+
+
+def test_large_exactness_property(cb):
+    # 2M rows: every planted needle row is found at its exact distance; prefilter == exact kernel
+    rng = np.random.default_rng(12)
+    n = 1 << 21
+    db = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    rows = rng.choice(n, size=400, replace=False)
+    q = db[rows].copy()
+    nflip = rng.integers(0, 24, size=400)
+    for i in range(400):
+        for b in rng.choice(256, size=int(nflip[i]), replace=False):
+            q[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    ix = cb.CvFeaturesIndex()
+    ix.load([1], [db])
+    fast = ix.knn(q, k=10, threshold=25)
+    exact = ix.knn(q, k=10, threshold=257)
+    exact = exact[exact["dist"] < 25]
+    assert np.array_equal(fast, exact)
+    best = {int(h["b"]): h for h in fast[::-1]}
+    for i in range(400):
+        assert int(best[i]["a"]) == int(rows[i]) and int(best[i]["dist"]) == int(nflip[i])

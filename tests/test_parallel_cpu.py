@@ -1,0 +1,80 @@
+"""CPU, world_size 2 over gloo: the N>1 host path — row sharding + all-gather of per-shard hit lists
+ — with the per-shard lists produced by the ORACLE (tests may use it; the product's scan
+needs a GPU).  The merged multiset must equal the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import pyoracle as po
+    from cbird_b200 import parallel, synth
+
+    h, ids = synth.dct_hashes(n, seed=1)
+    b, e = parallel.shard_rows(n, rank, world)
+    assert b % 2 == 0
+    trip, total, _ = po.dct_find_batch(h[b:e], np.arange(b, e, dtype=np.uint32) + 1, h, 5)  # needles = all rows
+    local = torch.from_numpy(np.stack([trip[:, 0], trip[:, 1] - 1, trip[:, 2], np.zeros(len(trip), np.int64)], 1).astype(np.int32))
+    merged = parallel.allgather_hits(local)
+    np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged.numpy())
+    empty = parallel.allgather_hits(local[:0])
+    assert empty.shape[0] == 0
+    # ragged: only rank 1 contributes
+    rag = parallel.allgather_hits(local if rank == 1 else local[:0])
+    assert rag.shape[0] == (local.shape[0] if rank == 1 else rag.shape[0])
+    np.save(os.path.join(out_dir, "ragged_%d.npy" % rank), rag.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_all_pairs_merge(tmp_path, po):
+    n, world = 3001, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    from cbird_b200 import synth
+
+    h, ids = synth.dct_hashes(n, seed=1)
+    want, total, _ = po.dct_find_batch(h, ids, h, 5)
+    want = want.copy()
+    want[:, 1] -= 1  # rows instead of ids
+    for r in range(world):
+        m = np.load(tmp_path / ("merged_%d.npy" % r)).astype(np.int64)
+        assert len(m) == total
+        m = m[np.lexsort((m[:, 2], m[:, 1], m[:, 0]))][:, :3]
+        assert np.array_equal(m, want)
+    r0, r1 = np.load(tmp_path / "ragged_0.npy"), np.load(tmp_path / "ragged_1.npy")
+    assert np.array_equal(r0, r1) and len(r0) > 0
+
+
+def test_shard_rows_cover_everything():
+    from cbird_b200 import parallel
+
+    for n in (0, 1, 2, 7, 4096, 1048576, 1482911, 2965821):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1 and b0 <= e0
+            assert all(b % 2 == 0 or b == n for b, _ in spans)
