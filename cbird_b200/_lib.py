@@ -86,6 +86,12 @@ SIGNATURES = {
     "cb_video_index_find_video": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
     "cb_video_index_find_videos_alloc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_video_index_find_frame": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_video_index_set_video_file": (C.c_int, [_vp, C.c_uint32, C.c_char_p]),
+    "cb_vdx_decode_alloc": (C.c_int, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(C.c_int)]),
+    "cb_vdx_encode_alloc": (C.c_int, [_vp, _vp, _i64, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_vdx_is_valid": (C.c_int, [_vp, _i64]),
+    "cb_vdx_load_alloc": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(C.c_int)]),
+    "cb_vdx_save": (C.c_int, [C.c_char_p, _vp, _vp, _i64, C.c_char_p]),
     "cb_orb_index_create": (_vp, []),
     "cb_orb_index_destroy": (None, [_vp]),
     "cb_orb_index_load": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),

@@ -382,10 +382,17 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   std::lock_guard<std::mutex> lock(I.mu);
   const int64_t n = int64_t(I.hashes.size());
   std::vector<cb_hit> hits;
-  int rc = run_find_batch(I, nullptr, 0, p->dctThresh, 0, n, true, p->filterSelf != 0, hits);
+  // maxThresh escalation (database.cpp:1703-1725): the reference re-runs find() with dht+1, dht+2, ...
+  // while the needle has <= minMatches matches (self included) and the threshold stays <= maxThresh.
+  // One scan at the largest threshold any needle can reach gives every one of those result sets.
+  const int dht = p->dctThresh;
+  const bool escalate = p->maxThresh > 0 && p->maxThresh > dht;
+  const int scan_thresh = escalate ? p->maxThresh : dht;
+  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, hits);
   if (rc != CB_OK) return rc;
   // searchIndex post step (database.cpp:1729-1737): hits are already sorted by (needle, score, id);
-  // cut every needle's list at maxMatches. Needles without hash find nothing.
+  // drop the needle itself when filterSelf, cut every needle's list at maxMatches. Needles without
+  // hash find nothing.
   int64_t* offsets = static_cast<int64_t*>(malloc(size_t(n + 1) * sizeof(int64_t)));
   if (!offsets) {
     set_error("out of host memory");
@@ -395,14 +402,28 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   size_t w = 0, i = 0;
   for (int64_t row = 0; row < n; ++row) {
     offsets[row] = int64_t(w);
-    int64_t kept = 0;
-    while (i < hits.size() && int64_t(hits[i].needle) == row) {
-      if (kept < max_matches && I.hashes[row] != 0) {
-        hits[w++] = hits[i];
+    size_t j = i;
+    while (j < hits.size() && int64_t(hits[j].needle) == row) ++j;
+    if (I.hashes[row] != 0) {
+      // effective threshold of this needle
+      int t = dht;
+      if (escalate) {
+        for (;;) {
+          size_t cnt = 0;
+          for (size_t k = i; k < j && hits[k].score < t; ++k) ++cnt;
+          if (int64_t(cnt) > p->minMatches || t + 1 > p->maxThresh) break;
+          ++t;
+        }
+      }
+      int64_t kept = 0;
+      for (size_t k = i; k < j && hits[k].score < t; ++k) {
+        if (p->filterSelf && hits[k].mediaId == I.ids[row]) continue;
+        if (kept >= max_matches) break;
+        hits[w++] = hits[k];
         ++kept;
       }
-      ++i;
     }
+    i = j;
   }
   offsets[n] = int64_t(w);
   hits.resize(w);

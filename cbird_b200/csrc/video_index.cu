@@ -444,6 +444,23 @@ int cb_video_index_set_video(cb_video_index* ix, uint32_t media_id, const int32_
   return CB_OK;
 }
 
+int cb_video_index_set_video_file(cb_video_index* ix, uint32_t media_id, const char* vdx_path) {
+  if (!ix || !vdx_path) {
+    set_error("cb_video_index_set_video_file: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  int32_t* frames = nullptr;
+  uint64_t* hashes = nullptr;
+  int64_t n = 0;
+  int version = 0;
+  int rc = cb_vdx_load_alloc(vdx_path, &frames, &hashes, &n, &version);
+  if (rc != CB_OK) return rc;  // "index file missing" / invalid: the video contributes no frames (:65-72)
+  rc = cb_video_index_set_video(ix, media_id, frames, hashes, n);
+  free(frames);
+  free(hashes);
+  return rc;
+}
+
 int cb_video_index_is_loaded(const cb_video_index* ix) { return ix && ix->impl.loaded ? 1 : 0; }
 int64_t cb_video_index_count(const cb_video_index* ix) { return ix ? int64_t(ix->impl.mediaId.size()) : 0; }
 size_t cb_video_index_memory_usage(const cb_video_index* ix) {

@@ -394,3 +394,11 @@ class CvFeaturesIndex:
         ptr, n = C.c_void_p(), C.c_int64(0)
         check(self._L.cb_orb_index_knn_alloc(self._h, d.ctypes.data, len(d), int(k), int(threshold), C.byref(ptr), C.byref(n)))
         return _lib.take_array(ptr.value, n.value, _lib.PAIR_DTYPE)
+
+
+def _video_set_file(self, media_id, path):
+    """read <dataPath>/<mediaId>.vdx like insertHashes (dctvideoindex.cpp:64-72)."""
+    check(self._L.cb_video_index_set_video_file(self._h, int(media_id), str(path).encode()))
+
+
+DctVideoIndex.setVideoFile = _video_set_file

@@ -196,6 +196,23 @@ int cb_video_index_find_videos_alloc(cb_video_index* ix, const int64_t* needle_o
 int cb_video_index_find_frame(cb_video_index* ix, uint64_t hash, int32_t needle_dst_in, const cb_params* p,
                               cb_match* out, int64_t cap, int64_t* n_out);
 
+/* read "<dataPath>/<mediaId>.vdx" like insertHashes does (src/dctvideoindex.cpp:64-72) and hand the table
+ * to the index; a missing or invalid file leaves the video without frames (warning semantics) */
+int cb_video_index_set_video_file(cb_video_index* ix, uint32_t media_id, const char* vdx_path);
+
+/* ---- .vdx codec (src/videoindex.cpp), host only ------------------------------------------------
+ * decode: v1 or v2 by the "cbird" magic (getVersion :41-50), incl. the v1 repairs (:462-533); any
+ * failure returns CB_ERR_INVALID with empty outputs (VideoIndex::load clears the table, :84-87).
+ * encode: format v2 (save_v2 :271-349); frames[0] must be 0, frames strictly increasing. */
+int cb_vdx_decode_alloc(const uint8_t* data, int64_t size, int32_t** frames, uint64_t** hashes, int64_t* n,
+                        int* version);
+int cb_vdx_encode_alloc(const int32_t* frames, const uint64_t* hashes, int64_t n, const char* writer_version,
+                        uint8_t** data, int64_t* size);
+int cb_vdx_is_valid(const uint8_t* data, int64_t size);                      /* isValid :90-102 */
+int cb_vdx_load_alloc(const char* path, int32_t** frames, uint64_t** hashes, int64_t* n, int* version);
+int cb_vdx_save(const char* path, const int32_t* frames, const uint64_t* hashes, int64_t n,
+                const char* writer_version);
+
 /* ---- CvFeaturesIndex (src/cvfeaturesindex.{h,cpp}): 256-bit ORB descriptors, kernel (c) ----------
  * Descriptors are rows of 32 bytes (cv::Mat N x 32 CV_8U); media m owns rows
  * [row_offsets[m], row_offsets[m+1]) of `desc`.  The reference's flann LSH knnSearch(k=10) (:497) is

@@ -384,6 +384,31 @@ int orc_search_index_post(uint32_t* ids, int* scores, int n, uint32_t needle_id,
 }
 
 
+// Database::searchIndex for AlgoDCT, src/database.cpp:1691-1757, literally: find(), the maxThresh
+// escalation loop (:1703-1725, re-running find with dht+1, dht+2, ... while the needle has
+// <= minMatches matches and the threshold stays <= maxThresh), then the post step.
+int orc_search_index_dct(const uint64_t* hashes, const uint32_t* ids, long long n, uint64_t needle_hash,
+                         uint32_t needle_id, int dctThresh, int maxThresh, int minMatches, int filter_self,
+                         int max_matches, uint32_t* out_ids, int* out_scores, int cap) {
+  std::vector<uint32_t> mi(n > 0 ? n : 1);
+  std::vector<int> ms(n > 0 ? n : 1);
+  long long cnt = orc_dct_find(hashes, ids, n, needle_hash, dctThresh, mi.data(), ms.data(), n);
+  if (maxThresh > 0) {
+    int t = dctThresh;
+    while (cnt <= minMatches) {
+      t++;
+      if (t > maxThresh) break;
+      cnt = orc_dct_find(hashes, ids, n, needle_hash, t, mi.data(), ms.data(), n);
+    }
+  }
+  int k = orc_search_index_post(mi.data(), ms.data(), int(cnt), needle_id, filter_self, max_matches);
+  for (int i = 0; i < k && i < cap; ++i) {
+    out_ids[i] = mi[i];
+    out_scores[i] = ms[i];
+  }
+  return k;
+}
+
 // ---------------------------------------------------------------------------------------------
 // DctVideoIndex — src/dctvideoindex.cpp.  The .vdx tables are handed in by the caller (the reference
 // reads "<dataPath>/<mediaId>.vdx", :64-72); everything else follows the cited lines.

@@ -49,6 +49,8 @@ def oracle():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
         L.orc_dct_find_batch.restype = C.c_longlong
         L.orc_search_index_post.argtypes = [_u32p, _i32p, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        L.orc_search_index_dct.argtypes = [_u64p, _u32p, C.c_longlong, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, _u32p, _i32p, C.c_int]
         L.orc_video_create.restype = C.c_void_p
         L.orc_video_destroy.argtypes = [C.c_void_p]
         L.orc_video_load.argtypes = [C.c_void_p, _u32p, C.c_longlong]

@@ -175,6 +175,27 @@ def test_similar_post_step(cb, po, cfg1, index, filter_self):
         assert np.all(np.diff(off) >= 1)  # every item matches itself
 
 
+@pytest.mark.parametrize("max_thresh,min_matches", [(9, 1), (12, 2), (4, 1), (7, 0)])
+def test_similar_max_thresh_escalation(cb, po, max_thresh, min_matches):
+    # maxThresh: raise dht per needle until it has > minMatches matches (database.cpp:1703-1725)
+    h, ids = synth.dct_hashes(3000, seed=21, planted_frac=0.3, max_flips=10)
+    ix = cb.DctHashIndex()
+    ix.load(ids, h)
+    p = cb.SearchParams(dctThresh=5, maxThresh=max_thresh, minMatches=min_matches, maxMatches=4, filterSelf=True)
+    off, hits = ix.similar(p)
+    O = po.oracle()
+    oi, os_ = np.zeros(64, np.uint32), np.zeros(64, np.int32)
+    escalated = 0
+    for row in range(0, 3000, 7):
+        k = O.orc_search_index_dct(h, ids, len(h), int(h[row]), int(ids[row]), 5, max_thresh, min_matches, 1, 4, oi, os_, 64)
+        g = hits[off[row]:off[row + 1]]
+        assert g["score"].tolist() == os_[:k].tolist(), row
+        assert g["mediaId"].tolist() == oi[:k].tolist(), row
+        escalated += int(k > 0 and os_[:k].max() >= 5)
+    if max_thresh > 5:
+        assert escalated > 0
+
+
 def test_large_property_checks(cb):
     # full-size property test (no oracle): 2^20 rows, each planted pair must be found symmetrically
     n = 1 << 20
