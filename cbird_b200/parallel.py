@@ -82,3 +82,73 @@ class ShardedSimilar:
 
     def similar(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
         return allgather_hits(self.scan_local(d_hashes, threshold))
+
+
+def shard_items(items, rank: int, world: int):
+    """contiguous split of a list of media (videos / ORB media) across ranks — whole items stay on one GPU."""
+    per = (len(items) + world - 1) // world
+    return items[rank * per:(rank + 1) * per]
+
+
+def allgather_objects(obj, group=None):
+    """small host-side results (final Match lists) from every rank, in rank order."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def merge_video_matches(per_rank):
+    """DctVideoIndex sharded by video: scoring is per matched video (dctvideoindex.cpp:595-654), so every
+    rank's match list is final; the merged result is their union in ascending mediaId (QMap order)."""
+    rows = [m for part in per_rank for m in part]
+    return sorted(rows, key=lambda m: m.mediaId)
+
+
+def merge_orb_knn(per_rank_hits, row_offsets, k=10):
+    """CvFeaturesIndex sharded by media: per-shard lists of the k nearest rows under the threshold
+    (cb_orb_index_knn_alloc) -> global k nearest per needle row, ties by ascending GLOBAL row
+    (row_offsets[rank] = first global row of that shard).  Returns a structured array like the input
+    with `a` rewritten to global rows, sorted by (needle row, dist, row)."""
+    import numpy as np
+
+    parts = []
+    for rank, h in enumerate(per_rank_hits):
+        h = h.copy()
+        h["a"] = h["a"] + np.uint32(row_offsets[rank])
+        parts.append(h)
+    allh = np.concatenate(parts) if parts else np.zeros(0)
+    if len(allh) == 0:
+        return allh
+    order = np.lexsort((allh["a"], allh["dist"], allh["b"]))
+    allh = allh[order]
+    # rank within each needle-row run
+    b = allh["b"]
+    starts = np.r_[0, np.nonzero(np.diff(b))[0] + 1]
+    run_start = np.repeat(starts, np.diff(np.r_[starts, len(b)]))
+    keep = (np.arange(len(b)) - run_start) < k
+    return allh[keep]
+
+
+def score_orb_matches(hits):
+    """CvFeaturesIndex::find scoring (cvfeaturesindex.cpp:571-596) over merged kNN hits whose `pad` field
+    carries the media id of the row (0 = removed): {mediaId: median*1000/count}, ascending mediaId."""
+    import numpy as np
+
+    out = []
+    media = hits["pad"]
+    for mid in np.unique(media):
+        if mid == 0:
+            continue
+        s = np.sort(hits["dist"][media == mid].astype(np.int64))
+        n = len(s)
+        if n < 2:
+            score = int(s[0])
+        elif n % 2 == 0:
+            score = int((s[n // 2 - 1] + s[n // 2]) // 2)
+        else:
+            score = int(s[n // 2])
+        out.append((int(mid), score * 1000 // n))
+    return out

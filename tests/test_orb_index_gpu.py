@@ -133,3 +133,27 @@ def test_large_exactness_property(cb):
     best = {int(h["b"]): h for h in fast[::-1]}
     for i in range(400):
         assert int(best[i]["a"]) == int(rows[i]) and int(best[i]["dist"]) == int(nflip[i])
+
+
+def test_sharded_by_media_equals_single(cb, orb):
+    # multi-GPU layout: media split across ranks, per-shard top-10 lists merged then scored
+    from cbird_b200 import parallel
+
+    ids, descs, gx, _ = orb
+    shards, offsets, base = [], [], 0
+    for r in range(4):
+        part = parallel.shard_items(list(range(len(ids))), r, 4)
+        ix = cb.CvFeaturesIndex()
+        ix.load([ids[i] for i in part], [descs[i] for i in part])
+        shards.append(ix)
+        offsets.append(base)
+        base += ix.count()
+    rng = np.random.default_rng(77)
+    for _ in range(6):
+        needle = descs[int(rng.integers(0, len(descs)))].copy()
+        needle[:, 0] ^= np.uint8(3)
+        merged = parallel.merge_orb_knn([ix.knn(needle, k=10, threshold=25) for ix in shards], offsets, k=10)
+        single = gx.knn(needle, k=10, threshold=25)
+        assert np.array_equal(merged, single)
+        want = rows_of(gx.find(cb.Media(descriptors=needle), cb.SearchParams(cvThresh=25)))
+        assert parallel.score_orb_matches(merged) == [(w[0], w[1]) for w in want]

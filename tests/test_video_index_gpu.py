@@ -169,3 +169,48 @@ def test_empty_and_degenerate(cb):
     # low-detail hashes (<5 ones or zeros) are never indexed (dctvideoindex.cpp:89)
     gx.load([9], {9: (f, np.full(10, 0x0E, np.uint64))})
     assert gx.find(cb.Media(type=cb.Media.TypeVideo, frames=f, hashes=np.full(10, 0x0E, np.uint64)), sp) == []
+
+
+def test_tables_from_vdx_files(cb, po, hay, tmp_path):
+    # the reference reads <dataPath>/<mediaId>.vdx (dctvideoindex.cpp:64-72): same results from files
+    from cbird_b200 import vdx
+
+    ids, tables = hay
+    ids = ids[:30]
+    gx, ox = cb.DctVideoIndex(), po.OracleVideoIndex()
+    gx.load(ids)
+    ox.load(ids, {int(k): tables[int(k)] for k in ids})
+    for k in ids:
+        path = str(tmp_path / ("%d.vdx" % int(k)))
+        vdx.save(path, *tables[int(k)])
+        gx.setVideoFile(int(k), path)
+    with pytest.raises(cb.CbirdError):
+        gx.setVideoFile(999, str(tmp_path / "missing.vdx"))
+    sp = cb.SearchParams(**TEST_SHAPE)
+    for k in ids[:8]:
+        f, h = tables[int(k)]
+        got = as_rows(gx.find(cb.Media(type=cb.Media.TypeVideo, frames=f[::2], hashes=h[::2]), sp))
+        assert got == orc_rows(ox.find_video(f[::2], h[::2], 0, **orc_kwargs(TEST_SHAPE)))
+        assert int(k) in [g[0] for g in got]
+
+
+def test_sharded_by_video_equals_single(cb, hay):
+    # multi-GPU layout: videos split across ranks, per-rank results are final, union = single index
+    from cbird_b200 import parallel
+
+    ids, tables = hay
+    full = cb.DctVideoIndex()
+    full.load(ids, tables)
+    shards = []
+    for r in range(3):
+        part = parallel.shard_items(list(ids), r, 3)
+        ix = cb.DctVideoIndex()
+        ix.load(part, {int(k): tables[int(k)] for k in part})
+        shards.append(ix)
+    needles = synth.video_needles(ids, tables, 6, 2, 400, seed=33)
+    for params in (TEST_SHAPE, dict(DEFAULTS, skipFrames=100, minFramesMatched=10)):
+        sp = cb.SearchParams(**params)
+        for (nid, f, h, _) in needles:
+            m = cb.Media(id=nid, type=cb.Media.TypeVideo, frames=f, hashes=h)
+            merged = parallel.merge_video_matches([ix.find(m, sp) for ix in shards])
+            assert as_rows(merged) == as_rows(full.find(m, sp))
