@@ -1,0 +1,148 @@
+"""BASELINE configs 4 and 5 (and config 1) on one B200 with the reference CPU path timed beside them.
+
+    python tools/bench_configs.py [--videos 10000] [--frames 2000] [--orb-media 25000]
+
+cfg4: DctVideoIndex, haystack videos x frames random-walk hashes vs 100 needle videos (50 re-timed copies
+      + 50 unrelated), both parameter sets of SURVEY §8d; CPU = the reference's radix.h (oracle/_ref) driven
+      by the restated findVideo on all host cores (threads over needles).
+cfg5: CvFeaturesIndex, media x 400 descriptors vs needles x 400 rows, k=10, odt=25; CPU = cv2 BFMatcher (exact)
+      and cv2 flann LSH (the reference algorithm) on a subsample.
+Prints one JSON object; numbers under ncu or other profilers are not bench values.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import cbird_b200 as cb  # noqa: E402
+from cbird_b200 import synth  # noqa: E402
+
+
+def bench_video(n_videos, n_frames, n_needles, out):
+    import pyoracle as po
+
+    ids, tables = synth.video_tables(n_videos, n_frames, seed=4)
+    needles = synth.video_needles(ids, tables, n_needles // 2, n_needles - n_needles // 2, n_frames, seed=9)
+    media = [cb.Media(id=0, type=cb.Media.TypeVideo, frames=f, hashes=h) for (_, f, h, _) in needles]
+    gx = cb.DctVideoIndex()
+    t0 = time.time()
+    gx.load(ids, tables)
+    load_s = time.time() - t0
+    threads = os.cpu_count() or 1
+    n_q = sum(len(m.frames) for m in media)
+    for name, params in (("test_shape_vradix0", dict(dctThresh=1, minFramesMatched=1, minFramesNear=1, skipFrames=0, videoRadix=0, filterSelf=False)),
+                         ("defaults_vradix10", dict(dctThresh=5, minFramesMatched=30, minFramesNear=60, skipFrames=300, videoRadix=10, filterSelf=True))):
+        sp = cb.SearchParams(**params)
+        t0 = time.time()
+        gx.find_videos(media[:2], sp)  # builds the bucket layout
+        build_s = time.time() - t0
+        t0 = time.time()
+        res = gx.find_videos(media, sp)
+        gpu_s = time.time() - t0
+        rows = gx.memoryUsage() // 16
+        pair_tests = float(n_q) * rows / (1 << min(24, max(0, params["videoRadix"])))
+        # CPU: restated findVideo over the oracle's own bucket layout, needles across host threads
+        ox = po.OracleVideoIndex()
+        ox.load(ids, tables)
+        kw = dict(dht=params["dctThresh"], skip=params["skipFrames"], vfm=params["minFramesMatched"],
+                  vfn=params["minFramesNear"], vradix=params["videoRadix"], filter_self=params["filterSelf"])
+        sample = media if params["videoRadix"] else media[: max(2, min(len(media), 2 * threads // 4))]
+        ox.find_video(sample[0].frames, sample[0].hashes, 0, **kw)  # build
+        t0 = time.time()
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL
+            cres = list(ex.map(lambda m: ox.find_video(m.frames, m.hashes, 0, **kw), sample))
+        cpu_s = (time.time() - t0) * len(media) / len(sample)
+        same = all([(x.mediaId, x.score, x.range.srcIn, x.range.dstIn, x.range.len) for x in g] ==
+                   [(int(c["mediaId"]), int(c["score"]), int(c["srcIn"]), int(c["dstIn"]), int(c["len"])) for c in cc]
+                   for g, cc in zip(res, cres))
+        out["cfg4_" + name] = {
+            "videos": n_videos, "frames_per_video": n_frames, "needle_videos": len(media), "needle_frames": n_q,
+            "index_rows": int(rows), "gpu_seconds": gpu_s, "gpu_layout_build_seconds": build_s,
+            "nominal_frame_comparisons": pair_tests, "gpu_frame_comparisons_per_s": pair_tests / gpu_s,
+            "cpu_seconds_all_needles": cpu_s, "cpu_threads": threads, "cpu_sample_needles": len(sample),
+            "cpu_kind": "oracle restatement of findVideo (bucket scan pinned against the reference radix.h)",
+            "speedup": cpu_s / gpu_s, "matches": int(sum(len(r) for r in res)), "identical_to_cpu_on_sample": bool(same)}
+    out["cfg4_load_seconds"] = load_s
+
+
+def bench_orb(n_media, rows_per_media, n_needles, out):
+    import cv2
+
+    ids, descs = synth.orb_descriptors(n_media, rows_per_media, seed=5)
+    ix = cb.CvFeaturesIndex()
+    t0 = time.time()
+    ix.load(ids, descs)
+    load_s = time.time() - t0
+    rng = np.random.default_rng(7)
+    needles = []
+    for k in range(n_needles):
+        src = descs[int(rng.integers(0, n_media))].copy()
+        flips = rng.integers(0, 256, size=(len(src), 8))
+        for j in range(8):
+            src[np.arange(len(src)), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
+        needles.append(src)
+    sp = cb.SearchParams(cvThresh=25)
+    ix.find(cb.Media(descriptors=needles[0]), sp)
+    t0 = time.time()
+    found = 0
+    for d in needles:
+        found += len(ix.find(cb.Media(descriptors=d), sp))
+    gpu_s = time.time() - t0
+    allq = np.concatenate(needles)
+    t0 = time.time()
+    hits = ix.knn(allq, k=10, threshold=25)
+    batch_s = time.time() - t0
+    n_db = ix.count()
+    pair = float(n_db) * len(allq)
+    # CPU: exact brute force (cv2.BFMatcher, all cores) and the reference algorithm (flann LSH) on a sample
+    db = np.concatenate(descs)
+    sample = needles[: max(1, min(len(needles), 4))]
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    t0 = time.time()
+    for d in sample:
+        bf.knnMatch(d, db, k=10)
+    bf_s = (time.time() - t0) * len(needles) / len(sample)
+    key = max(1, int(np.log2(max(2, n_db / 128))))
+    t0 = time.time()
+    fl = cv2.flann_Index(db, dict(algorithm=6, table_number=1, key_size=min(key, 30), multi_probe_level=1))
+    lsh_build_s = time.time() - t0
+    t0 = time.time()
+    for d in needles:
+        fl.knnSearch(d, 10, params={})
+    lsh_s = time.time() - t0
+    out["cfg5"] = {"descriptors": int(n_db), "needles": n_needles, "needle_rows": int(len(allq)), "k": 10, "odt": 25,
+                   "gpu_find_seconds_per_needle": gpu_s / n_needles, "gpu_batch_seconds": batch_s,
+                   "gpu_pair_tests_per_s_batched": pair / batch_s, "nominal_roofline_8popc": 5.8e11,
+                   "cpu_bfmatcher_seconds_per_needle": bf_s / n_needles, "cpu_threads": os.cpu_count(),
+                   "cpu_lsh_seconds_per_needle": lsh_s / n_needles, "cpu_lsh_build_seconds": lsh_build_s,
+                   "matches_found": int(found), "knn_hits": int(len(hits)), "load_seconds": load_s}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--videos", type=int, default=10000)
+    ap.add_argument("--frames", type=int, default=2000)
+    ap.add_argument("--needle-videos", type=int, default=100)
+    ap.add_argument("--orb-media", type=int, default=25000)
+    ap.add_argument("--orb-needles", type=int, default=50)
+    ap.add_argument("--skip-video", action="store_true")
+    ap.add_argument("--skip-orb", action="store_true")
+    a = ap.parse_args()
+    out = {}
+    if not a.skip_video:
+        bench_video(a.videos, a.frames, a.needle_videos, out)
+    if not a.skip_orb:
+        bench_orb(a.orb_media, 400, a.orb_needles, out)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
