@@ -106,10 +106,11 @@ def bench_orb(n_media, rows_per_media, n_needles, out):
     db = np.concatenate(descs)
     sample = needles[: max(1, min(len(needles), 4))]
     bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    sub = db[:200000]  # BFMatcher refuses > 2^18 train rows; brute force is linear in rows, so scale
     t0 = time.time()
     for d in sample:
-        bf.knnMatch(d, db, k=10)
-    bf_s = (time.time() - t0) * len(needles) / len(sample)
+        bf.knnMatch(d, sub, k=10)
+    bf_s = (time.time() - t0) * len(needles) / len(sample) * (len(db) / len(sub))
     key = max(1, int(np.log2(max(2, n_db / 128))))
     t0 = time.time()
     fl = cv2.flann_Index(db, dict(algorithm=6, table_number=1, key_size=min(key, 30), multi_probe_level=1))
@@ -139,6 +140,7 @@ def main():
     out = {}
     if not a.skip_video:
         bench_video(a.videos, a.frames, a.needle_videos, out)
+        print(json.dumps(out, indent=1), flush=True)
     if not a.skip_orb:
         bench_orb(a.orb_media, 400, a.orb_needles, out)
     print(json.dumps(out, indent=1))
