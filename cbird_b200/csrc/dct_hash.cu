@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kHashThreads, 4)
     double v = double(c0) + double(c1);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
-    const float thresh = __fdiv_rn(float(v), 64.f);  // :528-529
+    const float thresh = __fmul_rn(float(v), 0.015625f);  // sum / 64 (:528-529); exact scaling by 2^-6
     const uint32_t lo = __ballot_sync(0xffffffffu, c0 > thresh) & ~1u;  // bit 0 is never set (:537)
     const uint32_t hi = __ballot_sync(0xffffffffu, c1 > thresh);
     if (lane == 0) {

@@ -15,6 +15,7 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <unordered_set>
 
@@ -23,6 +24,18 @@
 namespace cbird {
 
 namespace {
+
+struct StageTimer {  // verbose per-find timing like the reference prints (dctvideoindex.cpp:345-350)
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(bool enabled) : on(enabled), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cbird_b200 video] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct VHit {
   uint32_t needle;   // needle index in the batch (0xFFFFFFFF = dropped)
@@ -289,8 +302,10 @@ static int find_videos(VideoIndex& I, const std::vector<Needle>& needles, const 
     set_error("video index not loaded");
     return CB_ERR_NOT_LOADED;
   }
+  StageTimer timer(p.verbose != 0);
   int rc = I.build(p.videoRadix, p.skipFrames);
   if (rc != CB_OK) return rc;
+  timer.lap("bucket layout");
   CB_CUDA(cudaSetDevice(I.device));
   const int thr = clamp_thresh(p.dctThresh);
 
@@ -325,8 +340,11 @@ static int find_videos(VideoIndex& I, const std::vector<Needle>& needles, const 
   std::vector<uint32_t> order;
   int swapped = 0;
   unsigned long long n_pairs = 0;
+  timer.lap("needle frames");
   rc = I.scan_queries(q_hash, thr, order, &swapped, &n_pairs);
   if (rc != CB_OK) return rc;
+  timer.lap("scan");
+  if (p.verbose) fprintf(stderr, "[cbird_b200 video] %zu needle frames, %zu rows, %llu raw hits\n", nq, I.n_rows, n_pairs);
   if (!n_pairs) return CB_OK;
 
   // per-query metadata in the bucket-sorted order the scan used
@@ -369,6 +387,7 @@ static int find_videos(VideoIndex& I, const std::vector<Needle>& needles, const 
     CB_CUDA(cudaStreamSynchronize(I.stream));
   }
 
+  timer.lap("reduce + D2H");
   // range scoring per (needle, video): dctvideoindex.cpp:592-654. `sel` is sorted by needle, video,
   // needle frame — the order the reference reaches with QMap + std::sort(ranges).
   const int frameMargin = 15;
@@ -394,6 +413,7 @@ static int find_videos(VideoIndex& I, const std::vector<Needle>& needles, const 
     }
     i = j;
   }
+  timer.lap("range scoring");
   return CB_OK;
 }
 
