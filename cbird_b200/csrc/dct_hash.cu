@@ -19,6 +19,7 @@
 //   vs OpenCV's FFT-based f32 DCT only coefficients tied with the mean to ~1e-4 can flip
 //   (measured rate in DESIGN.md).  HBM traffic: 1 KiB in + 8 B out per frame.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -64,8 +65,6 @@ int upload_tables() {
   return CB_OK;
 }
 
-constexpr int kFramesPerCta = 32;
-constexpr int kHashThreads = 256;
 constexpr int kTStride = 297;  // 9*33: (9*frame + 9*y + u) mod 32 is a permutation for 32 consecutive tasks
 
 // acc = 0; acc = fma(C[U][x], v[x], acc) for x ascending — the oracle's order (oracle: chain())
@@ -120,7 +119,8 @@ __device__ __forceinline__ float byte_of(const uint32_t (&w)[8], int x) {
   return __fsub_rn(__uint_as_float(bits), 8388608.f);
 }
 
-__global__ void __launch_bounds__(kHashThreads, 4)
+template <int kFramesPerCta, int kHashThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kHashThreads, kMinBlocks)
     dct_hash32_kernel(const uint8_t* __restrict__ frames, long long n, long long row_stride, long long frame_stride,
                       int aligned16, uint64_t* __restrict__ out) {
   __shared__ float sT[kFramesPerCta * kTStride];
@@ -331,8 +331,24 @@ int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long 
     t_frame = 1024;
   }
   const int aligned16 = ((reinterpret_cast<uintptr_t>(tiles) | uintptr_t(t_row) | uintptr_t(t_frame)) & 15) == 0;
-  const unsigned blocks = unsigned((n + kFramesPerCta - 1) / kFramesPerCta);
-  dct_hash32_kernel<<<blocks, kHashThreads, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+  static const int variant = getenv("CB_HASH_VARIANT") ? atoi(getenv("CB_HASH_VARIANT")) : 0;  // tuning aid
+  switch (variant) {
+    case 1:
+      dct_hash32_kernel<16, 128, 8><<<unsigned((n + 15) / 16), 128, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+      break;
+    case 2:
+      dct_hash32_kernel<8, 64, 16><<<unsigned((n + 7) / 8), 64, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+      break;
+    case 3:
+      dct_hash32_kernel<32, 128, 4><<<unsigned((n + 31) / 32), 128, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+      break;
+    case 4:
+      dct_hash32_kernel<32, 288, 4><<<unsigned((n + 31) / 32), 288, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+      break;
+    default:
+      dct_hash32_kernel<32, 256, 4><<<unsigned((n + 31) / 32), 256, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
+      break;
+  }
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
   counters().frames += uint64_t(n);
