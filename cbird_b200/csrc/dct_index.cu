@@ -66,9 +66,15 @@ struct DctIndex {
   DevBuf<unsigned char> d_temp;
   DevBuf<unsigned long long> d_counts;  // [0] scan count, [1] valid count
   unsigned long long* h_counts = nullptr;  // pinned
+  // pinned staging for the latency path (few needles, few hits): needles in, first raw hits out
+  static constexpr size_t kStageNeedles = 1024, kStagePairs = 4096;
+  uint64_t* h_stage_needles = nullptr;
+  cb_pair* h_stage_pairs = nullptr;
 
   ~DctIndex() {
     if (h_counts) cudaFreeHost(h_counts);
+    if (h_stage_needles) cudaFreeHost(h_stage_needles);
+    if (h_stage_pairs) cudaFreeHost(h_stage_pairs);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -78,6 +84,8 @@ struct DctIndex {
     device = current_device();
     if (!stream) CB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (!h_counts) CB_CUDA(cudaMallocHost(&h_counts, 2 * sizeof(unsigned long long)));
+    if (!h_stage_needles) CB_CUDA(cudaMallocHost(&h_stage_needles, kStageNeedles * sizeof(uint64_t)));
+    if (!h_stage_pairs) CB_CUDA(cudaMallocHost(&h_stage_pairs, kStagePairs * sizeof(cb_pair)));
     rc = d_counts.reserve(2);
     return rc;
   }
@@ -100,9 +108,13 @@ struct DctIndex {
 
   // Runs the scan of `needles` (device, n_q) against rows [row_begin,row_end) and leaves sorted,
   // filtered cb_hit records in d_hits; *n_valid_out = number of leading valid records.
+  // host_small: when non-null and the scan produced <= kStagePairs raw hits, they are mapped, filtered
+  // and sorted on the host into *host_small (one stream sync in total) and *done_on_host is set.
   int search_device(const uint64_t* d_q, uint32_t n_q, uint32_t row_begin, uint32_t row_end, int threshold,
-                    const uint32_t* d_needle_ids, uint32_t needle_offset, unsigned long long* n_valid_out) {
+                    const uint32_t* d_needle_ids, uint32_t needle_offset, unsigned long long* n_valid_out,
+                    std::vector<cb_hit>* host_small = nullptr, bool* done_on_host = nullptr) {
     *n_valid_out = 0;
+    if (done_on_host) *done_on_host = false;
     const uint32_t n_rows = row_end - row_begin;
     if (!n_q || !n_rows || threshold <= 0) return CB_OK;
     // the register side of the scan wants the long array
@@ -122,7 +134,30 @@ struct DctIndex {
       rc = scan64_launch(L, stream);
       if (rc != CB_OK) return rc;
       CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      if (host_small && attempt == 0)
+        CB_CUDA(cudaMemcpyAsync(h_stage_pairs, d_pairs.p, std::min<size_t>(kStagePairs, cap) * sizeof(cb_pair),
+                                cudaMemcpyDeviceToHost, stream));
       CB_CUDA(cudaStreamSynchronize(stream));
+      if (host_small && attempt == 0 && h_counts[0] <= kStagePairs && h_counts[0] <= cap) {
+        const size_t n = size_t(h_counts[0]);
+        counters().hits += n;
+        host_small->clear();
+        for (size_t i = 0; i < n; ++i) {
+          const cb_pair& pr = h_stage_pairs[i];
+          const uint32_t needle = swapped ? pr.b : pr.a, row = (swapped ? pr.a : pr.b) + row_begin;
+          const uint32_t id = ids[row];
+          if (id == 0) continue;  // removed row (dcthashindex.cpp:211-216)
+          host_small->push_back(cb_hit{needle + needle_offset, id, int32_t(pr.dist)});
+        }
+        std::sort(host_small->begin(), host_small->end(), [](const cb_hit& x, const cb_hit& y) {
+          if (x.needle != y.needle) return x.needle < y.needle;
+          if (x.score != y.score) return x.score < y.score;
+          return x.mediaId < y.mediaId;
+        });
+        *n_valid_out = host_small->size();
+        *done_on_host = true;
+        return CB_OK;
+      }
       if (h_counts[0] <= cap) break;
       cap = h_counts[0] + h_counts[0] / 8 + 1024;  // overflow: exact size is known now, run again
       if (attempt == 2) {
@@ -281,15 +316,24 @@ static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int 
     d_q = I.d_hashes.p;
     nq = int64_t(I.d_rows);
   } else {
-    rc = I.d_needles.reserve(size_t(nq) + 2);
+    rc = I.d_needles.reserve(std::max<size_t>(size_t(nq) + 2, DctIndex::kStageNeedles));
     if (rc != CB_OK) return rc;
-    if (nq) CB_CUDA(cudaMemcpyAsync(I.d_needles.p, needles, size_t(nq) * 8, cudaMemcpyHostToDevice, I.stream));
+    const uint64_t* src = needles;
+    if (size_t(nq) <= DctIndex::kStageNeedles) {  // latency path: pinned staging makes the copy truly async
+      memcpy(I.h_stage_needles, needles, size_t(nq) * 8);
+      src = I.h_stage_needles;
+    }
+    if (nq) CB_CUDA(cudaMemcpyAsync(I.d_needles.p, src, size_t(nq) * 8, cudaMemcpyHostToDevice, I.stream));
     d_q = I.d_needles.p;
   }
   unsigned long long n_valid = 0;
+  bool on_host = false;
+  const bool latency_path = !self_needles && size_t(nq) <= DctIndex::kStageNeedles;
   rc = I.search_device(d_q, uint32_t(nq), uint32_t(row_begin), uint32_t(row_end), threshold,
-                       (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid);
+                       (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid, latency_path ? &out : nullptr,
+                       &on_host);
   if (rc != CB_OK) return rc;
+  if (on_host) return CB_OK;
   out.resize(n_valid);
   if (n_valid) {
     CB_CUDA(cudaMemcpyAsync(out.data(), I.d_hits.p, n_valid * sizeof(cb_hit), cudaMemcpyDeviceToHost, I.stream));
