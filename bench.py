@@ -34,6 +34,24 @@ SM_COUNT = 148
 POPC_PER_CLK_SM = 16.0  # measured: tools/probe/pipe_probe.cu -> profiles/pipe_probe_r01.json
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full summary
+    (profiles/ncu_full_r01.json; capture sizes are stated there), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_full_r01.json")) as f:
+            prof = json.load(f)
+        for k in prof["kernels"]:
+            if kernel_substr in k["Kernel Name"]:
+                def to_bytes(v, unit_hint):
+                    return float(v)
+                rd, wr = float(k["dram__bytes_read.sum"]), float(k["dram__bytes_write.sum"])
+                # ncu prints read in Gbyte and write in Mbyte for these kernels (see the raw page units)
+                return rd * 1e9 + wr * 1e6
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -369,7 +387,7 @@ def main():
                     "d2h_bytes_per_step": HASH_FRAMES * 8},
             "roofline": {"bound": "hbm", "achieved": hash_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": hash_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic("dct_hash32_kernel"), "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": 1032}}
         # CPU baseline for the hash: the oracle's plain-C++ restatement on all host cores, bounded sample
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -406,7 +424,8 @@ def main():
         roofline = {
             "bound": "int_pipe", "kernel": "scan64_kernel<%d>" % variant,
             "achieved": kern_rate * 2.0 / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s (nominal 2 POPC.b32 per 64-bit pair)",
-            "frac": kern_rate / pair_peak, "traffic": None,
+            "frac": kern_rate / pair_peak, "traffic": ncu_traffic("scan64_kernel<%d>" % variant),
+            "traffic_note": "bytes per launch from the committed ncu capture at 2^19 x 2^19 rows (algorithmic: 8 B per row = 4.2 MB)",
             "peak_source": "148 SM x 16 POPC lanes/clk/SM (measured, profiles/pipe_probe_r01.json) x %.0f MHz max SM clock" % sm_max_mhz,
             "kernel_ms": kern_ms, "pairs_per_launch": comparisons / world, "algorithmic_popc_per_pair": 2,
             "issued_popc_per_pair": {2: 0.5, 1: 1.0, 0: 2.0}[variant],
