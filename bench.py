@@ -37,16 +37,17 @@ POPC_PER_CLK_SM = 16.0  # measured: tools/probe/pipe_probe.cu -> profiles/pipe_p
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full summary
     (profiles/ncu_full_r01.json; capture sizes are stated there), or None."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_full_r01.json")) as f:
             prof = json.load(f)
+        units = prof.get("units", {})
         for k in prof["kernels"]:
             if kernel_substr in k["Kernel Name"]:
-                def to_bytes(v, unit_hint):
-                    return float(v)
-                rd, wr = float(k["dram__bytes_read.sum"]), float(k["dram__bytes_write.sum"])
-                # ncu prints read in Gbyte and write in Mbyte for these kernels (see the raw page units)
-                return rd * 1e9 + wr * 1e6
+                total = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(k[key]) * scale[units.get(key, "byte")]
+                return total
     except Exception:
         pass
     return None
