@@ -5,4 +5,5 @@ host-side mirror of the reference interface.  Importing the package never touche
 """
 from ._lib import CbirdError, LIB_PATH, lib  # noqa: F401
 from .index import CvFeaturesIndex, DctHashIndex, DctVideoIndex, Match, MatchRange, Media, SearchParams  # noqa: F401
-from .hashing import dct_hash64, dct_hash64_batch, hash_tables  # noqa: F401,E402
+from .hashing import (autocrop_batch, dct_hash64, dct_hash64_batch, dct_hash64_rects, hash_tables, make_video_index,
+                      video_compress)  # noqa: F401,E402

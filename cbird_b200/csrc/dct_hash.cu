@@ -247,6 +247,185 @@ __global__ void __launch_bounds__(1024)
   dst[(long long)blockIdx.x * 1024 + threadIdx.x] = r;
 }
 
+// ---- per-frame crop rectangles: autocrop + dctHash64 of the cropped view ---------------------------
+// rect = {left, top, right, bottom} (right/bottom exclusive) inside the w x h parent frame.
+
+// autocrop(img, range) — src/cvutil.cpp:1285-1401: de-letterbox. Per row/column the extent of pixels
+// within `range` of the corner colour is found in parallel; the reference's scans from the centre
+// outwards then reduce to "nearest qualifying row/column", done by one thread over <= max(w,h) entries.
+__global__ void autocrop_kernel(const uint8_t* __restrict__ frames, long long row_stride, long long frame_stride, int w,
+                                int h, int range, int32_t* __restrict__ rects) {
+  extern __shared__ int s_ext[];  // rowL[h], rowR[h], colT[w], colB[w]
+  int* rowL = s_ext;
+  int* rowR = rowL + h;
+  int* colT = rowR + h;
+  int* colB = colT + w;
+  const uint8_t* img = frames + (long long)blockIdx.x * frame_stride;
+  const int color = img[0];
+  for (int y = threadIdx.x; y < h; y += blockDim.x) {
+    const uint8_t* px = img + (long long)y * row_stride;
+    int left = 0, right = w - 1;
+    while (left < w && abs(int(px[left]) - color) <= range) ++left;
+    while (right >= 0 && abs(int(px[right]) - color) <= range) --right;
+    rowL[y] = left;
+    rowR[y] = right + 1;
+  }
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    int top = 0, bottom = h - 1;
+    while (top < h && abs(int(img[(long long)top * row_stride + x]) - color) <= range) ++top;
+    while (bottom >= 0 && abs(int(img[(long long)bottom * row_stride + x]) - color) <= range) --bottom;
+    colT[x] = top;
+    colB[x] = bottom + 1;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int minW = int(float(w) * 0.66f), minH = int(float(h) * 0.66f);
+  const int maxHd = int(float(w) * 0.05f), maxVd = int(float(h) * 0.05f);
+  int top, bottom, left, right;
+  for (top = h / 2; top >= 0; --top)
+    if (rowL[top] > 0 && rowR[top] < w && rowL[top] + w - rowR[top] > minW) break;
+  ++top;
+  for (bottom = h / 2 + 1; bottom < h; ++bottom)
+    if (rowL[bottom] + w - rowR[bottom] > minW) break;  // (no left>0 && right<cols test on this side, :1341)
+  for (left = w / 2; left >= 0; --left)
+    if (colT[left] > 0 && colB[left] < h && colT[left] + h - colB[left] > minH) break;
+  ++left;
+  for (right = w / 2 + 1; right < w; ++right)
+    if (colT[right] > 0 && colB[right] < h && colT[right] + h - colB[right] > minH) break;
+  const int bmargin = h - bottom;  // centre the crop using the lesser margin (:1372-1388)
+  if (abs(top - bmargin) > maxVd) {
+    if (top > bmargin) top = bmargin;
+    else bottom = h - top;
+  }
+  const int rmargin = w - right;
+  if (abs(left - rmargin) > maxHd) {
+    if (left > rmargin) left = rmargin;
+    else right = w - left;
+  }
+  bool crop = false;
+  if ((left != 0 && right != w) || (top != 0 && bottom != h))
+    if (left < right && top < bottom && float(right - left) / float(w) > 0.65f && float(bottom - top) / float(h) > 0.65f)
+      crop = true;
+  int32_t* r = rects + 4 * (long long)blockIdx.x;
+  r[0] = crop ? left : 0;
+  r[1] = crop ? top : 0;
+  r[2] = crop ? right : w;
+  r[3] = crop ? bottom : h;
+}
+
+__device__ __forceinline__ int blur_k_for(long long area) {  // src/cvutil.cpp:446-455
+  if (area <= 32 * 32) return 0;
+  if (area <= 64 * 64) return 3;
+  if (area <= 128 * 128) return 5;
+  return 7;
+}
+
+// cv::blur on a cropped VIEW: the filter reads the parent's pixels outside the view (the ROI is not
+// BORDER_ISOLATED) and reflects (101) only at the parent's own edges. Output: dense crop at stride w.
+__global__ void box_blur_rect_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride,
+                                     int w, int h, const int32_t* __restrict__ rects, uint8_t* __restrict__ dst) {
+  const int32_t* rc = rects + 4 * (long long)blockIdx.z;
+  const int cw = rc[2] - rc[0], ch = rc[3] - rc[1];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= cw || y >= ch) return;
+  const uint8_t* f = src + (long long)blockIdx.z * frame_stride;
+  const int k = blur_k_for((long long)cw * ch);
+  const int px = rc[0] + x, py = rc[1] + y;
+  uint8_t out;
+  if (k == 0) {
+    out = f[(long long)py * row_stride + px];
+  } else {
+    const int r = k >> 1, area = k * k;
+    int s = 0;
+    for (int dy = -r; dy <= r; ++dy) {
+      const uint8_t* row = f + (long long)reflect101(py + dy, h) * row_stride;
+      for (int dx = -r; dx <= r; ++dx) s += row[reflect101(px + dx, w)];
+    }
+    out = uint8_t((2 * s + area) / (2 * area));
+  }
+  dst[((long long)blockIdx.z * h + y) * w + x] = out;
+}
+
+// coverage taps of destination cell d along one axis, generated on the fly in f64 exactly like
+// area_taps() below; returns the number of taps (<= ceil(scale)+2), tap i = (si[i], alpha[i])
+struct TapIter {
+  int sx1, sx2, ssize;
+  double fsx1, fsx2, cell;
+  __device__ TapIter(int d, int ssize_, double scale) : ssize(ssize_) {
+    fsx1 = d * scale;
+    fsx2 = fsx1 + scale;
+    cell = fmin(scale, ssize - fsx1);
+    sx1 = int(ceil(fsx1));
+    sx2 = int(floor(fsx2));
+    sx2 = min(sx2, ssize - 1);
+    sx1 = min(sx1, sx2);
+  }
+  __device__ bool head() const { return sx1 - fsx1 > 1e-3; }
+  __device__ float head_alpha() const { return float((sx1 - fsx1) / cell); }
+  __device__ float body_alpha() const { return float(1.0 / cell); }
+  __device__ bool tail() const { return fsx2 - sx2 > 1e-3; }
+  __device__ float tail_alpha() const { return float(fmin(fmin(fsx2 - sx2, 1.), cell) / cell); }
+};
+
+// cv::resize(32x32, INTER_AREA) of every frame's (already blurred) crop; crops smaller than 32 px on a
+// side are flagged (OpenCV would up-scale through a different path that is not restated)
+__global__ void __launch_bounds__(1024)
+    area_resize_rect_kernel(const uint8_t* __restrict__ src, int w, int h, const int32_t* __restrict__ rects,
+                            uint8_t* __restrict__ dst, uint8_t* __restrict__ bad) {
+  const int32_t* rc = rects + 4 * (long long)blockIdx.x;
+  const int cw = rc[2] - rc[0], ch = rc[3] - rc[1];
+  const int dx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const uint8_t* f = src + (long long)blockIdx.x * h * w;
+  uint8_t r = 0;
+  const bool unsupported = cw < 32 || ch < 32;
+  if (threadIdx.x == 0) bad[blockIdx.x] = unsupported ? 1 : 0;
+  if (!unsupported) {
+    const double sx = cw / 32.0, sy = ch / 32.0;
+    const int ix = int(rint(sx)), iy = int(rint(sy));
+    const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
+    if (cw == 32 && ch == 32) {
+      r = f[(long long)dy * w + dx];
+    } else if (fast && ix == 2 && iy == 2) {
+      const uint8_t* a = f + (long long)(2 * dy) * w + 2 * dx;
+      r = uint8_t((int(a[0]) + a[1] + a[w] + a[w + 1] + 2) >> 2);
+    } else if (fast) {
+      int s = 0;
+      for (int j = 0; j < iy; ++j)
+        for (int i = 0; i < ix; ++i) s += f[(long long)(dy * iy + j) * w + dx * ix + i];
+      r = uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
+    } else {
+      const TapIter tx(dx, cw, sx), ty(dy, ch, sy);
+      auto row_sum = [&](int syi) {
+        const uint8_t* row = f + (long long)syi * w;
+        float buf = 0.f;
+        if (tx.head()) buf = __fadd_rn(buf, __fmul_rn(float(row[tx.sx1 - 1]), tx.head_alpha()));
+        const float ba = tx.body_alpha();
+        for (int k = tx.sx1; k < tx.sx2; ++k) buf = __fadd_rn(buf, __fmul_rn(float(row[k]), ba));
+        if (tx.tail()) buf = __fadd_rn(buf, __fmul_rn(float(row[tx.sx2]), tx.tail_alpha()));
+        return buf;
+      };
+      float sum = 0.f;
+      bool first = true;
+      auto acc = [&](int syi, float beta) {
+        const float t = __fmul_rn(beta, row_sum(syi));
+        sum = first ? t : __fadd_rn(sum, t);
+        first = false;
+      };
+      if (ty.head()) acc(ty.sx1 - 1, ty.head_alpha());
+      const float bb = ty.body_alpha();
+      for (int k = ty.sx1; k < ty.sx2; ++k) acc(k, bb);
+      if (ty.tail()) acc(ty.sx2, ty.tail_alpha());
+      r = uint8_t(min(255, max(0, __float2int_rn(sum))));
+    }
+  }
+  dst[(long long)blockIdx.x * 1024 + threadIdx.x] = r;
+}
+
+__global__ void zero_bad_hashes_kernel(const uint8_t* __restrict__ bad, long long n, uint64_t* out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n && bad[i]) out[i] = 0;  // 0 == "no hash" (src/index.cpp:46-49)
+}
+
 // OpenCV computeResizeAreaTab (third-party imgproc, restated): coverage weights in f32
 void area_taps(int ssize, double scale, std::vector<AreaTap>& tab, std::vector<int>& ofs) {
   tab.clear();
@@ -266,11 +445,15 @@ void area_taps(int ssize, double scale, std::vector<AreaTap>& tab, std::vector<i
 }
 
 struct HashWorkspace {
-  DevBuf<uint8_t> blurred, tiles;
+  DevBuf<uint8_t> blurred, tiles, bad;
+  DevBuf<int32_t> rects;
   DevBuf<AreaTap> xt, yt;
   DevBuf<int> xofs, yofs;
   int tab_w = -1, tab_h = -1;
 };
+
+int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long t_frame, uint64_t* d_out,
+                  cudaStream_t stream);
 
 // frames already on the device. ws may be null only for 32x32 input.
 int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride,
@@ -330,6 +513,54 @@ int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long 
     t_row = 32;
     t_frame = 1024;
   }
+  return launch_hash32(tiles, n, t_row, t_frame, d_out, stream);
+}
+
+// autocrop rectangles for frames on the device -> d_rects (n x 4 int32)
+int autocrop_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride, long long frame_stride,
+                    int range, int32_t* d_rects, cudaStream_t stream) {
+  if (n <= 0) return CB_OK;
+  const size_t smem = size_t(2 * h + 2 * w) * sizeof(int);
+  if (smem > 200 * 1024) {
+    set_error("autocrop: %dx%d frames are larger than the supported 12800 px of width+height", w, h);
+    return CB_ERR_UNSUPPORTED;
+  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(autocrop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(autocrop_kernel)", __FILE__, __LINE__);
+  autocrop_kernel<<<unsigned(n), 128, smem, stream>>>(d_frames, row_stride, frame_stride, w, h, range, d_rects);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  return CB_OK;
+}
+
+// dctHash64 of every frame's crop rectangle (a view into the frame, as autocrop leaves it)
+int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride, long long frame_stride,
+                      const int32_t* d_rects, uint64_t* d_out, HashWorkspace* ws, cudaStream_t stream) {
+  if (n <= 0) return CB_OK;
+  int rc = upload_tables();
+  if (rc != CB_OK) return rc;
+  if ((rc = ws->blurred.reserve(size_t(n) * w * h)) != CB_OK || (rc = ws->tiles.reserve(size_t(n) * 1024)) != CB_OK ||
+      (rc = ws->bad.reserve(size_t(n))) != CB_OK)
+    return rc;
+  dim3 grid((w + 127) / 128, h, unsigned(n));
+  box_blur_rect_kernel<<<grid, 128, 0, stream>>>(d_frames, row_stride, frame_stride, w, h, d_rects, ws->blurred.p);
+  CB_CUDA(cudaGetLastError());
+  area_resize_rect_kernel<<<unsigned(n), 1024, 0, stream>>>(ws->blurred.p, w, h, d_rects, ws->tiles.p, ws->bad.p);
+  CB_CUDA(cudaGetLastError());
+  rc = launch_hash32(ws->tiles.p, n, 32, 1024, d_out, stream);
+  if (rc != CB_OK) return rc;
+  zero_bad_hashes_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(ws->bad.p, n, d_out);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 3;
+  return CB_OK;
+}
+
+int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long t_frame, uint64_t* d_out,
+                  cudaStream_t stream) {
   const int aligned16 = ((reinterpret_cast<uintptr_t>(tiles) | uintptr_t(t_row) | uintptr_t(t_frame)) & 15) == 0;
   // CTA shape: measured on B200 (tools/hash_bench.py) 8 frames x 64 threads 0.481 ms, 16x128 0.492,
   // 32x256 0.513, 32x128 0.572 per 2^20 frames — the kernel is issue-bound, the shape hardly matters.
@@ -451,6 +682,175 @@ int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_st
     CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
     CB_CUDA(cudaStreamSynchronize(ctx.stream));
   }
+  return CB_OK;
+}
+
+
+}  // extern "C"
+
+// shared host-side driver: copy frames in, run `fn` on the device copy, copy results out
+template <typename Fn>
+static int with_device_frames(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                              Fn fn) {
+  int rc = check_geometry(w, h, n, row_stride, frame_stride);
+  if (rc != CB_OK) return rc;
+  if (n == 0) return CB_OK;
+  if (!frames) {
+    set_error("null frame pointer");
+    return CB_ERR_INVALID;
+  }
+  rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  HostHashContext& ctx = g_ctx[current_device() & 15];
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  if (!ctx.stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  const long long frame_bytes = (long long)(h - 1) * row_stride + w;
+  const long long per_frame = n > 1 ? frame_stride : frame_bytes;
+  long long chunk = std::max(1ll, (128ll << 20) / std::max(1ll, per_frame));
+  chunk = std::min<long long>(chunk, n);
+  rc = ctx.d_in.reserve(size_t(chunk) * per_frame + 16);
+  if (rc != CB_OK) return rc;
+  for (long long i0 = 0; i0 < n; i0 += chunk) {
+    const long long m = std::min(chunk, n - i0);
+    CB_CUDA(cudaMemcpyAsync(ctx.d_in.p, frames + i0 * frame_stride, size_t(m - 1) * per_frame + frame_bytes,
+                            cudaMemcpyHostToDevice, ctx.stream));
+    rc = fn(ctx, ctx.d_in.p, i0, m, per_frame);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  return CB_OK;
+}
+
+extern "C" {
+
+int cb_autocrop_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride, int range,
+                      int32_t* rects) {
+  if (n > 0 && !rects) {
+    set_error("cb_autocrop_batch: null output");
+    return CB_ERR_INVALID;
+  }
+  return with_device_frames(frames, n, w, h, row_stride, frame_stride,
+                            [&](HostHashContext& ctx, const uint8_t* d, long long i0, long long m, long long per_frame) {
+                              int rc = ctx.ws.rects.reserve(size_t(m) * 4);
+                              if (rc != CB_OK) return rc;
+                              rc = autocrop_device(d, m, w, h, row_stride, per_frame, range, ctx.ws.rects.p, ctx.stream);
+                              if (rc != CB_OK) return rc;
+                              CB_CUDA(cudaMemcpyAsync(rects + 4 * i0, ctx.ws.rects.p, size_t(m) * 16, cudaMemcpyDeviceToHost, ctx.stream));
+                              return int(CB_OK);
+                            });
+}
+
+int cb_hash_batch_rects(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                        const int32_t* rects, uint64_t* out) {
+  if (n > 0 && (!rects || !out)) {
+    set_error("cb_hash_batch_rects: null pointer");
+    return CB_ERR_INVALID;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* r = rects + 4 * i;
+    if (r[0] < 0 || r[1] < 0 || r[2] > w || r[3] > h || r[0] >= r[2] || r[1] >= r[3]) {
+      set_error("cb_hash_batch_rects: rectangle %lld (%d,%d,%d,%d) outside the %dx%d frame", (long long)i, r[0], r[1], r[2], r[3], w, h);
+      return CB_ERR_INVALID;
+    }
+  }
+  return with_device_frames(frames, n, w, h, row_stride, frame_stride,
+                            [&](HostHashContext& ctx, const uint8_t* d, long long i0, long long m, long long per_frame) {
+                              int rc = ctx.ws.rects.reserve(size_t(m) * 4);
+                              if (rc == CB_OK) rc = ctx.d_out.reserve(size_t(m));
+                              if (rc != CB_OK) return rc;
+                              CB_CUDA(cudaMemcpyAsync(ctx.ws.rects.p, rects + 4 * i0, size_t(m) * 16, cudaMemcpyHostToDevice, ctx.stream));
+                              rc = hash_rects_device(d, m, w, h, row_stride, per_frame, ctx.ws.rects.p, ctx.d_out.p, &ctx.ws, ctx.stream);
+                              if (rc != CB_OK) return rc;
+                              CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+                              return int(CB_OK);
+                            });
+}
+
+// near-frame compression of Media::makeVideoIndex (src/media.cpp:958-1031): frame 0 is always kept and
+// is NOT put in the window; a later frame is kept iff some hash in the window differs from it by
+// >= threshold (which also clears the window); the last frame is always kept.
+int cb_video_compress(const uint64_t* hashes, int64_t n, int threshold, int32_t* out_frames, uint64_t* out_hashes,
+                      int64_t* n_out) {
+  if (n < 0 || !n_out || (n && (!hashes || !out_frames || !out_hashes))) {
+    set_error("cb_video_compress: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  int64_t k = 0;
+  std::vector<uint64_t> window;
+  int frame = 0;
+  if (n > 0) {
+    out_hashes[k] = hashes[0];
+    out_frames[k++] = 0;
+    frame = 1;
+  }
+  for (int64_t i = 1; i < n; ++i) {
+    const uint64_t h = hashes[i];
+    if (threshold > 0) {
+      size_t close = 0;
+      for (uint64_t prev : window)
+        if (__builtin_popcountll(prev ^ h) < threshold) ++close;
+      if (close != window.size()) {
+        window.clear();
+        out_hashes[k] = h;
+        out_frames[k++] = frame;
+      }
+      window.push_back(h);
+    } else {
+      out_hashes[k] = h;
+      out_frames[k++] = frame;
+    }
+    ++frame;
+    if (frame == (1 << 24)) break;  // MAX_FRAMES_PER_VIDEO (:1018-1021)
+  }
+  --frame;
+  if (k > 0 && out_frames[k - 1] != frame) {  // always include the last frame (:1026-1029)
+    out_hashes[k] = window.back();
+    out_frames[k++] = frame;
+  }
+  *n_out = k;
+  return CB_OK;
+}
+
+// Media::makeVideoIndex on a video's decoded luma frames: autocrop(20) -> dctHash64 -> compression
+int cb_make_video_index_alloc(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                              int threshold, int32_t** out_frames, uint64_t** out_hashes, int64_t* n_out) {
+  if (!out_frames || !out_hashes || !n_out) {
+    set_error("cb_make_video_index_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  *out_frames = nullptr;
+  *out_hashes = nullptr;
+  *n_out = 0;
+  std::vector<uint64_t> hashes(size_t(std::max<int64_t>(n, 0)));
+  int rc = with_device_frames(frames, n, w, h, row_stride, frame_stride,
+                              [&](HostHashContext& ctx, const uint8_t* d, long long i0, long long m, long long per_frame) {
+                                int rc2 = ctx.ws.rects.reserve(size_t(m) * 4);
+                                if (rc2 == CB_OK) rc2 = ctx.d_out.reserve(size_t(m));
+                                if (rc2 != CB_OK) return rc2;
+                                rc2 = autocrop_device(d, m, w, h, row_stride, per_frame, 20, ctx.ws.rects.p, ctx.stream);  // :963,:994
+                                if (rc2 != CB_OK) return rc2;
+                                rc2 = hash_rects_device(d, m, w, h, row_stride, per_frame, ctx.ws.rects.p, ctx.d_out.p, &ctx.ws, ctx.stream);
+                                if (rc2 != CB_OK) return rc2;
+                                CB_CUDA(cudaMemcpyAsync(hashes.data() + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+                                return int(CB_OK);
+                              });
+  if (rc != CB_OK) return rc;
+  int32_t* f = static_cast<int32_t*>(malloc(size_t(std::max<int64_t>(1, n + 1)) * sizeof(int32_t)));
+  uint64_t* hh = static_cast<uint64_t*>(malloc(size_t(std::max<int64_t>(1, n + 1)) * sizeof(uint64_t)));
+  if (!f || !hh) {
+    free(f);
+    free(hh);
+    set_error("out of host memory");
+    return CB_ERR_INVALID;
+  }
+  rc = cb_video_compress(hashes.data(), n, threshold, f, hh, n_out);
+  if (rc != CB_OK) {
+    free(f);
+    free(hh);
+    return rc;
+  }
+  *out_frames = f;
+  *out_hashes = hh;
   return CB_OK;
 }
 

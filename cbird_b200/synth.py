@@ -134,3 +134,35 @@ def orb_descriptors(n_media, rows_per_media, seed, planted_frac=0.05, max_flips=
         d[dst] = v
     ids = np.arange(first_id, first_id + n_media, dtype=np.uint32)
     return ids, [d[i * rows_per_media:(i + 1) * rows_per_media] for i in range(n_media)]
+
+
+def video_frames(n, seed, w=128, h=128, letterbox=(0, 0), border=16, scene_len=40):
+    """decoded-video-like luma frames (the decoder hands 128x128 gray, src/scanner.cpp:1043-1048):
+    slowly drifting smooth content with scene cuts every `scene_len` frames, optional letterbox
+    (top/bottom rows, left/right columns) of near-constant `border` level with +-2 noise."""
+    rng = np.random.default_rng(seed)
+    frames = np.empty((n, h, w), np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    base = None
+    for i in range(n):
+        if i % scene_len == 0 or base is None:
+            coef = rng.normal(0, 1, size=(4, 4)).astype(np.float32)
+            phase = rng.uniform(0, 6.28, size=(4, 4)).astype(np.float32)
+            base = np.zeros((h, w), np.float32)
+            for a in range(4):
+                for b in range(4):
+                    base += coef[a, b] * np.cos((a + 1) * yy / h * 3.1 + phase[a, b]) * np.cos((b + 1) * xx / w * 3.1 - phase[b, a])
+            base = 128 + 40 * base / max(1e-3, np.abs(base).max())
+            drift = rng.normal(0, 0.6, size=(h, w)).astype(np.float32)
+        base = base + drift
+        f = base + rng.normal(0, 3, size=(h, w))
+        f = np.clip(f, 40, 255)  # keep content away from the border level
+        lb_v, lb_h = letterbox
+        if lb_v:
+            f[:lb_v] = border + rng.integers(-2, 3, size=(lb_v, w))
+            f[h - lb_v:] = border + rng.integers(-2, 3, size=(lb_v, w))
+        if lb_h:
+            f[:, :lb_h] = border + rng.integers(-2, 3, size=(h, lb_h))
+            f[:, w - lb_h:] = border + rng.integers(-2, 3, size=(h, lb_h))
+        frames[i] = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    return frames

@@ -105,6 +105,25 @@ int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_st
 /* device-resident variant on a caller stream (cudaStream_t passed as void*); asynchronous */
 int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                       uint64_t* d_out, void* stream);
+/* autocrop(img, range) of every frame — src/cvutil.cpp:1285-1401 (de-letterbox before hashing video
+ * frames, src/media.cpp:963,994): rects[4*i..] = {left, top, right, bottom}, right/bottom exclusive;
+ * the full frame when no crop applies. */
+int cb_autocrop_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                      int range, int32_t* rects);
+/* dctHash64 of each frame's rectangle taken as a VIEW into the frame (what autocrop leaves in cvImg):
+ * blur size by the rectangle's area, blur border pixels come from the parent frame. Rectangles smaller
+ * than 32 px on a side give hash 0 ("no hash"). */
+int cb_hash_batch_rects(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                        const int32_t* rects, uint64_t* out);
+/* near-frame compression window of Media::makeVideoIndex (src/media.cpp:958-1031) over the hashes of
+ * consecutive frames 0..n-1; threshold = IndexParams vht (8). out arrays need n+1 entries. Host only. */
+int cb_video_compress(const uint64_t* hashes, int64_t n, int threshold, int32_t* out_frames, uint64_t* out_hashes,
+                      int64_t* n_out);
+/* Media::makeVideoIndex (src/media.cpp:925-1037) on one video's decoded luma frames (the decoder hands
+ * 128x128 gray, src/scanner.cpp:1043-1048): autocrop(20) -> dctHash64 -> compression. Library-allocated
+ * VideoIndex{frames, hashes} (cb_free). */
+int cb_make_video_index_alloc(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
+                              int threshold, int32_t** out_frames, uint64_t** out_hashes, int64_t* n_out);
 /* the f32 DCT basis rows 0..8 (9*32 floats) and the 81-entry zig-zag table the kernel uses */
 void cb_hash_tables(float* basis_9x32, int32_t* zigzag81);
 

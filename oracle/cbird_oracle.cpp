@@ -292,6 +292,156 @@ double orc_dct_hash64_batch(const uint8_t* frames, long long n, int w, int h, in
   return std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
 
+// autocrop(cvImg, range) — src/cvutil.cpp:1285-1401, loop for loop. rect = {left, top, right, bottom}
+// (right/bottom exclusive); the full frame when the final sanity checks refuse the crop.
+void orc_autocrop(const uint8_t* img, int cols, int rows, int stride, int range, int* rect) {
+  rect[0] = 0; rect[1] = 0; rect[2] = cols; rect[3] = rows;
+  if (rows == 0 || cols == 0) return;
+  auto at = [&](int y, int x) { return int(img[(size_t)y * stride + x]); };
+  const int color = at(0, 0);
+  const int minWidthCovered = int(cols * 0.66f), minHeightCovered = int(rows * 0.66f);
+  const int maxHMarginDifference = int(cols * 0.05f), maxVMarginDifference = int(rows * 0.05f);
+  int top;
+  for (top = rows / 2; top >= 0; top--) {
+    int left, right;
+    for (left = 0; left < cols; left++)
+      if (abs(at(top, left) - color) > range) break;
+    for (right = cols - 1; right >= 0; right--)
+      if (abs(at(top, right) - color) > range) break;
+    right++;
+    if (left > 0 && right < cols && left + cols - right > minWidthCovered) break;
+  }
+  top++;
+  int bottom;
+  for (bottom = rows / 2 + 1; bottom < rows; bottom++) {
+    int left, right;
+    for (left = 0; left < cols; left++)
+      if (abs(at(bottom, left) - color) > range) break;
+    for (right = cols - 1; right >= 0; right--)
+      if (abs(at(bottom, right) - color) > range) break;
+    right++;
+    if (left + cols - right > minWidthCovered) break;
+  }
+  int left;
+  for (left = cols / 2; left >= 0; left--) {
+    int t, b;
+    for (t = 0; t < rows; t++)
+      if (abs(at(t, left) - color) > range) break;
+    for (b = rows - 1; b >= 0; b--)
+      if (abs(at(b, left) - color) > range) break;
+    b++;
+    if (t > 0 && b < rows && t + rows - b > minHeightCovered) break;
+  }
+  left++;
+  int right;
+  for (right = cols / 2 + 1; right < cols; right++) {
+    int t, b;
+    for (t = 0; t < rows; t++)
+      if (abs(at(t, right) - color) > range) break;
+    for (b = rows - 1; b >= 0; b--)
+      if (abs(at(b, right) - color) > range) break;
+    b++;
+    if (t > 0 && b < rows && t + rows - b > minHeightCovered) break;
+  }
+  int bmargin = rows - bottom;
+  if (abs(top - bmargin) > maxVMarginDifference) {
+    if (top > bmargin) top = bmargin;
+    else bottom = rows - top;
+  }
+  int rmargin = cols - right;
+  if (abs(left - rmargin) > maxHMarginDifference) {
+    if (left > rmargin) left = rmargin;
+    else right = cols - left;
+  }
+  if ((left != 0 && right != cols) || (top != 0 && bottom != rows))
+    if (left < right && top < bottom && (right - left) / float(cols) > 0.65f && (bottom - top) / float(rows) > 0.65f) {
+      rect[0] = left; rect[1] = top; rect[2] = right; rect[3] = bottom;
+    }
+}
+
+// dctHash64 of a crop VIEW (what autocrop leaves in cvImg): blur size from the view's area; cv::blur on
+// a view reads the parent's pixels beyond the view (not BORDER_ISOLATED) and reflects only at the
+// parent's edges == blur the parent, then take the view. 32x32 tile optional out. Returns 0 for views
+// smaller than 32 px on a side (INTER_AREA up-scaling not restated).
+uint64_t orc_dct_hash64_rect(const uint8_t* img, int w, int h, int stride, const int* rect, uint8_t* tile_out) {
+  const int cw = rect[2] - rect[0], ch = rect[3] - rect[1];
+  if (cw < 32 || ch < 32) return 0;
+  const long area = (long)cw * ch;
+  int k = 7;
+  if (area <= 32 * 32) k = 0;
+  else if (area <= 64 * 64) k = 3;
+  else if (area <= 128 * 128) k = 5;
+  uint8_t tile[32 * 32];
+  int rc;
+  if (k) {
+    std::vector<uint8_t> blurred;
+    box_blur(img, w, h, stride, k, blurred);
+    rc = area_resize32(blurred.data() + (size_t)rect[1] * w + rect[0], cw, ch, w, tile);
+  } else {
+    rc = area_resize32(img + (size_t)rect[1] * stride + rect[0], cw, ch, stride, tile);
+  }
+  if (rc != 0) return 0;
+  if (tile_out) memcpy(tile_out, tile, sizeof(tile));
+  return orc_hash_from_tile32(tile, nullptr, nullptr);
+}
+
+// near-frame compression loop of Media::makeVideoIndex, src/media.cpp:958-1031, over precomputed hashes
+long long orc_video_compress(const uint64_t* hashes, long long n, int threshold, int* out_frames, uint64_t* out_hashes) {
+  std::vector<int> frames;
+  std::vector<uint64_t> kept;
+  std::vector<uint64_t> window;
+  int frameNumber = 0;
+  long long i = 0;
+  if (n > 0) {  // first frame :958-968
+    kept.push_back(hashes[0]);
+    frames.push_back(frameNumber);
+    frameNumber++;
+    i = 1;
+  }
+  for (; i < n; ++i) {
+    const uint64_t hash = hashes[i];
+    if (threshold > 0) {
+      size_t close = 0;
+      for (uint64_t prev : window)
+        if (orc_hamm64(prev, hash) < threshold) close++;
+      if (close != window.size()) {
+        window.clear();
+        kept.push_back(hash);
+        frames.push_back(frameNumber);
+      }
+      window.push_back(hash);
+    } else {
+      kept.push_back(hash);
+      frames.push_back(frameNumber);
+    }
+    frameNumber++;
+    if (frameNumber == (1 << 24)) break;
+  }
+  frameNumber--;
+  if (frames.size() > 0 && frames.back() != frameNumber) {
+    kept.push_back(window.back());
+    frames.push_back(frameNumber);
+  }
+  for (size_t k = 0; k < frames.size(); ++k) {
+    out_frames[k] = frames[k];
+    out_hashes[k] = kept[k];
+  }
+  return (long long)frames.size();
+}
+
+// makeVideoIndex over decoded frames: autocrop(20) + dctHash64 + compression
+long long orc_make_video_index(const uint8_t* frames, long long n, int w, int h, int threshold, int* out_frames,
+                               uint64_t* out_hashes) {
+  std::vector<uint64_t> hashes(n > 0 ? n : 0);
+  for (long long i = 0; i < n; ++i) {
+    int rect[4];
+    const uint8_t* f = frames + (size_t)i * w * h;
+    orc_autocrop(f, w, h, w, 20, rect);
+    hashes[i] = orc_dct_hash64_rect(f, w, h, w, rect, nullptr);
+  }
+  return orc_video_compress(hashes.data(), n, threshold, out_frames, out_hashes);
+}
+
 // ---------------------------------------------------------------------------------------------
 // DctHashIndex::find — src/dcthashindex.cpp:193-220. The shipped path is the VP tree (exact radius
 // search, strict `<`, src/tree/vptree.h:239,248); an exact radius search is order-insensitive, so the

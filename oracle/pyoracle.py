@@ -49,6 +49,13 @@ def oracle():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
         L.orc_dct_find_batch.restype = C.c_longlong
         L.orc_search_index_post.argtypes = [_u32p, _i32p, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        L.orc_autocrop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p]
+        L.orc_dct_hash64_rect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
+        L.orc_dct_hash64_rect.restype = C.c_uint64
+        L.orc_video_compress.argtypes = [_u64p, C.c_longlong, C.c_int, _i32p, _u64p]
+        L.orc_video_compress.restype = C.c_longlong
+        L.orc_make_video_index.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, _i32p, _u64p]
+        L.orc_make_video_index.restype = C.c_longlong
         L.orc_search_index_dct.argtypes = [_u64p, _u32p, C.c_longlong, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_int, _u32p, _i32p, C.c_int]
         L.orc_video_create.restype = C.c_void_p
@@ -306,3 +313,37 @@ class OracleOrbIndex:
             n = self.L.orc_orb_find(self.h, d.ctypes.data, len(d), int(needle_id), odt, out.ctypes.data, len(out))
         assert n <= len(out)
         return out[:n].copy()
+
+
+def autocrop(img, range_=20):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    rect = np.zeros(4, np.int32)
+    oracle().orc_autocrop(img.ctypes.data, w, h, img.strides[0], range_, rect)
+    return rect
+
+
+def dct_hash64_rect(img, rect, return_tile=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    tile = np.zeros((32, 32), np.uint8)
+    v = int(oracle().orc_dct_hash64_rect(img.ctypes.data, w, h, img.strides[0], np.ascontiguousarray(rect, np.int32),
+                                         tile.ctypes.data))
+    return (v, tile) if return_tile else v
+
+
+def video_compress(hashes, threshold=8):
+    hashes = np.ascontiguousarray(hashes, np.uint64)
+    of = np.zeros(len(hashes) + 1, np.int32)
+    oh = np.zeros(len(hashes) + 1, np.uint64)
+    n = oracle().orc_video_compress(hashes, len(hashes), threshold, of, oh)
+    return of[:n].copy(), oh[:n].copy()
+
+
+def make_video_index(frames, threshold=8):
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    of = np.zeros(n + 1, np.int32)
+    oh = np.zeros(n + 1, np.uint64)
+    k = oracle().orc_make_video_index(frames.ctypes.data, n, w, h, threshold, of, oh)
+    return of[:k].copy(), oh[:k].copy()
