@@ -34,6 +34,8 @@ class cb_stats(C.Structure):
 
 HIT_DTYPE = np.dtype([("needle", np.uint32), ("mediaId", np.uint32), ("score", np.int32)])
 PAIR_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("dist", np.uint32), ("pad", np.uint32)])
+TREE_MATCH_DTYPE = np.dtype([("needle", np.uint32), ("index", np.uint32), ("distance", np.int32), ("pad", np.uint32),
+                             ("hash", np.uint64)])
 MATCH_DTYPE = np.dtype([("mediaId", np.uint32), ("score", np.int32), ("srcIn", np.int32), ("dstIn", np.int32),
                         ("len", np.int32)])
 
@@ -96,6 +98,14 @@ SIGNATURES = {
     "cb_vdx_is_valid": (C.c_int, [_vp, _i64]),
     "cb_vdx_load_alloc": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(C.c_int)]),
     "cb_vdx_save": (C.c_int, [C.c_char_p, _vp, _vp, _i64, C.c_char_p]),
+    "cb_hamming_tree_create": (_vp, []),
+    "cb_hamming_tree_destroy": (None, [_vp]),
+    "cb_hamming_tree_insert": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "cb_hamming_tree_remove": (C.c_int, [_vp, _vp, _i64]),
+    "cb_hamming_tree_stats": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_i64)]),
+    "cb_hamming_tree_search_batch_alloc": (C.c_int, [_vp, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_hamming_tree_write": (C.c_int, [_vp, C.c_char_p]),
+    "cb_hamming_tree_read": (C.c_int, [_vp, C.c_char_p]),
     "cb_orb_index_create": (_vp, []),
     "cb_orb_index_destroy": (None, [_vp]),
     "cb_orb_index_load": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),

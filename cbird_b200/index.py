@@ -402,3 +402,42 @@ def _video_set_file(self, media_id, path):
 
 
 DctVideoIndex.setVideoFile = _video_set_file
+
+
+class HammingTree:
+    """src/tree/hammingtree.h HammingTree_t<uint32_t>: approximate LSB-trie search (DctFeaturesIndex's tree)."""
+
+    def __init__(self):
+        self._L = lib()
+        self._h = self._L.cb_hamming_tree_create()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.cb_hamming_tree_destroy(h)
+
+    def insert(self, indices, hashes):
+        i, h = _u32(indices), _u64(hashes)
+        assert len(i) == len(h)
+        check(self._L.cb_hamming_tree_insert(self._h, i.ctypes.data, h.ctypes.data, len(i)))
+
+    def remove(self, indices):
+        i = _u32(indices)
+        check(self._L.cb_hamming_tree_remove(self._h, i.ctypes.data, len(i)))
+
+    def stats(self):
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        check(self._L.cb_hamming_tree_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"numNodes": a.value, "maxHeight": b.value, "numValues": c.value}
+
+    def search(self, needle_hashes, threshold) -> np.ndarray:
+        q = _u64(np.atleast_1d(needle_hashes))
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        check(self._L.cb_hamming_tree_search_batch_alloc(self._h, q.ctypes.data, len(q), int(threshold), C.byref(ptr), C.byref(n)))
+        return _lib.take_array(ptr.value, n.value, _lib.TREE_MATCH_DTYPE)
+
+    def write(self, path):
+        check(self._L.cb_hamming_tree_write(self._h, str(path).encode()))
+
+    def read(self, path):
+        check(self._L.cb_hamming_tree_read(self._h, str(path).encode()))

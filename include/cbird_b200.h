@@ -78,6 +78,15 @@ typedef struct cb_scan_tile {
   uint32_t a_begin, a_count, b_begin, b_count;
 } cb_scan_tile;
 
+/* HammingTree_t::Match (src/tree/hammingtree.h:75-87) of a batched search */
+typedef struct cb_tree_match {
+  uint32_t needle;  /* index into the needle array of the call */
+  uint32_t index;   /* Value::index (0 = removed) */
+  int32_t distance;
+  uint32_t pad_;
+  uint64_t hash;    /* Value::hash */
+} cb_tree_match;
+
 typedef struct cb_stats {
   uint64_t comparisons;     /* pair tests issued by scan kernels since cb_stats_reset */
   uint64_t hits;            /* pairs under threshold */
@@ -231,6 +240,22 @@ int cb_vdx_is_valid(const uint8_t* data, int64_t size);                      /* 
 int cb_vdx_load_alloc(const char* path, int32_t** frames, uint64_t** hashes, int64_t* n, int* version);
 int cb_vdx_save(const char* path, const int32_t* frames, const uint64_t* hashes, int64_t n,
                 const char* writer_version);
+
+/* ---- HammingTree_t<uint32_t> (src/tree/hammingtree.h) — the approximate LSB-trie search that
+ * DctFeaturesIndex uses (leaves of <= 8192 hashes; a needle is compared only with the leaf its low bits
+ * select).  Same result sets as the reference, computed with the tile-list scan kernel. ------------ */
+typedef struct cb_hamming_tree cb_hamming_tree;
+cb_hamming_tree* cb_hamming_tree_create(void);
+void cb_hamming_tree_destroy(cb_hamming_tree* t);
+int cb_hamming_tree_insert(cb_hamming_tree* t, const uint32_t* indices, const uint64_t* hashes, int64_t n); /* :127-134 */
+int cb_hamming_tree_remove(cb_hamming_tree* t, const uint32_t* indices, int64_t n);   /* index -> 0, :137-139 */
+int cb_hamming_tree_stats(cb_hamming_tree* t, int32_t* num_nodes, int32_t* max_height, int64_t* num_values); /* :152-154 */
+/* search() for every needle: matches sorted by (needle, distance, index, hash); library-allocated */
+int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needles, int64_t n_needles, int threshold,
+                                       cb_tree_match** out, int64_t* n_out);
+/* cache file format v2 (:156-200,:472-521), byte-compatible with the reference's reader/writer */
+int cb_hamming_tree_write(cb_hamming_tree* t, const char* path);
+int cb_hamming_tree_read(cb_hamming_tree* t, const char* path);
 
 /* ---- CvFeaturesIndex (src/cvfeaturesindex.{h,cpp}): 256-bit ORB descriptors, kernel (c) ----------
  * Descriptors are rows of 32 bytes (cv::Mat N x 32 CV_8U); media m owns rows

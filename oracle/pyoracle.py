@@ -116,6 +116,14 @@ def ref():
         L.ref_radix_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, _u32p, _i32p, _u64p, _i32p, C.c_int]
         L.ref_radix_search_batch_count.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.ref_radix_search_batch_count.restype = C.c_longlong
+        L.ref_htree_create.restype = C.c_void_p
+        L.ref_htree_destroy.argtypes = [C.c_void_p]
+        L.ref_htree_insert.argtypes = [C.c_void_p, _u32p, _u64p, C.c_int]
+        L.ref_htree_remove.argtypes = [C.c_void_p, _u32p, C.c_int]
+        L.ref_htree_search.argtypes = [C.c_void_p, C.c_uint64, C.c_int, _u32p, _u64p, _i32p, C.c_int]
+        L.ref_htree_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_htree_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_htree_read.argtypes = [C.c_void_p, C.c_char_p]
         _ref = L
     return _ref
 
@@ -347,3 +355,40 @@ def make_video_index(frames, threshold=8):
     oh = np.zeros(n + 1, np.uint64)
     k = oracle().orc_make_video_index(frames.ctypes.data, n, w, h, threshold, of, oh)
     return of[:k].copy(), oh[:k].copy()
+
+
+class RefHammingTree:
+    """the reference's own HammingTree_t<uint32_t> (src/tree/hammingtree.h compiled unmodified)."""
+
+    def __init__(self):
+        self.L = ref()
+        self.h = self.L.ref_htree_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_htree_destroy(self.h)
+            self.h = None
+
+    def insert(self, indices, hashes):
+        self.L.ref_htree_insert(self.h, np.ascontiguousarray(indices, np.uint32), np.ascontiguousarray(hashes, np.uint64),
+                                len(indices))
+
+    def remove(self, indices):
+        self.L.ref_htree_remove(self.h, np.ascontiguousarray(indices, np.uint32), len(indices))
+
+    def stats(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.L.ref_htree_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"numNodes": a.value, "maxHeight": b.value, "numValues": c.value}
+
+    def search(self, hash_, threshold, cap=1 << 16):
+        oi, oh, od = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.int32)
+        n = self.L.ref_htree_search(self.h, int(hash_), int(threshold), oi, oh, od, cap)
+        assert n <= cap
+        return oi[:n].copy(), oh[:n].copy(), od[:n].copy()
+
+    def write(self, path):
+        assert self.L.ref_htree_write(self.h, str(path).encode()) == 0
+
+    def read(self, path):
+        return self.L.ref_htree_read(self.h, str(path).encode())

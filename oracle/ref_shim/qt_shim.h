@@ -9,6 +9,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -29,6 +30,26 @@ typedef uint32_t mediaid_t;  // src/global.h:66
   C(C&&) = delete;             \
   C& operator=(C&&) = delete;
 
-#define qWarning(...) ((void)fprintf(stderr, __VA_ARGS__), (void)fputc('\n', stderr))
-#define qInfo(...) ((void)0)
-#define qDebug(...) ((void)0)
+// qDebug()/qInfo()/qWarning(): both the printf form and the `<<` stream form appear in the headers
+struct QtNullStream {
+  template <typename T>
+  QtNullStream& operator<<(const T&) { return *this; }
+};
+inline QtNullStream qt_quiet(const char* = nullptr, ...) { return QtNullStream(); }
+inline QtNullStream qt_warn(const char* fmt = nullptr, ...) {
+  if (fmt) {
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+  }
+  return QtNullStream();
+}
+#define qWarning(...) qt_warn(__VA_ARGS__)
+#define qInfo(...) qt_quiet(__VA_ARGS__)
+#define qDebug(...) qt_quiet(__VA_ARGS__)
+
+// src/global.h:58-62 (typed malloc/realloc helpers the tree headers call)
+#define strict_malloc(ptr, count) reinterpret_cast<decltype(ptr)>(malloc(uint(count) * sizeof(*ptr)))
+#define strict_realloc(ptr, count) reinterpret_cast<decltype(ptr)>(realloc(ptr, uint(count) * sizeof(*ptr)))

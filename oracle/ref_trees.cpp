@@ -5,13 +5,18 @@
 //     /root/reference/src/hamm.h            hamm64()
 //     /root/reference/src/tree/vptree.h     VpTree  (what DctHashIndex ships, dcttree.h:26 VPTREE)
 //     /root/reference/src/tree/radix.h      RadixMap_t (what DctVideoIndex ships, dctvideoindex.h:58-60)
+//     /root/reference/src/tree/hammingtree.h HammingTree_t (what DctFeaturesIndex ships, incl. its cache file IO)
 // and exposes them through a flat C interface for ctypes.  The DctTree glue below restates
 // src/tree/dcttree.h:103-138 (it cannot be included: it pulls in index.h → Qt).
 #include "ref_shim/qt_shim.h"
+#include "ref_shim/qt_io_stub.h"
+
+#include <string.h>
 
 #include "hamm.h"
 #include "tree/vptree.h"
 #include "tree/radix.h"
+#include "tree/hammingtree.h"
 
 #include <chrono>
 #include <thread>
@@ -174,6 +179,58 @@ long long ref_radix_search_batch_count(void* r, const uint64_t* needles, int nq,
   long long total = 0;
   for (auto c : counts) total += c;
   return total;
+}
+
+
+// ---- HammingTree_t<uint32_t> : hammingtree.h ----------------------------------------------------
+typedef HammingTree_t<uint32_t> RefHammingTree;
+
+void* ref_htree_create() { return new RefHammingTree; }
+void ref_htree_destroy(void* t) { delete static_cast<RefHammingTree*>(t); }
+void ref_htree_insert(void* t, const uint32_t* indices, const uint64_t* hashes, int n) {
+  std::vector<RefHammingTree::Value> values;
+  values.reserve(n);
+  for (int i = 0; i < n; ++i) values.push_back(RefHammingTree::Value(indices[i], hashes[i]));
+  static_cast<RefHammingTree*>(t)->insert(values);
+}
+void ref_htree_remove(void* t, const uint32_t* indices, int n) {
+  std::unordered_set<uint32_t> set(indices, indices + n);
+  static_cast<RefHammingTree*>(t)->remove(set);
+}
+// matches sorted by distance (std::sort, ties in unspecified order)
+int ref_htree_search(void* t, uint64_t hash, int threshold, uint32_t* out_index, uint64_t* out_hash, int* out_dist,
+                     int cap) {
+  std::vector<RefHammingTree::Match> matches;
+  static_cast<RefHammingTree*>(t)->search(hash, threshold, matches);
+  int n = int(matches.size());
+  for (int i = 0; i < n && i < cap; ++i) {
+    out_index[i] = matches[i].value.index;
+    out_hash[i] = matches[i].value.hash;
+    out_dist[i] = matches[i].distance;
+  }
+  return n;
+}
+void ref_htree_stats(void* t, int* num_nodes, int* max_height, int* num_values) {
+  RefHammingTree::Stats st = static_cast<RefHammingTree*>(t)->stats();
+  *num_nodes = st.numNodes;
+  *max_height = st.maxHeight;
+  *num_values = st.numValues;
+}
+int ref_htree_write(void* t, const char* path) {
+  FILE* fp = fopen(path, "wb");
+  if (!fp) return -1;
+  QFile f(fp);
+  static_cast<RefHammingTree*>(t)->write(f);
+  fclose(fp);
+  return 0;
+}
+int ref_htree_read(void* t, const char* path) {
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return -1;
+  QFile f(fp);
+  bool ok = static_cast<RefHammingTree*>(t)->read(f);
+  fclose(fp);
+  return ok ? 0 : -2;
 }
 
 }  // extern "C"
