@@ -62,6 +62,7 @@ SIGNATURES = {
     "cb_make_video_index_alloc": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_hash_tables": (None, [_vp, _vp]),
     "cb_scan64_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
+    "cb_scan64_self_dev": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),

@@ -75,6 +75,8 @@ struct Scan64Launch {
   cb_pair* out;
   unsigned long long cap;
   unsigned long long* count;
+  uint32_t b_lo = 0;       // dense scan only: B rows [b_lo, n_b), indices stay absolute
+  bool symmetric = false;  // dense scan only: A == B, test tiles on/above the diagonal and mirror the hits
 };
 int scan64_launch(const Scan64Launch& L, cudaStream_t stream);
 int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, uint64_t pair_tests,

@@ -112,7 +112,8 @@ struct DctIndex {
   // and sorted on the host into *host_small (one stream sync in total) and *done_on_host is set.
   int search_device(const uint64_t* d_q, uint32_t n_q, uint32_t row_begin, uint32_t row_end, int threshold,
                     const uint32_t* d_needle_ids, uint32_t needle_offset, unsigned long long* n_valid_out,
-                    std::vector<cb_hit>* host_small = nullptr, bool* done_on_host = nullptr) {
+                    std::vector<cb_hit>* host_small = nullptr, bool* done_on_host = nullptr,
+                    bool symmetric_self = false) {
     *n_valid_out = 0;
     if (done_on_host) *done_on_host = false;
     const uint32_t n_rows = row_end - row_begin;
@@ -126,7 +127,11 @@ struct DctIndex {
       cap = d_pairs.cap;
       CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 2 * sizeof(unsigned long long), stream));
       Scan64Launch L;
-      if (swapped) {
+      if (symmetric_self) {
+        // `-similar` over the whole index: d(a,b) == d(b,a), so only tiles on/above the diagonal are
+        // tested and every off-diagonal hit is emitted in both orders (half the pair tests)
+        L = Scan64Launch{d_hashes.p, n_rows, d_hashes.p, n_rows, threshold, 0, d_pairs.p, cap, d_counts.p, 0, true};
+      } else if (swapped) {
         L = Scan64Launch{d_hashes.p + row_begin, n_rows, d_q, n_q, threshold, 0, d_pairs.p, cap, d_counts.p};
       } else {
         L = Scan64Launch{d_q, n_q, d_hashes.p + row_begin, n_rows, threshold, 0, d_pairs.p, cap, d_counts.p};
@@ -302,7 +307,8 @@ int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, i
 }
 
 static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int threshold, int64_t row_begin,
-                          int64_t row_end, bool self_needles, bool filter_self, std::vector<cb_hit>& out) {
+                          int64_t row_end, bool self_needles, bool filter_self, std::vector<cb_hit>& out,
+                          bool symmetric_ok = false) {
   out.clear();
   if (!I.loaded) {
     set_error("index not loaded");
@@ -329,9 +335,10 @@ static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int 
   unsigned long long n_valid = 0;
   bool on_host = false;
   const bool latency_path = !self_needles && size_t(nq) <= DctIndex::kStageNeedles;
+  const bool symmetric = self_needles && row_begin == 0 && row_end == int64_t(I.d_rows) && symmetric_ok;
   rc = I.search_device(d_q, uint32_t(nq), uint32_t(row_begin), uint32_t(row_end), threshold,
                        (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid, latency_path ? &out : nullptr,
-                       &on_host);
+                       &on_host, symmetric);
   if (rc != CB_OK) return rc;
   if (on_host) return CB_OK;
   out.resize(n_valid);
@@ -432,7 +439,7 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   const int dht = p->dctThresh;
   const bool escalate = p->maxThresh > 0 && p->maxThresh > dht;
   const int scan_thresh = escalate ? p->maxThresh : dht;
-  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, hits);
+  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, hits, true);
   if (rc != CB_OK) return rc;
   // searchIndex post step (database.cpp:1729-1737): hits are already sorted by (needle, score, id);
   // drop the needle itself when filterSelf, cut every needle's list at maxMatches. Needles without

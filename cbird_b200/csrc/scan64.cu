@@ -41,6 +41,8 @@ struct ScanParams {
   const uint64_t* __restrict__ b;
   uint32_t n_a, n_b;
   uint32_t slab;        // B rows per blockIdx.y, multiple of kBTile
+  uint32_t b_lo;        // dense kernel: first B row searched (B rows [b_lo, n_b))
+  int symmetric;        // A and B are the same array: test only tiles on/above the diagonal, mirror hits
   int threshold;
   uint32_t radix_mask;  // bucket bits of (h >> 1); 0 = no bucket predicate
   cb_pair* out;
@@ -52,21 +54,20 @@ struct TileBounds {
   uint32_t a_base;   // A row of thread 0, register 0
   uint32_t a_limit;  // first invalid A row
   uint32_t b_begin, b_end;
+  uint32_t mirror_above;  // B tiles starting above this row also emit the mirrored pair (0xFFFFFFFF = never)
 };
 
 __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds& B, uint32_t alo, uint32_t ahi,
-                                           uint32_t blo, uint32_t bhi, uint32_t ai, uint32_t bi) {
+                                           uint32_t blo, uint32_t bhi, uint32_t ai, uint32_t bi, bool mirror) {
   // opaque copies: without them the compiler shares the XORs of this rare path with the pre-filter
   // and the hot loop grows from 3 to 6 LOP3 per pair of pairs (seen in SASS / ncu: ALU pipe 92 %)
   asm volatile("" : "+r"(alo), "+r"(ahi));
   const uint32_t xlo = alo ^ blo;
   const int d = __popc(xlo) + __popc(ahi ^ bhi);
   if (d < P.threshold && ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
-    const unsigned long long pos = atomicAdd(P.count, 1ull);
-    if (pos < P.cap) {
-      uint4 rec = make_uint4(ai, bi, uint32_t(d), 0u);
-      *reinterpret_cast<uint4*>(P.out + pos) = rec;
-    }
+    const unsigned long long pos = atomicAdd(P.count, mirror ? 2ull : 1ull);
+    if (pos < P.cap) *reinterpret_cast<uint4*>(P.out + pos) = make_uint4(ai, bi, uint32_t(d), 0u);
+    if (mirror && pos + 1 < P.cap) *reinterpret_cast<uint4*>(P.out + pos + 1) = make_uint4(bi, ai, uint32_t(d), 0u);
   }
 }
 
@@ -101,6 +102,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
     }
     __syncthreads();
     const int pairs = (min(uint32_t(kBTile), slab_end - t0) + 1) >> 1;
+    const bool mirror = t0 > B.mirror_above;  // symmetric self-scan: tile strictly above the diagonal
 
 #pragma unroll 2
     for (int j = 0; j < pairs; ++j) {
@@ -121,8 +123,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
           for (int r = 0; r < kR; ++r)
             if (int(p[r]) < T) {
               const uint32_t ai = a_base + r * kThreads;
-              emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
-              emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+              emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+              emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
             }
         }
       } else if (VARIANT == 1) {
@@ -140,8 +142,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
-            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
           }
         }
       } else {
@@ -159,8 +161,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi);
-            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
           }
         }
       }
@@ -175,8 +177,15 @@ __global__ void __launch_bounds__(kThreads, 3) scan64_kernel(const ScanParams P)
   TileBounds B;
   B.a_base = blockIdx.x * kABlock;
   B.a_limit = P.n_a;
-  B.b_begin = blockIdx.y * P.slab;
+  B.b_begin = P.b_lo + blockIdx.y * P.slab;
   B.b_end = min(B.b_begin + P.slab, P.n_b);
+  B.mirror_above = 0xFFFFFFFFu;
+  if (P.symmetric) {
+    // tiles below this A block's diagonal tile are covered (mirrored) by the CTAs that own them as A
+    B.b_begin = max(B.b_begin, B.a_base);
+    B.mirror_above = B.a_base;
+    if (B.b_begin >= B.b_end) return;
+  }
   scan_tile<VARIANT>(P, B, tile);
 }
 
@@ -192,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 3)
   B.a_limit = t.a_begin + t.a_count;
   B.b_begin = t.b_begin;
   B.b_end = t.b_begin + t.b_count;
+  B.mirror_above = 0xFFFFFFFFu;
   scan_tile<VARIANT>(P, B, tile);
 }
 
@@ -231,9 +241,16 @@ int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
   P.out = L.out;
   P.cap = L.cap;
   P.count = L.count;
+  P.b_lo = L.b_lo;
+  P.symmetric = L.symmetric ? 1 : 0;
+  if (L.b_lo >= L.n_b) return CB_OK;
+  if (L.symmetric && (L.a != L.b || L.n_a != L.n_b || (L.b_lo % kBTile) != 0)) {
+    set_error("scan64: the symmetric self-scan needs A == B and a %d-aligned first row", kBTile);
+    return CB_ERR_INVALID;
+  }
 
   const uint32_t a_blocks = (L.n_a + kABlock - 1) / kABlock;
-  const uint32_t b_tiles = (L.n_b + kBTile - 1) / kBTile;
+  const uint32_t b_tiles = (L.n_b - L.b_lo + kBTile - 1) / kBTile;
   // enough CTAs for ~24 waves of 148 SMs x 3 resident CTAs when the job is large, never more
   // slabs than tiles, and gridDim.y <= 65535
   const uint32_t target_ctas = 148u * 3u * 24u;
@@ -253,7 +270,7 @@ int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
   }
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
-  counters().comparisons += uint64_t(L.n_a) * uint64_t(L.n_b);
+  counters().comparisons += uint64_t(L.n_a) * uint64_t(L.n_b - L.b_lo);  // nominal (reference semantics)
   return CB_OK;
 }
 
@@ -270,6 +287,8 @@ int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint
   P.n_a = L.n_a;
   P.n_b = L.n_b;
   P.slab = 0;
+  P.b_lo = 0;
+  P.symmetric = 0;
   P.threshold = L.threshold > 65 ? 65 : L.threshold;
   P.radix_mask = L.radix_bits ? ((1u << L.radix_bits) - 1u) : 0u;
   P.out = L.out;
@@ -297,7 +316,7 @@ int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, 
                         void* stream) {
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
-  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, 0, d_out, cap, d_count};
+  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, 0, d_out, cap, d_count, 0, false};
   return scan64_tiles_launch(L, d_tiles, n_tiles, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -305,7 +324,25 @@ int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32
                   int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
-  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, radix_bits, d_out, cap, d_count};
+  Scan64Launch L{d_a, n_a, d_b, n_b, threshold, radix_bits, d_out, cap, d_count, 0, false};
+  return scan64_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin, uint32_t row_end, int threshold,
+                       int symmetric, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  if (row_end > n || row_begin > row_end) {
+    set_error("cb_scan64_self_dev: rows [%u,%u) outside [0,%u)", row_begin, row_end, n);
+    return CB_ERR_INVALID;
+  }
+  // A = all rows (the needles); B = the same array limited to [row_begin, row_end)
+  Scan64Launch L{d_hashes, symmetric ? n : n, d_hashes, row_end, threshold, 0, d_out, cap, d_count, row_begin, symmetric != 0};
+  if (symmetric && row_end != n) {
+    // rows above the shard are not searched, but the diagonal rule needs A == B: restrict A as well;
+    // pairs (a >= row_end, b in shard) are covered by mirroring from the ranks that own those rows
+    L.n_a = row_end;
+  }
   return scan64_launch(L, static_cast<cudaStream_t>(stream));
 }
 

@@ -40,45 +40,74 @@ def allgather_hits(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
 
+TILE_ROWS = 2048  # scan kernel tile (A block == B tile), the granularity of the symmetric self-scan
+
+
+def shard_rows_symmetric(n_rows: int, rank: int, world: int):
+    """row range of `rank` for the symmetric self-scan.  B tile j costs (j+1) tile pairs (only A blocks
+    on/below it are tested), so equal-cost contiguous ranges have boundaries at tiles * sqrt(k / world)."""
+    tiles = (n_rows + TILE_ROWS - 1) // TILE_ROWS
+    def bound(k):
+        return min(n_rows, int(round(tiles * (k / world) ** 0.5)) * TILE_ROWS)
+    return bound(rank), (n_rows if rank == world - 1 else bound(rank + 1))
+
+
+def issued_pair_tests(n_rows: int, begin: int, end: int, symmetric: bool) -> int:
+    """pair tests the scan kernel really issues for needles = all rows vs searched rows [begin, end)."""
+    if not symmetric:
+        return n_rows * (end - begin)
+    total = 0
+    for t0 in range(begin, end, TILE_ROWS):
+        rows = min(TILE_ROWS, end - t0)
+        total += min(end, t0 + TILE_ROWS) * rows  # A rows [0, end of this diagonal tile)
+    return total
+
+
 class ShardedSimilar:
     """`-similar` all-pairs over an index sharded by row across the ranks of the default process group.
 
     Every rank holds all hashes (they are also the needles: 8 B each), scans only its own row shard
     with the C-ABI scan kernel, and the (needle, row, distance) lists are merged with allgather_hits.
+    symmetric=True (default) uses d(a,b) == d(b,a): each rank tests only the 2048-row tiles on/above
+    the diagonal of its shard and emits every off-diagonal hit in both orders — half the pair tests,
+    the same merged hit set.
     """
 
-    def __init__(self, n_rows: int, device: torch.device, cap: int = 1 << 22):
+    def __init__(self, n_rows: int, device: torch.device, cap: int = 1 << 22, symmetric: bool = True):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.n_rows = n_rows
         self.device = device
-        self.begin, self.end = shard_rows(n_rows, self.rank, self.world)
+        self.symmetric = symmetric
+        if symmetric:
+            self.begin, self.end = shard_rows_symmetric(n_rows, self.rank, self.world)
+        else:
+            self.begin, self.end = shard_rows(n_rows, self.rank, self.world)
         self.cap = cap
         self.pairs = torch.empty((cap, 4), dtype=torch.int32, device=device)
         self.count = torch.zeros(1, dtype=torch.int64, device=device)
         self._L = lib()
 
+    def issued_pair_tests(self) -> int:
+        return issued_pair_tests(self.n_rows, self.begin, self.end, self.symmetric)
+
     def scan_local(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
-        """this rank's shard: needles = all rows (A side), rows [begin,end) on the B side.
-        Returns [m,4] int32 (needle, GLOBAL row, dist, 0) on the device."""
+        """this rank's shard: needles = all rows, searched rows [begin,end).
+        Returns [m,4] int32 (needle row, matched row, dist, 0) on the device, rows absolute."""
         assert d_hashes.dtype == torch.int64 and d_hashes.is_cuda and d_hashes.numel() == self.n_rows
         stream = torch.cuda.current_stream(self.device).cuda_stream
         while True:
             self.count.zero_()
-            n_b = self.end - self.begin
-            if n_b > 0:
-                check(self._L.cb_scan64_dev(d_hashes.data_ptr(), self.n_rows, d_hashes.data_ptr() + 8 * self.begin, n_b,
-                                            int(threshold), 0, self.pairs.data_ptr(), self.cap, self.count.data_ptr(),
-                                            C.c_void_p(stream)))
+            if self.end > self.begin:
+                check(self._L.cb_scan64_self_dev(d_hashes.data_ptr(), self.n_rows, self.begin, self.end, int(threshold),
+                                                 1 if self.symmetric else 0, self.pairs.data_ptr(), self.cap,
+                                                 self.count.data_ptr(), C.c_void_p(stream)))
             m = int(self.count.item())
             if m <= self.cap:
                 break
             self.cap = m + m // 8 + 1024  # overflow: the exact size is known now
             self.pairs = torch.empty((self.cap, 4), dtype=torch.int32, device=self.device)
-        out = self.pairs[:m]
-        if self.begin:
-            out[:, 1] += self.begin
-        return out
+        return self.pairs[:m]
 
     def similar(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
         return allgather_hits(self.scan_local(d_hashes, threshold))

@@ -144,6 +144,13 @@ void cb_hash_tables(float* basis_9x32, int32_t* zigzag81);
  * Asynchronous on `stream`. ---------------------------------------------------------------------- */
 int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
                   int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
+/* `-similar` self-scan: needles = rows [0,n) of d_hashes, searched rows = [row_begin,row_end); indices
+ * in the hits are absolute rows. symmetric=1 halves the pair tests: d(a,b)==d(b,a), so only 2048-row
+ * tiles on/above the diagonal are tested, rows >= row_end are left to the ranks that own them, and every
+ * off-diagonal hit is emitted as (a,b) and (b,a); the union over a tile-aligned partition of the rows is
+ * exactly the full -similar hit set (row_begin must be a multiple of 2048). */
+int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin, uint32_t row_end, int threshold,
+                       int symmetric, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
 /* same inner loop over an explicit list of (A block, B range) work items, one CTA each — the
  * radix-bucket search of DctVideoIndex (src/tree/radix.h:187-210 scans one bucket per needle frame) */
 int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b,

@@ -224,3 +224,48 @@ def test_large_property_checks(cb):
     both = np.concatenate([h0, h1])
     assert len(both) == len(hits)
     assert np.array_equal(np.sort(both, order=["needle", "mediaId", "score"]), np.sort(hits, order=["needle", "mediaId", "score"]))
+
+
+@pytest.mark.parametrize("n", [5000, 2048, 4096, 10000])
+@pytest.mark.parametrize("world", [1, 3])
+def test_symmetric_self_scan_equals_full(cb, po, n, world):
+    # d(a,b)==d(b,a): tiles on/above the diagonal + mirrored hits == the full all-pairs hit set, also when
+    # the rows are split into tile-aligned shards (the multi-GPU layout of parallel.ShardedSimilar)
+    import ctypes as C
+
+    import torch
+
+    from cbird_b200 import parallel
+
+    h, ids = synth.dct_hashes(n, seed=n + world, planted_frac=0.3)
+    d = torch.from_numpy(h.view(np.int64)).cuda()
+    want, total, _ = po.dct_find_batch(h, np.arange(n, dtype=np.uint32) + 1, h, 5, threads=4)
+    want = want.copy()
+    want[:, 1] -= 1
+    L = cb.lib()
+    cap = 1 << 20
+    got = []
+    issued = 0
+    for r in range(world):
+        b, e = parallel.shard_rows_symmetric(n, r, world)
+        assert b % 2048 == 0 and (r == 0) == (b == 0) or world == 1 or b <= e
+        out = torch.empty((cap, 4), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if e > b:
+            assert L.cb_scan64_self_dev(d.data_ptr(), n, b, e, 5, 1, out.data_ptr(), cap, cnt.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        got.append(out[: int(cnt.item())].cpu().numpy().astype(np.int64))
+        issued += parallel.issued_pair_tests(n, b, e, True)
+    got = np.concatenate(got)[:, :3]
+    got = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))]
+    assert len(got) == total and np.array_equal(got, want)
+    assert issued < n * n * 0.75 or n <= 4096
+    # and the non-symmetric shard API returns exactly the shard's rows
+    out = torch.empty((cap, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lo, hi = n // 3 // 2 * 2, n // 3 * 2
+    assert L.cb_scan64_self_dev(d.data_ptr(), n, lo, hi, 5, 0, out.data_ptr(), cap, cnt.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    part = out[: int(cnt.item())].cpu().numpy().astype(np.int64)[:, :3]
+    part = part[np.lexsort((part[:, 2], part[:, 1], part[:, 0]))]
+    assert np.array_equal(part, want[(want[:, 1] >= lo) & (want[:, 1] < hi)])

@@ -78,3 +78,19 @@ def test_shard_rows_cover_everything():
             for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
                 assert e0 == b1 and b0 <= e0
             assert all(b % 2 == 0 or b == n for b, _ in spans)
+
+
+def test_symmetric_shards_are_tile_aligned_and_balanced():
+    from cbird_b200 import parallel
+
+    for n in (2048, 10000, 1048576, 2969600):
+        for world in (1, 2, 4, 8):
+            spans = [parallel.shard_rows_symmetric(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1 and b0 <= e0 and (b1 % 2048 == 0 or b1 == n)
+            cost = [parallel.issued_pair_tests(n, b, e, True) for b, e in spans]
+            assert sum(cost) <= n * (n + 2048) // 2 + 2048 * 2048
+            if n >= 1048576:
+                assert max(cost) / (sum(cost) / world) < 1.05  # equal-cost ranges
+            assert sum(parallel.issued_pair_tests(n, b, e, False) for b, e in spans) == n * n
