@@ -2,6 +2,7 @@
 missing or a call fails: there is no CPU fallback anywhere in this package."""
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -144,12 +145,12 @@ def check(status):
 
 
 def take_array(ptr, n, dtype):
-    """copy a library-allocated array into numpy and release it with cb_free."""
-    try:
-        if n == 0 or not ptr:
-            return np.zeros(0, dtype)
-        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
-        return np.frombuffer(buf, dtype=dtype, count=n).copy()
-    finally:
+    """wrap a library-allocated array as numpy WITHOUT copying; cb_free runs when the array is collected."""
+    if n == 0 or not ptr:
         if ptr:
             lib().cb_free(ptr)
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    weakref.finalize(buf, lib().cb_free, ptr)  # arr.base keeps buf alive; freeing follows the last view
+    return arr

@@ -306,9 +306,14 @@ int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, i
   return (out && k > cap) ? CB_ERR_CAPACITY : CB_OK;
 }
 
+struct RawHits {  // malloc'ed result buffer handed to the caller (cb_free) without another copy
+  cb_hit* p = nullptr;
+  size_t n = 0;
+};
+
 static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int threshold, int64_t row_begin,
                           int64_t row_end, bool self_needles, bool filter_self, std::vector<cb_hit>& out,
-                          bool symmetric_ok = false) {
+                          bool symmetric_ok = false, RawHits* raw = nullptr) {
   out.clear();
   if (!I.loaded) {
     set_error("index not loaded");
@@ -340,6 +345,21 @@ static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int 
                        (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid, latency_path ? &out : nullptr,
                        &on_host, symmetric);
   if (rc != CB_OK) return rc;
+  if (raw) {
+    raw->n = on_host ? out.size() : size_t(n_valid);
+    raw->p = static_cast<cb_hit*>(malloc(std::max<size_t>(1, raw->n) * sizeof(cb_hit)));
+    if (!raw->p) {
+      set_error("out of host memory");
+      return CB_ERR_INVALID;
+    }
+    if (on_host) {
+      if (raw->n) memcpy(raw->p, out.data(), raw->n * sizeof(cb_hit));
+    } else if (raw->n) {
+      CB_CUDA(cudaMemcpyAsync(raw->p, I.d_hits.p, raw->n * sizeof(cb_hit), cudaMemcpyDeviceToHost, I.stream));
+      CB_CUDA(cudaStreamSynchronize(I.stream));
+    }
+    return CB_OK;
+  }
   if (on_host) return CB_OK;
   out.resize(n_valid);
   if (n_valid) {
@@ -432,32 +452,41 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   DctIndex& I = ix->impl;
   std::lock_guard<std::mutex> lock(I.mu);
   const int64_t n = int64_t(I.hashes.size());
-  std::vector<cb_hit> hits;
   // maxThresh escalation (database.cpp:1703-1725): the reference re-runs find() with dht+1, dht+2, ...
   // while the needle has <= minMatches matches (self included) and the threshold stays <= maxThresh.
   // One scan at the largest threshold any needle can reach gives every one of those result sets.
   const int dht = p->dctThresh;
   const bool escalate = p->maxThresh > 0 && p->maxThresh > dht;
   const int scan_thresh = escalate ? p->maxThresh : dht;
-  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, hits, true);
-  if (rc != CB_OK) return rc;
+  std::vector<cb_hit> scratch;
+  RawHits raw;
+  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, scratch, true, &raw);
+  if (rc != CB_OK) {
+    free(raw.p);
+    return rc;
+  }
+  cb_hit* hits = raw.p;
+  const size_t n_hits = raw.n;
   // searchIndex post step (database.cpp:1729-1737): hits are already sorted by (needle, score, id);
   // drop the needle itself when filterSelf, cut every needle's list at maxMatches. Needles without
-  // hash find nothing.
+  // hash find nothing. Compaction happens in place in the buffer that is handed to the caller.
   int64_t* offsets = static_cast<int64_t*>(malloc(size_t(n + 1) * sizeof(int64_t)));
   if (!offsets) {
+    free(raw.p);
     set_error("out of host memory");
     return CB_ERR_INVALID;
   }
   const int64_t max_matches = p->maxMatches < 0 ? 0 : p->maxMatches;
+  const bool filter_self = p->filterSelf != 0;
+  const uint64_t* row_hash = I.hashes.data();
+  const uint32_t* row_id = I.ids.data();
   size_t w = 0, i = 0;
   for (int64_t row = 0; row < n; ++row) {
     offsets[row] = int64_t(w);
     size_t j = i;
-    while (j < hits.size() && int64_t(hits[j].needle) == row) ++j;
-    if (I.hashes[row] != 0) {
-      // effective threshold of this needle
-      int t = dht;
+    while (j < n_hits && int64_t(hits[j].needle) == row) ++j;
+    if (row_hash[row] != 0) {
+      int t = dht;  // effective threshold of this needle
       if (escalate) {
         for (;;) {
           size_t cnt = 0;
@@ -468,21 +497,18 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
       }
       int64_t kept = 0;
       for (size_t k = i; k < j && hits[k].score < t; ++k) {
-        if (p->filterSelf && hits[k].mediaId == I.ids[row]) continue;
+        if (filter_self && hits[k].mediaId == row_id[row]) continue;
         if (kept >= max_matches) break;
-        hits[w++] = hits[k];
+        if (w != k) hits[w] = hits[k];
+        ++w;
         ++kept;
       }
     }
     i = j;
   }
   offsets[n] = int64_t(w);
-  hits.resize(w);
-  rc = export_hits(hits, hits_out, n_hits_out);
-  if (rc != CB_OK) {
-    free(offsets);
-    return rc;
-  }
+  *hits_out = hits;
+  *n_hits_out = int64_t(w);
   *offsets_out = offsets;
   return CB_OK;
 }
