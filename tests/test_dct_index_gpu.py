@@ -269,3 +269,63 @@ def test_symmetric_self_scan_equals_full(cb, po, n, world):
     part = out[: int(cnt.item())].cpu().numpy().astype(np.int64)[:, :3]
     part = part[np.lexsort((part[:, 2], part[:, 1], part[:, 0]))]
     assert np.array_equal(part, want[(want[:, 1] >= lo) & (want[:, 1] < hi)])
+
+
+def test_cfg3_10M_all_pairs_properties(cb):
+    # BASELINE configs[2] size on one GPU (no oracle at this size): 10^7 rows, 10^14 nominal comparisons
+    n = 10_000_000
+    h, ids = synth.dct_hashes_fast(n, seed=3)
+    ix = cb.DctHashIndex()
+    ix.load(ids, h)
+    off, hits = ix.similar(cb.SearchParams(dctThresh=5, filterSelf=False, maxMatches=1 << 30))
+    assert len(off) == n + 1 and off[-1] == len(hits)
+    a = hits["needle"].astype(np.int64)
+    b = hits["mediaId"].astype(np.int64) - 1
+    assert np.all(np.diff(off) >= 1)                       # every row finds itself ...
+    assert int((a == b).sum()) == n                        # ... exactly once
+    assert np.array_equal(np.sort(a * n + b), np.sort(b * n + a))  # symmetric hit set
+    x = h[a] ^ h[b]
+    d = np.zeros(len(x), np.int64)
+    for s in range(0, 64, 8):
+        byte = ((x >> np.uint64(s)) & np.uint64(0xFF)).astype(np.uint8)
+        d += np.unpackbits(byte[:, None], axis=1).sum(axis=1)
+    assert np.array_equal(d, hits["score"].astype(np.int64)) and d.max() < 5
+    assert len(hits) > n + n // 50                         # the planted near-duplicates are there
+
+
+def test_100M_rows_needle_search(cb):
+    # the north-star index size: 10^8 rows (1.2 GB in HBM); 32-bit row arithmetic, ragged tail, planted rows
+    n = 100_000_003
+    rng = np.random.default_rng(8)
+    h = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) << np.uint64(1)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    rows = np.array([0, 1, 2047, 2048, 77_777_777, n - 2049, n - 2, n - 1], dtype=np.int64)
+    needles = h[rows].copy()
+    needles ^= np.uint64(1) << np.arange(1, 9, dtype=np.uint64)  # distance 1 from their row
+    ix = cb.DctHashIndex()
+    ix.load(ids, h)
+    assert ix.count() == n and ix.memoryUsage() == 12 * n
+    got = ix.find_batch(needles, cb.SearchParams(dctThresh=2))
+    assert got["needle"].tolist() == list(range(8))
+    assert got["mediaId"].tolist() == (rows + 1).tolist() and got["score"].tolist() == [1] * 8
+    m = ix.find(cb.Media(dctHash=int(h[n - 1])), cb.SearchParams(dctThresh=1))
+    assert [(x.mediaId, x.score) for x in m] == [(n, 0)]
+
+
+def test_concurrent_find_from_many_threads(cb, po, cfg1, index):
+    # Index::find is called from every pool thread under a read lock (src/database.cpp:1400,1698)
+    from concurrent.futures import ThreadPoolExecutor
+
+    h, ids = cfg1
+    rows = list(range(0, 10000, 125))
+    sp = cb.SearchParams(dctThresh=5)
+
+    def one(row):
+        return [(m.score, m.mediaId) for m in index.find(cb.Media(id=int(ids[row]), dctHash=int(h[row])), sp)]
+
+    with ThreadPoolExecutor(8) as ex:
+        got = list(ex.map(one, rows * 3))
+    oi, od = np.zeros(256, np.uint32), np.zeros(256, np.int32)
+    for row, g in zip(rows * 3, got):
+        k = po.oracle().orc_dct_find(h, ids, len(h), int(h[row]), 5, oi, od, 256)
+        assert g == sorted(zip(od[:k].tolist(), oi[:k].tolist()))
