@@ -288,7 +288,7 @@ def test_cfg3_10M_all_pairs_properties(cb):
     d = np.zeros(len(x), np.int64)
     for s in range(0, 64, 8):
         byte = ((x >> np.uint64(s)) & np.uint64(0xFF)).astype(np.uint8)
-        d += np.unpackbits(byte[:, None], axis=1).sum(axis=1)
+        d += np.unpackbits(byte[:, None], axis=1).sum(axis=1, dtype=np.int64)
     assert np.array_equal(d, hits["score"].astype(np.int64)) and d.max() < 5
     assert len(hits) > n + n // 50                         # the planted near-duplicates are there
 
