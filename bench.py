@@ -423,6 +423,31 @@ def main():
                                    "batched_1000_needles_per_s": 1000 / batch_s,
                                    "note": "8 MB streamed per needle = 1.2 us at HBM peak: launch/sync latency bound"}
         extras["cpu_baseline"] = cpu_reference_rate(hashes, ids, 12.0, threads)
+        # equal-work CPU leg: the reference's RadixMap_t with radix 0 = one bucket = brute force (radix.h:187-210)
+        ref = po.ref()
+        if ref is not None:
+            hh = np.ascontiguousarray(hashes[:BASE_ROWS])
+            radix = ref.ref_radix_create(0)
+            ref.ref_radix_insert(radix, np.zeros(len(hh), np.uint32), np.arange(len(hh), dtype=np.int32), hh, len(hh))
+            m = 256 * threads
+            ms = C.c_double(0)
+            ref.ref_radix_search_batch_count(radix, hh[:m], m, DHT, threads, C.byref(ms))
+            m2 = int(min(len(hh), max(m, m * 4000.0 / max(ms.value, 1e-3))))
+            ref.ref_radix_search_batch_count(radix, hh[:m2], m2, DHT, threads, C.byref(ms))
+            ref.ref_radix_destroy(radix)
+            extras["cpu_brute_force"] = {"value": m2 * float(len(hh)) / (ms.value * 1e-3), "unit": "comparisons/s",
+                                         "cores": threads, "kind": "reference",
+                                         "sample": "%d needles x %d rows through the reference RadixMap_t(radix 0), %.2f s" % (m2, len(hh), ms.value / 1e3)}
+        # OpenCV itself (the reference's own arithmetic) on one core, small sample
+        try:
+            import dcthash_cv2 as dc
+            t0 = time.time()
+            for f in frames[:20000]:
+                dc.hash_from_tile32_cv2(f)
+            extras["dct_hash"]["cpu_cv2_single_core"] = {"value": 20000 / (time.time() - t0), "unit": "frames/s",
+                                                         "sample": "20000 frames through python cv2 (cv2.dct etc., call overhead included)"}
+        except Exception as e:  # cv2 missing on the box: not fatal for the bench line
+            extras["dct_hash"]["cpu_cv2_single_core"] = {"unavailable": str(e)}
 
     if rank == 0:
         popc_peak = SM_COUNT * POPC_PER_CLK_SM * sm_max_mhz * 1e6          # POPC.b32 lanes / s
@@ -456,7 +481,7 @@ def main():
         if "cpu_baseline" in extras:
             cbl = extras["cpu_baseline"]
             line["cpu_baseline"] = {k: cbl[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        for k in ("dct_hash", "single_needle"):
+        for k in ("dct_hash", "single_needle", "cpu_brute_force"):
             if k in extras:
                 line[k] = extras[k]
         print(json.dumps(line), flush=True)
