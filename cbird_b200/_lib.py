@@ -106,6 +106,7 @@ SIGNATURES = {
     "cb_hamming_tree_remove": (C.c_int, [_vp, _vp, _i64]),
     "cb_hamming_tree_stats": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_i64)]),
     "cb_hamming_tree_search_batch_alloc": (C.c_int, [_vp, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_hamming_tree_find_votes": (C.c_int, [_vp, _vp, _i64, C.c_uint32, C.c_int, _vp, _i64, C.POINTER(_i64)]),
     "cb_hamming_tree_write": (C.c_int, [_vp, C.c_char_p]),
     "cb_hamming_tree_read": (C.c_int, [_vp, C.c_char_p]),
     "cb_orb_index_create": (_vp, []),

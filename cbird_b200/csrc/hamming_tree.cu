@@ -15,6 +15,7 @@
 // hashes hit an unsigned underflow in the reference's unrolled loop (`count - 4`, :264); this build
 // simply searches them.
 #include <algorithm>
+#include <map>
 #include <unordered_set>
 
 #include "common.h"
@@ -264,6 +265,76 @@ int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needl
   }
   if (!m.empty()) memcpy(*out, m.data(), m.size() * sizeof(cb_tree_match));
   return CB_OK;
+}
+
+// DctFeaturesIndex::find (src/dctfeaturesindex.cpp:260-358) on top of the tree: every needle hash votes
+// for the media of its 10 nearest matches; media with more votes score lower. needle hashes may be
+// omitted (n == 0) when needle_id > 0: they are then collected from the tree (findIndex, :270-274).
+// Ties at the 10-cut: the reference keeps whatever its unstable std::sort left first; here the order is
+// (distance, index, hash).
+int cb_hamming_tree_find_votes(cb_hamming_tree* t, const uint64_t* needle_hashes, int64_t n, uint32_t needle_id,
+                               int threshold, cb_match* out, int64_t cap, int64_t* n_out) {
+  if (!t || !n_out || n < 0 || (n && !needle_hashes)) {
+    set_error("cb_hamming_tree_find_votes: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  *n_out = 0;
+  HammingTree& T = t->impl;
+  std::lock_guard<std::mutex> lock(T.mu);
+  std::vector<uint64_t> own;
+  if (n == 0) {
+    if (needle_id > 0)
+      for (size_t i = 0; i < T.index.size(); ++i)
+        if (T.index[i] == needle_id) own.push_back(T.hash[i]);
+    if (own.empty()) return CB_OK;  // "needle has no hashes" (:276-279)
+    needle_hashes = own.data();
+    n = int64_t(own.size());
+  }
+  std::vector<cb_pair> pairs;
+  int rc = T.search(needle_hashes, n, threshold, pairs);
+  if (rc != CB_OK) return rc;
+  struct Cand {
+    uint32_t needle, index;
+    int32_t dist;
+    uint64_t hash;
+  };
+  std::vector<Cand> cand(pairs.size());
+  for (size_t i = 0; i < pairs.size(); ++i)
+    cand[i] = Cand{pairs[i].b, T.s_index[pairs[i].a], int32_t(pairs[i].dist), T.s_hash[pairs[i].a]};
+  std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) {
+    if (x.needle != y.needle) return x.needle < y.needle;
+    if (x.dist != y.dist) return x.dist < y.dist;
+    if (x.index != y.index) return x.index < y.index;
+    return x.hash < y.hash;
+  });
+  std::map<uint32_t, uint32_t> matches;  // QMap<uint32_t, uint32_t> :293
+  std::map<uint32_t, int> scores;
+  uint32_t maxMatches = 0;
+  for (size_t i = 0; i < cand.size();) {
+    size_t j = i;
+    while (j < cand.size() && cand[j].needle == cand[i].needle) ++j;
+    for (size_t k = i; k < j && k < i + 10; ++k) {  // "take the first 10" :299
+      const int index = int(cand[k].index);
+      if (index <= 0) continue;  // deleted :305
+      const uint32_t mediaId = uint32_t(index);
+      matches[mediaId] += 1;
+      scores[mediaId] += cand[k].dist;
+      if (needle_id != mediaId) maxMatches = std::max(matches[mediaId], maxMatches);  // :320
+    }
+    i = j;
+  }
+  int64_t w = 0;
+  for (auto& kv : matches) {  // :333-356
+    cb_match m{kv.first, 0, -1, -1, 0};
+    const float avgScore = float(scores[kv.first]) / float(kv.second);
+    if (kv.first == needle_id) m.score = -1;
+    else if (maxMatches == 1) m.score = int32_t(10 * avgScore);
+    else m.score = int32_t(maxMatches - kv.second);
+    if (w < cap) out[w] = m;
+    ++w;
+  }
+  *n_out = w;
+  return w > cap ? CB_ERR_CAPACITY : CB_OK;
 }
 
 // cache file v2 (:156-200, :472-521): "cbird hamming tree:2:<sizeof index>:8:65536\n" + pre-order nodes:

@@ -436,6 +436,21 @@ class HammingTree:
         check(self._L.cb_hamming_tree_search_batch_alloc(self._h, q.ctypes.data, len(q), int(threshold), C.byref(ptr), C.byref(n)))
         return _lib.take_array(ptr.value, n.value, _lib.TREE_MATCH_DTYPE)
 
+    def find_votes(self, needle_hashes, needle_id, threshold) -> List[Match]:
+        """DctFeaturesIndex::find over this tree (src/dctfeaturesindex.cpp:260-358)."""
+        q = _u64(needle_hashes if needle_hashes is not None else [])
+        cap = 4096
+        while True:
+            out = np.zeros(cap, _lib.MATCH_DTYPE)
+            n = C.c_int64(0)
+            rc = self._L.cb_hamming_tree_find_votes(self._h, q.ctypes.data if len(q) else None, len(q), int(needle_id),
+                                                    int(threshold), out.ctypes.data, cap, C.byref(n))
+            if rc == -4:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return _matches_from(out[: n.value])
+
     def write(self, path):
         check(self._L.cb_hamming_tree_write(self._h, str(path).encode()))
 

@@ -260,6 +260,12 @@ int cb_hamming_tree_stats(cb_hamming_tree* t, int32_t* num_nodes, int32_t* max_h
 /* search() for every needle: matches sorted by (needle, distance, index, hash); library-allocated */
 int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needles, int64_t n_needles, int threshold,
                                        cb_tree_match** out, int64_t* n_out);
+/* DctFeaturesIndex::find (src/dctfeaturesindex.cpp:260-358) over the tree: each needle hash votes for the
+ * media (index) of its 10 nearest matches; score = -1 for the needle itself, 10*avg distance when nothing
+ * has more than one vote, else maxVotes - votes; ascending mediaId. n == 0 && needle_id > 0: the needle's
+ * hashes are taken from the tree. */
+int cb_hamming_tree_find_votes(cb_hamming_tree* t, const uint64_t* needle_hashes, int64_t n, uint32_t needle_id,
+                               int threshold, cb_match* out, int64_t cap, int64_t* n_out);
 /* cache file format v2 (:156-200,:472-521), byte-compatible with the reference's reader/writer */
 int cb_hamming_tree_write(cb_hamming_tree* t, const char* path);
 int cb_hamming_tree_read(cb_hamming_tree* t, const char* path);

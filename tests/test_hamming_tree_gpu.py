@@ -89,3 +89,49 @@ def test_cache_files_are_interchangeable(cb, po, trees, tmp_path):
     bad.write_bytes(b"cbird hamming tree:1:4:8:65536\n")
     with pytest.raises(cb.CbirdError):
         cb.HammingTree().read(str(bad))
+
+
+def votes_from_reference(rt, needle_hashes, needle_id, threshold):
+    """DctFeaturesIndex::find (src/dctfeaturesindex.cpp:288-356) restated over the REFERENCE tree's search
+    results, with the product's tie rule (distance, index, hash) at the 10-cut."""
+    matches, scores, max_matches, straddle = {}, {}, 0, False
+    for q in needle_hashes:
+        ri, rh, rd = rt.search(int(q), threshold)
+        c = canon(ri, rh, rd)
+        if len(c) > 10 and c[9][0] == c[10][0]:
+            straddle = True
+        for d, index, _ in c[:10]:
+            if index <= 0:
+                continue
+            matches[int(index)] = matches.get(int(index), 0) + 1
+            scores[int(index)] = scores.get(int(index), 0) + int(d)
+            if needle_id != int(index):
+                max_matches = max(max_matches, matches[int(index)])
+    out = []
+    for mid in sorted(matches):
+        avg = np.float32(scores[mid]) / np.float32(matches[mid])
+        if mid == needle_id:
+            sc = -1
+        elif max_matches == 1:
+            sc = int(np.float32(10) * avg)
+        else:
+            sc = max_matches - matches[mid]
+        out.append((mid, sc))
+    return out, straddle
+
+
+def test_find_votes(cb, trees):
+    h, idx, gt, rt = trees
+    rng = np.random.default_rng(3)
+    for media in (1, 57, 300, 599):
+        own = h[idx == media]
+        needle = own.copy()
+        needle[::2] ^= np.uint64(1) << rng.integers(32, 64, size=len(needle[::2])).astype(np.uint64)
+        for needle_id, hashes in ((0, needle), (media, needle), (media, None)):
+            got = [(m.mediaId, m.score) for m in gt.find_votes(hashes, needle_id, 7)]
+            want, _ = votes_from_reference(rt, own if hashes is None else hashes, needle_id, 7)
+            assert got == want
+            assert media in [g[0] for g in got]
+            if needle_id == media:
+                assert (media, -1) in got
+    assert gt.find_votes(None, 0, 7) == [] and gt.find_votes(None, 123456, 7) == []
