@@ -120,6 +120,8 @@ SIGNATURES = {
     "cb_orb_index_slice": (_vp, [_vp, _vp, _i64]),
     "cb_orb_index_descriptors": (C.c_int, [_vp, C.c_uint32, _vp, _i64, C.POINTER(_i64)]),
     "cb_orb_index_find": (C.c_int, [_vp, _vp, _i64, C.c_uint32, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_orb_index_save_cache": (C.c_int, [_vp, C.c_char_p]),
+    "cb_orb_index_load_cache": (C.c_int, [_vp, C.c_char_p]),
     "cb_orb_index_knn_alloc": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
 }
 

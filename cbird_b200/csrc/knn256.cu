@@ -487,4 +487,118 @@ int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uin
   return k > cap ? CB_ERR_CAPACITY : CB_OK;
 }
 
+
+// ---- cache files of CvFeaturesIndex::saveIndex / loadIndex (src/cvfeaturesindex.cpp:387-419) -----------
+//   cvfeatures.mat           MatrixHeader{u32 id=0; i32 rows, cols=32, type=CV_8U(0), stride=32} + rows x 32 B
+//                            (src/cvutil.cpp:42-45,60-70,151-163)
+//   cvfeatures_idmap.map     raw (u32 mediaId, u32 firstRow) pairs in key order, incl. (UINT32_MAX, rows)
+//   cvfeatures_indexmap.map  raw (u32 firstRow, u32 mediaId | 0 = removed) pairs, incl. (rows, 0)   (src/ioutil.h:204-232)
+//   cvfeatures.touch         marker written last
+namespace {
+struct MatrixHeader {
+  uint32_t id;
+  int32_t rows, cols, type, stride;
+};
+bool write_all(const std::string& path, const void* p, size_t n, const void* p2 = nullptr, size_t n2 = 0) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  bool ok = (n == 0 || fwrite(p, 1, n, f) == n) && (n2 == 0 || fwrite(p2, 1, n2, f) == n2);
+  ok = (fclose(f) == 0) && ok;
+  return ok;
+}
+bool read_all(const std::string& path, std::vector<uint8_t>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(sz > 0 ? size_t(sz) : 0);
+  const bool ok = out.empty() || fread(out.data(), 1, out.size(), f) == out.size();
+  fclose(f);
+  return ok;
+}
+}  // namespace
+
+int cb_orb_index_save_cache(cb_orb_index* ix, const char* cache_dir) {
+  if (!ix || !cache_dir) {
+    set_error("cb_orb_index_save_cache: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  const std::string dir(cache_dir);
+  const MatrixHeader h{0u, int32_t(I.rows()), 32, 0, 32};
+  std::vector<uint32_t> idmap, indexmap;
+  for (auto& kv : I.id_map) {
+    idmap.push_back(kv.first);
+    idmap.push_back(kv.second.first);
+  }
+  idmap.push_back(0xFFFFFFFFu);  // trailing values (:244-245)
+  idmap.push_back(I.rows());
+  for (size_t b = 0; b < I.first_row.size(); ++b) {
+    indexmap.push_back(I.first_row[b]);
+    indexmap.push_back(I.media[b]);
+  }
+  indexmap.push_back(I.rows());
+  indexmap.push_back(0u);
+  static const char mark[] = "this file indicates index was saved successfully";
+  if (!write_all(dir + "/cvfeatures.mat", &h, sizeof(h), I.desc.data(), I.desc.size()) ||
+      !write_all(dir + "/cvfeatures_idmap.map", idmap.data(), idmap.size() * 4) ||
+      !write_all(dir + "/cvfeatures_indexmap.map", indexmap.data(), indexmap.size() * 4) ||
+      !write_all(dir + "/cvfeatures.touch", mark, sizeof(mark) - 1)) {
+    set_error("cb_orb_index_save_cache: cannot write into %s", cache_dir);
+    return CB_ERR_INVALID;
+  }
+  return CB_OK;
+}
+
+int cb_orb_index_load_cache(cb_orb_index* ix, const char* cache_dir) {
+  if (!ix || !cache_dir) {
+    set_error("cb_orb_index_load_cache: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  OrbIndex& I = ix->impl;
+  std::lock_guard<std::mutex> lock(I.mu);
+  const std::string dir(cache_dir);
+  std::vector<uint8_t> mat, idm, ixm;
+  if (!read_all(dir + "/cvfeatures.mat", mat) || !read_all(dir + "/cvfeatures_idmap.map", idm) ||
+      !read_all(dir + "/cvfeatures_indexmap.map", ixm)) {
+    set_error("cb_orb_index_load_cache: cache files missing in %s", cache_dir);
+    return CB_ERR_INVALID;
+  }
+  MatrixHeader h;
+  if (mat.size() < sizeof(h)) {
+    set_error("cvfeatures.mat: truncated header");
+    return CB_ERR_INVALID;
+  }
+  memcpy(&h, mat.data(), sizeof(h));
+  if (h.cols != 32 || h.type != 0 || h.stride != 32 || h.rows < 0 || mat.size() != sizeof(h) + size_t(h.rows) * 32 ||
+      idm.size() % 8 || ixm.size() % 8) {
+    set_error("cvfeatures cache: unexpected geometry (rows=%d cols=%d type=%d stride=%d)", h.rows, h.cols, h.type, h.stride);
+    return CB_ERR_INVALID;
+  }
+  I.desc.assign(mat.begin() + sizeof(h), mat.end());
+  I.first_row.clear();
+  I.media.clear();
+  I.id_map.clear();
+  I.d_rows = 0;
+  const uint32_t* im = reinterpret_cast<const uint32_t*>(ixm.data());
+  for (size_t k = 0; k + 1 < ixm.size() / 4; k += 2) {
+    if (im[k] >= uint32_t(h.rows)) continue;  // the (rows, 0) trailer
+    I.first_row.push_back(im[k]);
+    I.media.push_back(im[k + 1]);
+  }
+  const uint32_t* dm = reinterpret_cast<const uint32_t*>(idm.data());
+  for (size_t k = 0; k + 1 < idm.size() / 4; k += 2) {
+    if (dm[k] == 0xFFFFFFFFu) continue;
+    const uint32_t first = dm[k + 1];
+    auto b = std::lower_bound(I.first_row.begin(), I.first_row.end(), first);
+    if (b == I.first_row.end() || *b != first) continue;
+    const uint32_t next = (b + 1 == I.first_row.end()) ? uint32_t(h.rows) : *(b + 1);
+    I.id_map[dm[k]] = {first, next - first};
+  }
+  I.loaded = true;
+  return I.sync_to_device();
+}
+
 }  // extern "C"

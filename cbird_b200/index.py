@@ -341,8 +341,14 @@ class CvFeaturesIndex:
         i, o, f = _pack_descriptors(ids, descriptors)
         check(self._L.cb_orb_index_load(self._h, i.ctypes.data, o.ctypes.data, f.ctypes.data, len(i)))
 
-    def save(self):
-        """cache files are out of scope; nothing to do."""
+    def save(self, cache_dir=None):
+        """save(): the reference's cache files (cvfeatures.mat / *_idmap.map / *_indexmap.map / .touch, :406-419)."""
+        if cache_dir is not None:
+            check(self._L.cb_orb_index_save_cache(self._h, str(cache_dir).encode()))
+
+    def loadCache(self, cache_dir):
+        """loadIndex(): read the reference's cache files (:387-404)."""
+        check(self._L.cb_orb_index_load_cache(self._h, str(cache_dir).encode()))
 
     def add(self, media: List[Media]):
         i, o, f = _pack_descriptors([m.id for m in media], [m.descriptors for m in media])

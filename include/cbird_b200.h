@@ -295,6 +295,10 @@ int cb_orb_index_descriptors(const cb_orb_index* ix, uint32_t media_id, uint8_t*
  * One match per media: score = median(distances) * 1000 / count, ascending mediaId.   :438-604 */
 int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uint32_t needle_id, const cb_params* p,
                       cb_match* out, int64_t cap, int64_t* n_out);
+/* saveIndex()/loadIndex() cache files in `cache_dir` (cvfeatures.mat, cvfeatures_idmap.map,
+ * cvfeatures_indexmap.map, cvfeatures.touch), byte-compatible with the reference    :387-419 */
+int cb_orb_index_save_cache(cb_orb_index* ix, const char* cache_dir);
+int cb_orb_index_load_cache(cb_orb_index* ix, const char* cache_dir);
 /* the exact k nearest rows with distance < threshold of every needle row: cb_pair{a = row, b = needle
  * row, dist, pad_ = media id of the row (0 = removed)}, sorted by (needle row, dist, row); k<=0 = all.
  * Building block for sharded search: per-shard lists are merged by (dist, row) and cut at k. */

@@ -157,3 +157,38 @@ def test_sharded_by_media_equals_single(cb, orb):
         assert np.array_equal(merged, single)
         want = rows_of(gx.find(cb.Media(descriptors=needle), cb.SearchParams(cvThresh=25)))
         assert parallel.score_orb_matches(merged) == [(w[0], w[1]) for w in want]
+
+
+def test_cache_files_round_trip_and_layout(cb, po, tmp_path):
+    # saveIndex/loadIndex (src/cvfeaturesindex.cpp:387-419): byte layout restated here independently
+    import struct
+
+    ids, descs = synth.orb_descriptors(40, 25, seed=13)
+    gx = cb.CvFeaturesIndex()
+    gx.load(ids, descs)
+    gx.remove([int(ids[7])])
+    gx.save(tmp_path)
+    rows = 40 * 25
+    mat = (tmp_path / "cvfeatures.mat").read_bytes()
+    assert mat[:20] == struct.pack("=Iiiii", 0, rows, 32, 0, 32) and mat[20:] == np.concatenate(descs).tobytes()
+    idmap = np.frombuffer((tmp_path / "cvfeatures_idmap.map").read_bytes(), np.uint32).reshape(-1, 2)
+    assert idmap[:-1, 0].tolist() == ids.tolist() and idmap[:-1, 1].tolist() == list(range(0, rows, 25))
+    assert idmap[-1].tolist() == [0xFFFFFFFF, rows]
+    ixmap = np.frombuffer((tmp_path / "cvfeatures_indexmap.map").read_bytes(), np.uint32).reshape(-1, 2)
+    want_media = ids.copy()
+    want_media[7] = 0
+    assert ixmap[:-1, 0].tolist() == list(range(0, rows, 25)) and ixmap[:-1, 1].tolist() == want_media.tolist()
+    assert ixmap[-1].tolist() == [rows, 0]
+    assert (tmp_path / "cvfeatures.touch").read_text() == "this file indicates index was saved successfully"
+    g2 = cb.CvFeaturesIndex()
+    g2.loadCache(tmp_path)
+    assert g2.count() == rows and g2.isLoaded()
+    sp = cb.SearchParams(cvThresh=25)
+    for k in (0, 7, 39):
+        a = rows_of(gx.find(cb.Media(descriptors=descs[k]), sp))
+        assert a == rows_of(g2.find(cb.Media(descriptors=descs[k]), sp))
+        assert (int(ids[k]) in [x[0] for x in a]) == (k != 7)
+    m = cb.Media(id=int(ids[7]))
+    assert g2.findIndexData(m) and np.array_equal(m.descriptors, descs[7])  # removed media keep their rows
+    with pytest.raises(cb.CbirdError):
+        cb.CvFeaturesIndex().loadCache(tmp_path / "nowhere")
