@@ -30,7 +30,7 @@ class cb_params(C.Structure):
 
 class cb_stats(C.Structure):
     _fields_ = [("comparisons", C.c_uint64), ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("frames_hashed", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("frames_hashed", C.c_uint64)]
 
 
 HIT_DTYPE = np.dtype([("needle", np.uint32), ("mediaId", np.uint32), ("score", np.int32)])

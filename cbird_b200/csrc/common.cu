@@ -105,7 +105,6 @@ int cb_stats_get(cb_stats* out) {
   out->hits = c.hits.load();
   out->kernel_launches = c.launches.load();
   out->frames_hashed = c.frames.load();
-  out->kernel_ms = double(c.kernel_us.load()) / 1000.0;
   return CB_OK;
 }
 
@@ -115,7 +114,6 @@ void cb_stats_reset(void) {
   c.hits = 0;
   c.launches = 0;
   c.frames = 0;
-  c.kernel_us = 0;
 }
 
 void cb_free(void* p) { free(p); }

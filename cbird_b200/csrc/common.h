@@ -21,7 +21,6 @@ int ensure_device();           // CB_OK or CB_ERR_NO_DEVICE; also cudaSetDevice(
 
 struct Counters {
   std::atomic<uint64_t> comparisons{0}, hits{0}, launches{0}, frames{0};
-  std::atomic<uint64_t> kernel_us{0};
 };
 Counters& counters();
 

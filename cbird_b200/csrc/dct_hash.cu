@@ -367,6 +367,47 @@ struct TapIter {
   __device__ float tail_alpha() const { return float(fmin(fmin(fsx2 - sx2, 1.), cell) / cell); }
 };
 
+// one pixel (dx,dy) of cv::resize(32x32, INTER_AREA) applied to a cw x ch image read through px(y,x):
+// (s+2)>>2 for 2x2, rint(sum * f32(1/area)) for other integer factors, otherwise OpenCV's f32 coverage
+// taps accumulated in OpenCV's order (no contraction), round half to even. Shared by the global-memory
+// and the shared-memory (fused) paths so both are the same arithmetic by construction.
+template <typename Px>
+__device__ __forceinline__ uint8_t area_pixel(Px px, int cw, int ch, int dx, int dy) {
+  const double sx = cw / 32.0, sy = ch / 32.0;
+  const int ix = int(rint(sx)), iy = int(rint(sy));
+  const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
+  if (cw == 32 && ch == 32) return px(dy, dx);
+  if (fast && ix == 2 && iy == 2)
+    return uint8_t((int(px(2 * dy, 2 * dx)) + px(2 * dy, 2 * dx + 1) + px(2 * dy + 1, 2 * dx) + px(2 * dy + 1, 2 * dx + 1) + 2) >> 2);
+  if (fast) {
+    int s = 0;
+    for (int j = 0; j < iy; ++j)
+      for (int i = 0; i < ix; ++i) s += px(dy * iy + j, dx * ix + i);
+    return uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
+  }
+  const TapIter tx(dx, cw, sx), ty(dy, ch, sy);
+  auto row_sum = [&](int syi) {
+    float buf = 0.f;
+    if (tx.head()) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx1 - 1)), tx.head_alpha()));
+    const float ba = tx.body_alpha();
+    for (int k = tx.sx1; k < tx.sx2; ++k) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, k)), ba));
+    if (tx.tail()) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx2)), tx.tail_alpha()));
+    return buf;
+  };
+  float sum = 0.f;
+  bool first = true;
+  auto acc = [&](int syi, float beta) {
+    const float t = __fmul_rn(beta, row_sum(syi));
+    sum = first ? t : __fadd_rn(sum, t);
+    first = false;
+  };
+  if (ty.head()) acc(ty.sx1 - 1, ty.head_alpha());
+  const float bb = ty.body_alpha();
+  for (int k = ty.sx1; k < ty.sx2; ++k) acc(k, bb);
+  if (ty.tail()) acc(ty.sx2, ty.tail_alpha());
+  return uint8_t(min(255, max(0, __float2int_rn(sum))));
+}
+
 // cv::resize(32x32, INTER_AREA) of every frame's (already blurred) crop; crops smaller than 32 px on a
 // side are flagged (OpenCV would up-scale through a different path that is not restated)
 __global__ void __launch_bounds__(1024)
@@ -379,51 +420,231 @@ __global__ void __launch_bounds__(1024)
   uint8_t r = 0;
   const bool unsupported = cw < 32 || ch < 32;
   if (threadIdx.x == 0) bad[blockIdx.x] = unsupported ? 1 : 0;
-  if (!unsupported) {
-    const double sx = cw / 32.0, sy = ch / 32.0;
-    const int ix = int(rint(sx)), iy = int(rint(sy));
-    const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
-    if (cw == 32 && ch == 32) {
-      r = f[(long long)dy * w + dx];
-    } else if (fast && ix == 2 && iy == 2) {
-      const uint8_t* a = f + (long long)(2 * dy) * w + 2 * dx;
-      r = uint8_t((int(a[0]) + a[1] + a[w] + a[w + 1] + 2) >> 2);
-    } else if (fast) {
-      int s = 0;
-      for (int j = 0; j < iy; ++j)
-        for (int i = 0; i < ix; ++i) s += f[(long long)(dy * iy + j) * w + dx * ix + i];
-      r = uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
-    } else {
-      const TapIter tx(dx, cw, sx), ty(dy, ch, sy);
-      auto row_sum = [&](int syi) {
-        const uint8_t* row = f + (long long)syi * w;
-        float buf = 0.f;
-        if (tx.head()) buf = __fadd_rn(buf, __fmul_rn(float(row[tx.sx1 - 1]), tx.head_alpha()));
-        const float ba = tx.body_alpha();
-        for (int k = tx.sx1; k < tx.sx2; ++k) buf = __fadd_rn(buf, __fmul_rn(float(row[k]), ba));
-        if (tx.tail()) buf = __fadd_rn(buf, __fmul_rn(float(row[tx.sx2]), tx.tail_alpha()));
-        return buf;
-      };
-      float sum = 0.f;
-      bool first = true;
-      auto acc = [&](int syi, float beta) {
-        const float t = __fmul_rn(beta, row_sum(syi));
-        sum = first ? t : __fadd_rn(sum, t);
-        first = false;
-      };
-      if (ty.head()) acc(ty.sx1 - 1, ty.head_alpha());
-      const float bb = ty.body_alpha();
-      for (int k = ty.sx1; k < ty.sx2; ++k) acc(k, bb);
-      if (ty.tail()) acc(ty.sx2, ty.tail_alpha());
-      r = uint8_t(min(255, max(0, __float2int_rn(sum))));
-    }
-  }
+  if (!unsupported) r = area_pixel([&](int y, int x) { return f[(long long)y * w + x]; }, cw, ch, dx, dy);
   dst[(long long)blockIdx.x * 1024 + threadIdx.x] = r;
 }
 
 __global__ void zero_bad_hashes_kernel(const uint8_t* __restrict__ bad, long long n, uint64_t* out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n && bad[i]) out[i] = 0;  // 0 == "no hash" (src/index.cpp:46-49)
+}
+
+// ---- fused, shared-memory staged path for frames that fit one CTA's shared memory (video frames) ----
+// one CTA = one frame: frame -> smem, [autocrop], separable integer box blur in smem (u16 row sums),
+// INTER_AREA to a 32x32 tile in smem, DCT hash by warp 0 — HBM traffic is the frame itself + 8 B.
+// Arithmetic is the same code (reflect101, blur rounding, area_pixel, dct9_of_32) as the unfused kernels.
+
+// hash of the CTA's 32x32 u8 tile (shared memory) — stages 1-3 of dct_hash32_kernel for one frame.
+// All threads must call it; returns the hash in every lane of warp 0.
+__device__ uint64_t hash_tile_cta(const uint8_t* tile, float* sT, float* sF) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + 32 * lane);
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = row[i];
+    float px[32], t[9];
+#pragma unroll
+    for (int x = 0; x < 32; ++x) px[x] = byte_of(w, x);
+    dct9_of_32(px, t);
+#pragma unroll
+    for (int u = 0; u < 9; ++u) sT[lane * 9 + u] = t[u];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const int u = threadIdx.x;
+    float cv[32], f[9];
+#pragma unroll
+    for (int y = 0; y < 32; ++y) cv[y] = sT[9 * y + u];
+    dct9_of_32(cv, f);
+#pragma unroll
+    for (int v = 0; v < 9; ++v) sF[9 * v + u] = f[v];
+  }
+  __syncthreads();
+  uint64_t hash = 0;
+  if (warp == 0) {
+    const float c0 = sF[c_zigzag[6 + lane]], c1 = sF[c_zigzag[38 + lane]];
+    double v = double(c0) + double(c1);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    const float thresh = __fmul_rn(float(v), 0.015625f);
+    const uint32_t lo = __ballot_sync(0xffffffffu, c0 > thresh) & ~1u;
+    const uint32_t hi = __ballot_sync(0xffffffffu, c1 > thresh);
+    hash = (uint64_t(hi) << 32) | lo;
+    if (hash == 0) hash = 1;
+  }
+  return hash;
+}
+
+__device__ __forceinline__ int blur_round(int s, int k) {  // nearest integer of s / k^2 (k^2 odd: no ties)
+  switch (k) {
+    case 3: return (2 * s + 9) / 18;
+    case 5: return (2 * s + 25) / 50;
+    default: return (2 * s + 49) / 98;
+  }
+}
+
+// mode 0: whole frame; 1: rectangle given in rects; 2: autocrop(range) first, rectangle written to rects
+__global__ void __launch_bounds__(256)
+    frame_hash_fused_kernel(const uint8_t* __restrict__ frames, long long row_stride, long long frame_stride, int w,
+                            int h, int mode, int range, int32_t* __restrict__ rects, uint64_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sT = reinterpret_cast<float*>(smem_raw);              // 288 floats
+  float* sF = sT + 288;                                        // 81 floats (+3 pad)
+  int* s_rect = reinterpret_cast<int*>(sF + 84);               // 4 ints
+  uint8_t* tile = reinterpret_cast<uint8_t*>(s_rect + 4);      // 1024 B
+  int* ext = reinterpret_cast<int*>(tile + 1024);              // rowL[h] rowR[h] colT[w] colB[w]
+  uint16_t* hs = reinterpret_cast<uint16_t*>(ext + 2 * h + 2 * w);  // h * w u16 row sums
+  uint8_t* img = reinterpret_cast<uint8_t*>(hs + (size_t(h) * w + 1) / 2 * 2);  // h * w u8 (later: blurred crop)
+
+  const uint8_t* src = frames + (long long)blockIdx.x * frame_stride;
+  const int tid = threadIdx.x;
+  // 1. frame -> shared memory
+  if ((w & 3) == 0 && (row_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+    const int wq = w >> 2;
+    uint32_t* img32 = reinterpret_cast<uint32_t*>(img);
+    for (int i = tid; i < h * wq; i += 256) {
+      const int y = i / wq, xq = i - y * wq;
+      img32[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (long long)y * row_stride) + xq);
+    }
+  } else {
+    for (int i = tid; i < h * w; i += 256) {
+      const int y = i / w, x = i - y * w;
+      img[i] = src[(long long)y * row_stride + x];
+    }
+  }
+  __syncthreads();
+
+  // 2. crop rectangle
+  if (mode == 2) {  // autocrop, the algorithm of autocrop_kernel on the staged frame
+    int* rowL = ext;
+    int* rowR = rowL + h;
+    int* colT = rowR + h;
+    int* colB = colT + w;
+    const int color = img[0];
+    for (int y = tid; y < h; y += 256) {
+      const uint8_t* px = img + y * w;
+      int left = 0, right = w - 1;
+      while (left < w && abs(int(px[left]) - color) <= range) ++left;
+      while (right >= 0 && abs(int(px[right]) - color) <= range) --right;
+      rowL[y] = left;
+      rowR[y] = right + 1;
+    }
+    for (int x = tid; x < w; x += 256) {
+      int top = 0, bottom = h - 1;
+      while (top < h && abs(int(img[top * w + x]) - color) <= range) ++top;
+      while (bottom >= 0 && abs(int(img[bottom * w + x]) - color) <= range) --bottom;
+      colT[x] = top;
+      colB[x] = bottom + 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int minW = int(float(w) * 0.66f), minH = int(float(h) * 0.66f);
+      const int maxHd = int(float(w) * 0.05f), maxVd = int(float(h) * 0.05f);
+      int top, bottom, left, right;
+      for (top = h / 2; top >= 0; --top)
+        if (rowL[top] > 0 && rowR[top] < w && rowL[top] + w - rowR[top] > minW) break;
+      ++top;
+      for (bottom = h / 2 + 1; bottom < h; ++bottom)
+        if (rowL[bottom] + w - rowR[bottom] > minW) break;
+      for (left = w / 2; left >= 0; --left)
+        if (colT[left] > 0 && colB[left] < h && colT[left] + h - colB[left] > minH) break;
+      ++left;
+      for (right = w / 2 + 1; right < w; ++right)
+        if (colT[right] > 0 && colB[right] < h && colT[right] + h - colB[right] > minH) break;
+      const int bmargin = h - bottom;
+      if (abs(top - bmargin) > maxVd) {
+        if (top > bmargin) top = bmargin;
+        else bottom = h - top;
+      }
+      const int rmargin = w - right;
+      if (abs(left - rmargin) > maxHd) {
+        if (left > rmargin) left = rmargin;
+        else right = w - left;
+      }
+      bool crop = false;
+      if ((left != 0 && right != w) || (top != 0 && bottom != h))
+        if (left < right && top < bottom && float(right - left) / float(w) > 0.65f && float(bottom - top) / float(h) > 0.65f)
+          crop = true;
+      s_rect[0] = crop ? left : 0;
+      s_rect[1] = crop ? top : 0;
+      s_rect[2] = crop ? right : w;
+      s_rect[3] = crop ? bottom : h;
+      int32_t* r = rects + 4 * (long long)blockIdx.x;
+      r[0] = s_rect[0]; r[1] = s_rect[1]; r[2] = s_rect[2]; r[3] = s_rect[3];
+    }
+  } else if (tid == 0) {
+    if (mode == 1) {
+      const int32_t* r = rects + 4 * (long long)blockIdx.x;
+      s_rect[0] = r[0]; s_rect[1] = r[1]; s_rect[2] = r[2]; s_rect[3] = r[3];
+    } else {
+      s_rect[0] = 0; s_rect[1] = 0; s_rect[2] = w; s_rect[3] = h;
+    }
+  }
+  __syncthreads();
+  const int rl = s_rect[0], rt = s_rect[1], cw = s_rect[2] - s_rect[0], ch = s_rect[3] - s_rect[1];
+  if (cw < 32 || ch < 32) {  // INTER_AREA up-scaling is not restated: "no hash"
+    if (tid == 0) out[blockIdx.x] = 0;
+    return;
+  }
+
+  // 3. cv::blur on the view: separable integer box sums; rows of the PARENT are used beyond the view
+  const int k = blur_k_for((long long)cw * ch);
+  const uint8_t* bl = img + rt * w + rl;  // blurred (or original) view
+  int bl_stride = w;
+  if (k) {
+    const int r = k >> 1;
+    for (int i = tid; i < h * cw; i += 256) {  // horizontal sums for every parent row, view columns
+      const int y = i / cw, x = rl + (i - y * cw);
+      const uint8_t* row = img + y * w;
+      int s = 0;
+      for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
+      hs[i] = uint16_t(s);
+    }
+    __syncthreads();
+    for (int i = tid; i < ch * cw; i += 256) {  // vertical sums -> blurred view (dense, stride cw), reusing img
+      const int yy = i / cw, xi = i - yy * cw, y = rt + yy;
+      int s = 0;
+      for (int dy = -r; dy <= r; ++dy) s += hs[reflect101(y + dy, h) * cw + xi];
+      img[i] = uint8_t(blur_round(s, k));
+    }
+    __syncthreads();
+    bl = img;
+    bl_stride = cw;
+  }
+
+  // 4. INTER_AREA -> 32x32 tile
+  for (int i = tid; i < 1024; i += 256)
+    tile[i] = area_pixel([&](int y, int x) { return bl[y * bl_stride + x]; }, cw, ch, i & 31, i >> 5);
+  __syncthreads();
+
+  // 5. hash
+  const uint64_t hsh = hash_tile_cta(tile, sT, sF);
+  if (tid == 0) out[blockIdx.x] = hsh;
+}
+
+size_t fused_smem_bytes(int w, int h) {
+  return (288 + 84) * 4 + 16 + 1024 + size_t(2 * h + 2 * w) * 4 + ((size_t(h) * w + 1) / 2 * 2) * 2 + size_t(h) * w + 16;
+}
+bool fused_ok(int w, int h) { return fused_smem_bytes(w, h) <= 200 * 1024; }
+
+int launch_fused(const uint8_t* d_frames, long long n, int w, int h, long long row_stride, long long frame_stride, int mode,
+                 int range, int32_t* d_rects, uint64_t* d_out, cudaStream_t stream) {
+  if (n <= 0) return CB_OK;
+  int rc = upload_tables();
+  if (rc != CB_OK) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(frame_hash_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(frame_hash_fused_kernel)", __FILE__, __LINE__);
+  frame_hash_fused_kernel<<<unsigned(n), 256, fused_smem_bytes(w, h), stream>>>(d_frames, row_stride, frame_stride, w, h,
+                                                                               mode, range, d_rects, d_out);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().frames += uint64_t(n);
+  return CB_OK;
 }
 
 // OpenCV computeResizeAreaTab (third-party imgproc, restated): coverage weights in f32
@@ -463,6 +684,9 @@ int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long 
   if (rc != CB_OK) return rc;
   const uint8_t* tiles = d_frames;
   long long t_row = row_stride, t_frame = frame_stride;
+  static const bool no_fused = getenv("CB_HASH_NO_FUSED") != nullptr;  // tuning / parity aid
+  if (!(w == 32 && h == 32) && fused_ok(w, h) && !no_fused)
+    return launch_fused(d_frames, n, w, h, row_stride, frame_stride, 0, 0, nullptr, d_out, stream);
   if (!(w == 32 && h == 32)) {
     const long long area = (long long)w * h;
     int k = 7;  // src/cvutil.cpp:446-455
@@ -543,6 +767,9 @@ int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long l
   if (n <= 0) return CB_OK;
   int rc = upload_tables();
   if (rc != CB_OK) return rc;
+  static const bool no_fused = getenv("CB_HASH_NO_FUSED") != nullptr;
+  if (fused_ok(w, h) && !no_fused)
+    return launch_fused(d_frames, n, w, h, row_stride, frame_stride, 1, 0, const_cast<int32_t*>(d_rects), d_out, stream);
   if ((rc = ws->blurred.reserve(size_t(n) * w * h)) != CB_OK || (rc = ws->tiles.reserve(size_t(n) * 1024)) != CB_OK ||
       (rc = ws->bad.reserve(size_t(n))) != CB_OK)
     return rc;
@@ -827,9 +1054,13 @@ int cb_make_video_index_alloc(const uint8_t* frames, int64_t n, int w, int h, in
                                 int rc2 = ctx.ws.rects.reserve(size_t(m) * 4);
                                 if (rc2 == CB_OK) rc2 = ctx.d_out.reserve(size_t(m));
                                 if (rc2 != CB_OK) return rc2;
-                                rc2 = autocrop_device(d, m, w, h, row_stride, per_frame, 20, ctx.ws.rects.p, ctx.stream);  // :963,:994
-                                if (rc2 != CB_OK) return rc2;
-                                rc2 = hash_rects_device(d, m, w, h, row_stride, per_frame, ctx.ws.rects.p, ctx.d_out.p, &ctx.ws, ctx.stream);
+                                if (fused_ok(w, h) && !getenv("CB_HASH_NO_FUSED")) {  // autocrop(20) + hash in one kernel
+                                  rc2 = launch_fused(d, m, w, h, row_stride, per_frame, 2, 20, ctx.ws.rects.p, ctx.d_out.p, ctx.stream);
+                                } else {
+                                  rc2 = autocrop_device(d, m, w, h, row_stride, per_frame, 20, ctx.ws.rects.p, ctx.stream);  // :963,:994
+                                  if (rc2 != CB_OK) return rc2;
+                                  rc2 = hash_rects_device(d, m, w, h, row_stride, per_frame, ctx.ws.rects.p, ctx.d_out.p, &ctx.ws, ctx.stream);
+                                }
                                 if (rc2 != CB_OK) return rc2;
                                 CB_CUDA(cudaMemcpyAsync(hashes.data() + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
                                 return int(CB_OK);

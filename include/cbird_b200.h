@@ -92,7 +92,6 @@ typedef struct cb_stats {
   uint64_t hits;            /* pairs under threshold */
   uint64_t kernel_launches; /* launches of this library's own kernels */
   uint64_t frames_hashed;
-  double kernel_ms;         /* device time of the last timed call (CUDA events) */
 } cb_stats;
 
 /* ---- library -------------------------------------------------------------------------------- */

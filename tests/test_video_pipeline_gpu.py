@@ -9,7 +9,8 @@ from cbird_b200 import synth
 pytestmark = pytest.mark.gpu
 
 CASES = [((0, 0), 128, 128), ((14, 0), 128, 128), ((0, 12), 128, 128), ((10, 9), 128, 128), ((16, 0), 128, 96),
-         ((30, 0), 128, 128), ((5, 20), 96, 128), ((8, 0), 64, 64), ((3, 0), 200, 150)]
+         ((30, 0), 128, 128), ((5, 20), 96, 128), ((8, 0), 64, 64), ((3, 0), 200, 150),
+         ((20, 0), 320, 240), ((0, 25), 400, 300)]  # the last two exceed one CTA's shared memory: unfused kernels
 
 
 @pytest.mark.parametrize("lb,w,h", CASES)
