@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kHashThreads, kMinBlocks)
 
 // ---- general geometry: blur + INTER_AREA -------------------------------------------------------
 __device__ __forceinline__ int reflect101(int p, int n) {
+  if (p >= 0 && p < n) return p;  // interior: the common case
   if (n == 1) return 0;
   while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
   return p;
@@ -346,52 +347,42 @@ __global__ void box_blur_rect_kernel(const uint8_t* __restrict__ src, long long 
   dst[((long long)blockIdx.z * h + y) * w + x] = out;
 }
 
-// coverage taps of destination cell d along one axis, generated on the fly in f64 exactly like
-// area_taps() below; returns the number of taps (<= ceil(scale)+2), tap i = (si[i], alpha[i])
-struct TapIter {
-  int sx1, sx2, ssize;
-  double fsx1, fsx2, cell;
-  __device__ TapIter(int d, int ssize_, double scale) : ssize(ssize_) {
-    fsx1 = d * scale;
-    fsx2 = fsx1 + scale;
-    cell = fmin(scale, ssize - fsx1);
-    sx1 = int(ceil(fsx1));
-    sx2 = int(floor(fsx2));
-    sx2 = min(sx2, ssize - 1);
-    sx1 = min(sx1, sx2);
-  }
-  __device__ bool head() const { return sx1 - fsx1 > 1e-3; }
-  __device__ float head_alpha() const { return float((sx1 - fsx1) / cell); }
-  __device__ float body_alpha() const { return float(1.0 / cell); }
-  __device__ bool tail() const { return fsx2 - sx2 > 1e-3; }
-  __device__ float tail_alpha() const { return float(fmin(fmin(fsx2 - sx2, 1.), cell) / cell); }
+// coverage taps of destination cell d along one axis, generated on the device in f64 exactly like
+// area_taps() below
+struct AxisTaps {  // coverage of one destination cell along one axis (OpenCV computeResizeAreaTab)
+  int sx1, sx2;          // full-weight source cells [sx1, sx2)
+  float head_alpha, body_alpha, tail_alpha;
+  int has_head, has_tail;  // partial cells sx1-1 and sx2
 };
+__device__ __forceinline__ AxisTaps make_taps(int d, int ssize, double scale) {
+  AxisTaps t;
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, ssize - fsx1);
+  int sx1 = int(ceil(fsx1)), sx2 = int(floor(fsx2));
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  t.sx1 = sx1;
+  t.sx2 = sx2;
+  t.has_head = sx1 - fsx1 > 1e-3;
+  t.head_alpha = float((sx1 - fsx1) / cell);
+  t.body_alpha = float(1.0 / cell);
+  t.has_tail = fsx2 - sx2 > 1e-3;
+  t.tail_alpha = float(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
+  return t;
+}
 
 // one pixel (dx,dy) of cv::resize(32x32, INTER_AREA) applied to a cw x ch image read through px(y,x):
 // (s+2)>>2 for 2x2, rint(sum * f32(1/area)) for other integer factors, otherwise OpenCV's f32 coverage
 // taps accumulated in OpenCV's order (no contraction), round half to even. Shared by the global-memory
 // and the shared-memory (fused) paths so both are the same arithmetic by construction.
 template <typename Px>
-__device__ __forceinline__ uint8_t area_pixel(Px px, int cw, int ch, int dx, int dy) {
-  const double sx = cw / 32.0, sy = ch / 32.0;
-  const int ix = int(rint(sx)), iy = int(rint(sy));
-  const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
-  if (cw == 32 && ch == 32) return px(dy, dx);
-  if (fast && ix == 2 && iy == 2)
-    return uint8_t((int(px(2 * dy, 2 * dx)) + px(2 * dy, 2 * dx + 1) + px(2 * dy + 1, 2 * dx) + px(2 * dy + 1, 2 * dx + 1) + 2) >> 2);
-  if (fast) {
-    int s = 0;
-    for (int j = 0; j < iy; ++j)
-      for (int i = 0; i < ix; ++i) s += px(dy * iy + j, dx * ix + i);
-    return uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
-  }
-  const TapIter tx(dx, cw, sx), ty(dy, ch, sy);
+__device__ __forceinline__ uint8_t area_pixel_taps(Px px, const AxisTaps& tx, const AxisTaps& ty) {
   auto row_sum = [&](int syi) {
     float buf = 0.f;
-    if (tx.head()) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx1 - 1)), tx.head_alpha()));
-    const float ba = tx.body_alpha();
+    if (tx.has_head) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx1 - 1)), tx.head_alpha));
+    const float ba = tx.body_alpha;
     for (int k = tx.sx1; k < tx.sx2; ++k) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, k)), ba));
-    if (tx.tail()) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx2)), tx.tail_alpha()));
+    if (tx.has_tail) buf = __fadd_rn(buf, __fmul_rn(float(px(syi, tx.sx2)), tx.tail_alpha));
     return buf;
   };
   float sum = 0.f;
@@ -401,11 +392,41 @@ __device__ __forceinline__ uint8_t area_pixel(Px px, int cw, int ch, int dx, int
     sum = first ? t : __fadd_rn(sum, t);
     first = false;
   };
-  if (ty.head()) acc(ty.sx1 - 1, ty.head_alpha());
-  const float bb = ty.body_alpha();
+  if (ty.has_head) acc(ty.sx1 - 1, ty.head_alpha);
+  const float bb = ty.body_alpha;
   for (int k = ty.sx1; k < ty.sx2; ++k) acc(k, bb);
-  if (ty.tail()) acc(ty.sx2, ty.tail_alpha());
+  if (ty.has_tail) acc(ty.sx2, ty.tail_alpha);
   return uint8_t(min(255, max(0, __float2int_rn(sum))));
+}
+
+// 0: copy, 1: 2x2, 2: integer factors, 3: general taps
+__device__ __forceinline__ int area_mode(int cw, int ch, int* ix, int* iy) {
+  const double sx = cw / 32.0, sy = ch / 32.0;
+  *ix = int(rint(sx));
+  *iy = int(rint(sy));
+  const bool fast = fabs(sx - *ix) < 2.220446049250313e-16 && fabs(sy - *iy) < 2.220446049250313e-16;
+  if (cw == 32 && ch == 32) return 0;
+  if (fast && *ix == 2 && *iy == 2) return 1;
+  return fast ? 2 : 3;
+}
+
+template <typename Px>
+__device__ __forceinline__ uint8_t area_pixel_fast(Px px, int mode, int ix, int iy, int dx, int dy) {
+  if (mode == 0) return px(dy, dx);
+  if (mode == 1)
+    return uint8_t((int(px(2 * dy, 2 * dx)) + px(2 * dy, 2 * dx + 1) + px(2 * dy + 1, 2 * dx) + px(2 * dy + 1, 2 * dx + 1) + 2) >> 2);
+  int s = 0;
+  for (int j = 0; j < iy; ++j)
+    for (int i = 0; i < ix; ++i) s += px(dy * iy + j, dx * ix + i);
+  return uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
+}
+
+template <typename Px>
+__device__ __forceinline__ uint8_t area_pixel(Px px, int cw, int ch, int dx, int dy) {
+  int ix, iy;
+  const int mode = area_mode(cw, ch, &ix, &iy);
+  if (mode != 3) return area_pixel_fast(px, mode, ix, iy, dx, dy);
+  return area_pixel_taps(px, make_taps(dx, cw, cw / 32.0), make_taps(dy, ch, ch / 32.0));
 }
 
 // cv::resize(32x32, INTER_AREA) of every frame's (already blurred) crop; crops smaller than 32 px on a
@@ -492,7 +513,8 @@ __global__ void __launch_bounds__(256)
   float* sT = reinterpret_cast<float*>(smem_raw);              // 288 floats
   float* sF = sT + 288;                                        // 81 floats (+3 pad)
   int* s_rect = reinterpret_cast<int*>(sF + 84);               // 4 ints
-  uint8_t* tile = reinterpret_cast<uint8_t*>(s_rect + 4);      // 1024 B
+  AxisTaps* s_taps = reinterpret_cast<AxisTaps*>(s_rect + 4);  // 32 x-taps + 32 y-taps
+  uint8_t* tile = reinterpret_cast<uint8_t*>(s_taps + 64);     // 1024 B
   int* ext = reinterpret_cast<int*>(tile + 1024);              // rowL[h] rowR[h] colT[w] colB[w]
   uint16_t* hs = reinterpret_cast<uint16_t*>(ext + 2 * h + 2 * w);  // h * w u16 row sums
   uint8_t* img = reinterpret_cast<uint8_t*>(hs + (size_t(h) * w + 1) / 2 * 2);  // h * w u8 (later: blurred crop)
@@ -592,30 +614,40 @@ __global__ void __launch_bounds__(256)
   const int k = blur_k_for((long long)cw * ch);
   const uint8_t* bl = img + rt * w + rl;  // blurred (or original) view
   int bl_stride = w;
+  const int lane = tid & 31, warp = tid >> 5;
   if (k) {
     const int r = k >> 1;
-    for (int i = tid; i < h * cw; i += 256) {  // horizontal sums for every parent row, view columns
-      const int y = i / cw, x = rl + (i - y * cw);
+    for (int y = warp; y < h; y += 8) {  // horizontal sums for every parent row, view columns
       const uint8_t* row = img + y * w;
-      int s = 0;
-      for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
-      hs[i] = uint16_t(s);
+      for (int xi = lane; xi < cw; xi += 32) {
+        const int x = rl + xi;
+        int s = 0;
+        for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
+        hs[y * cw + xi] = uint16_t(s);
+      }
     }
     __syncthreads();
-    for (int i = tid; i < ch * cw; i += 256) {  // vertical sums -> blurred view (dense, stride cw), reusing img
-      const int yy = i / cw, xi = i - yy * cw, y = rt + yy;
-      int s = 0;
-      for (int dy = -r; dy <= r; ++dy) s += hs[reflect101(y + dy, h) * cw + xi];
-      img[i] = uint8_t(blur_round(s, k));
+    for (int yy = warp; yy < ch; yy += 8) {  // vertical sums -> blurred view (dense, stride cw), reusing img
+      const int y = rt + yy;
+      for (int xi = lane; xi < cw; xi += 32) {
+        int s = 0;
+        for (int dy = -r; dy <= r; ++dy) s += hs[reflect101(y + dy, h) * cw + xi];
+        img[yy * cw + xi] = uint8_t(blur_round(s, k));
+      }
     }
     __syncthreads();
     bl = img;
     bl_stride = cw;
   }
 
-  // 4. INTER_AREA -> 32x32 tile
+  // 4. INTER_AREA -> 32x32 tile; the 64 coverage-tap sets are computed once per frame
+  int ix, iy;
+  const int amode = area_mode(cw, ch, &ix, &iy);
+  if (amode == 3 && tid < 64) s_taps[tid] = tid < 32 ? make_taps(tid, cw, cw / 32.0) : make_taps(tid - 32, ch, ch / 32.0);
+  __syncthreads();
+  auto px = [&](int y, int x) { return bl[y * bl_stride + x]; };
   for (int i = tid; i < 1024; i += 256)
-    tile[i] = area_pixel([&](int y, int x) { return bl[y * bl_stride + x]; }, cw, ch, i & 31, i >> 5);
+    tile[i] = amode == 3 ? area_pixel_taps(px, s_taps[i & 31], s_taps[32 + (i >> 5)]) : area_pixel_fast(px, amode, ix, iy, i & 31, i >> 5);
   __syncthreads();
 
   // 5. hash
@@ -624,7 +656,7 @@ __global__ void __launch_bounds__(256)
 }
 
 size_t fused_smem_bytes(int w, int h) {
-  return (288 + 84) * 4 + 16 + 1024 + size_t(2 * h + 2 * w) * 4 + ((size_t(h) * w + 1) / 2 * 2) * 2 + size_t(h) * w + 16;
+  return (288 + 84) * 4 + 16 + 64 * sizeof(AxisTaps) + 1024 + size_t(2 * h + 2 * w) * 4 + ((size_t(h) * w + 1) / 2 * 2) * 2 + size_t(h) * w + 16;
 }
 bool fused_ok(int w, int h) { return fused_smem_bytes(w, h) <= 200 * 1024; }
 
