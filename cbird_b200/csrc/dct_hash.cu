@@ -505,6 +505,21 @@ __device__ __forceinline__ int blur_round(int s, int k) {  // nearest integer of
   }
 }
 
+// 4 consecutive horizontal box sums (radius R) from the three words around them; b(j) = pixel x0-4+j
+template <int R>
+__device__ __forceinline__ void hsum4(uint32_t wl, uint32_t wc, uint32_t wr, int& s0, int& s1, int& s2, int& s3) {
+  auto b = [&](int j) -> int {  // j in 0..11, compile-time after unrolling
+    const uint32_t word = j < 4 ? wl : (j < 8 ? wc : wr);
+    return int((word >> (8 * (j & 3))) & 0xFFu);
+  };
+  s0 = 0;
+#pragma unroll
+  for (int j = 4 - R; j <= 4 + R; ++j) s0 += b(j);
+  s1 = s0 + b(5 + R) - b(4 - R);
+  s2 = s1 + b(6 + R) - b(5 - R);
+  s3 = s2 + b(7 + R) - b(6 - R);
+}
+
 // mode 0: whole frame; 1: rectangle given in rects; 2: autocrop(range) first, rectangle written to rects
 __global__ void __launch_bounds__(256)
     frame_hash_fused_kernel(const uint8_t* __restrict__ frames, long long row_stride, long long frame_stride, int w,
@@ -615,7 +630,50 @@ __global__ void __launch_bounds__(256)
   const uint8_t* bl = img + rt * w + rl;  // blurred (or original) view
   int bl_stride = w;
   const int lane = tid & 31, warp = tid >> 5;
-  if (k) {
+  if (k && (w & 3) == 0) {
+    // word-wise separable box sums over ALL parent columns (hs stride = w): a thread turns three u32
+    // loads into 4 horizontal sums with a sliding window; the vertical pass adds packed u16 pairs.
+    const int r = k >> 1, wq = w >> 2;
+    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
+    uint32_t* hs32 = reinterpret_cast<uint32_t*>(hs);
+    for (int y = warp; y < h; y += 8) {
+      const uint8_t* row = img + y * w;
+      for (int g = lane; g < wq; g += 32) {
+        int s0, s1, s2, s3;
+        if (g > 0 && g < wq - 1) {
+          const uint32_t wl = img32[y * wq + g - 1], wc = img32[y * wq + g], wr = img32[y * wq + g + 1];
+          if (r == 1) hsum4<1>(wl, wc, wr, s0, s1, s2, s3);
+          else if (r == 2) hsum4<2>(wl, wc, wr, s0, s1, s2, s3);
+          else hsum4<3>(wl, wc, wr, s0, s1, s2, s3);
+        } else {  // first / last word of the row: reflect at the parent's edge
+          int sv[4];
+          for (int q = 0; q < 4; ++q) {
+            int acc = 0;
+            for (int dx = -r; dx <= r; ++dx) acc += row[reflect101(4 * g + q + dx, w)];
+            sv[q] = acc;
+          }
+          s0 = sv[0]; s1 = sv[1]; s2 = sv[2]; s3 = sv[3];
+        }
+        hs32[(y * w >> 1) + 2 * g] = uint32_t(s0) | (uint32_t(s1) << 16);
+        hs32[(y * w >> 1) + 2 * g + 1] = uint32_t(s2) | (uint32_t(s3) << 16);
+      }
+    }
+    __syncthreads();
+    const int p0 = rl >> 1, p1 = (rl + cw + 1) >> 1, hw = w >> 1;  // parent column pairs touching the view
+    for (int yy = warp; yy < ch; yy += 8) {
+      const int y = rt + yy;
+      for (int p = p0 + lane; p < p1; p += 32) {
+        uint32_t acc = 0;
+        for (int d = -r; d <= r; ++d) acc += hs32[reflect101(y + d, h) * hw + p];  // two u16 lanes, max 255*49 each: no carry
+        const int x = 2 * p - rl;
+        if (x >= 0 && x < cw) img[yy * cw + x] = uint8_t(blur_round(int(acc & 0xFFFFu), k));
+        if (x + 1 >= 0 && x + 1 < cw) img[yy * cw + x + 1] = uint8_t(blur_round(int(acc >> 16), k));
+      }
+    }
+    __syncthreads();
+    bl = img;
+    bl_stride = cw;
+  } else if (k) {
     const int r = k >> 1;
     for (int y = warp; y < h; y += 8) {  // horizontal sums for every parent row, view columns
       const uint8_t* row = img + y * w;
