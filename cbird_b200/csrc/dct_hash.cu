@@ -520,6 +520,50 @@ __device__ __forceinline__ void hsum4(uint32_t wl, uint32_t wc, uint32_t wr, int
   s3 = s2 + b(7 + R) - b(6 - R);
 }
 
+// word-wise separable box blur (radius R) of the view [rl, rl+cw) x [rt, rt+ch) of the w x h frame in
+// `img` (w % 4 == 0); `hs` receives u16 row sums for all parent columns (stride w); the blurred view is
+// written back into `img` densely (stride cw). Pixels outside the view come from the parent frame,
+// reflect-101 only at the parent's edges — cv::blur on a non-isolated ROI. All 256 threads call it.
+template <int R>
+__device__ __forceinline__ void blur_view_words(uint8_t* img, uint16_t* hs, int w, int h, int rl, int rt, int cw, int ch) {
+  constexpr int K = 2 * R + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wq = w >> 2, hw = w >> 1;
+  const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
+  uint32_t* hs32 = reinterpret_cast<uint32_t*>(hs);
+  for (int y = warp; y < h; y += 8) {
+    const uint32_t* row32 = img32 + y * wq;
+    for (int g = lane; g < wq; g += 32) {
+      const uint32_t wc = row32[g];
+      uint32_t wl = row32[max(g - 1, 0)], wr = row32[min(g + 1, wq - 1)];
+      // reflect-101 at the frame edge, expressed on bytes: pixel -j == pixel j, pixel w-1+j == pixel w-1-j
+      if (g == 0) wl = __byte_perm(wc, wr, 0x1234);            // (p4, p3, p2, p1) stand in for pixels -4..-1
+      if (g == wq - 1) wr = __byte_perm(row32[max(g - 1, 0)], wc, 0x3456);  // pixels w..w+3 = (w-2, w-3, w-4, w-5)
+      int s0, s1, s2, s3;
+      hsum4<R>(wl, wc, wr, s0, s1, s2, s3);
+      hs32[y * hw + 2 * g] = uint32_t(s0) | (uint32_t(s1) << 16);
+      hs32[y * hw + 2 * g + 1] = uint32_t(s2) | (uint32_t(s3) << 16);
+    }
+  }
+  __syncthreads();
+  const int p0 = rl >> 1, p1 = (rl + cw + 1) >> 1;  // parent column pairs touching the view
+  for (int yy = warp; yy < ch; yy += 8) {
+    const int y = rt + yy;
+    int rows[K];
+#pragma unroll
+    for (int d = 0; d < K; ++d) rows[d] = reflect101(y + d - R, h) * hw;
+    for (int p = p0 + lane; p < p1; p += 32) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int d = 0; d < K; ++d) acc += hs32[rows[d] + p];  // two u16 lanes, max 255*49 each: no carry
+      const int x = 2 * p - rl;
+      if (x >= 0 && x < cw) img[yy * cw + x] = uint8_t(blur_round(int(acc & 0xFFFFu), K));
+      if (x + 1 >= 0 && x + 1 < cw) img[yy * cw + x + 1] = uint8_t(blur_round(int(acc >> 16), K));
+    }
+  }
+  __syncthreads();
+}
+
 // mode 0: whole frame; 1: rectangle given in rects; 2: autocrop(range) first, rectangle written to rects
 __global__ void __launch_bounds__(256)
     frame_hash_fused_kernel(const uint8_t* __restrict__ frames, long long row_stride, long long frame_stride, int w,
@@ -631,46 +675,9 @@ __global__ void __launch_bounds__(256)
   int bl_stride = w;
   const int lane = tid & 31, warp = tid >> 5;
   if (k && (w & 3) == 0) {
-    // word-wise separable box sums over ALL parent columns (hs stride = w): a thread turns three u32
-    // loads into 4 horizontal sums with a sliding window; the vertical pass adds packed u16 pairs.
-    const int r = k >> 1, wq = w >> 2;
-    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
-    uint32_t* hs32 = reinterpret_cast<uint32_t*>(hs);
-    for (int y = warp; y < h; y += 8) {
-      const uint8_t* row = img + y * w;
-      for (int g = lane; g < wq; g += 32) {
-        int s0, s1, s2, s3;
-        if (g > 0 && g < wq - 1) {
-          const uint32_t wl = img32[y * wq + g - 1], wc = img32[y * wq + g], wr = img32[y * wq + g + 1];
-          if (r == 1) hsum4<1>(wl, wc, wr, s0, s1, s2, s3);
-          else if (r == 2) hsum4<2>(wl, wc, wr, s0, s1, s2, s3);
-          else hsum4<3>(wl, wc, wr, s0, s1, s2, s3);
-        } else {  // first / last word of the row: reflect at the parent's edge
-          int sv[4];
-          for (int q = 0; q < 4; ++q) {
-            int acc = 0;
-            for (int dx = -r; dx <= r; ++dx) acc += row[reflect101(4 * g + q + dx, w)];
-            sv[q] = acc;
-          }
-          s0 = sv[0]; s1 = sv[1]; s2 = sv[2]; s3 = sv[3];
-        }
-        hs32[(y * w >> 1) + 2 * g] = uint32_t(s0) | (uint32_t(s1) << 16);
-        hs32[(y * w >> 1) + 2 * g + 1] = uint32_t(s2) | (uint32_t(s3) << 16);
-      }
-    }
-    __syncthreads();
-    const int p0 = rl >> 1, p1 = (rl + cw + 1) >> 1, hw = w >> 1;  // parent column pairs touching the view
-    for (int yy = warp; yy < ch; yy += 8) {
-      const int y = rt + yy;
-      for (int p = p0 + lane; p < p1; p += 32) {
-        uint32_t acc = 0;
-        for (int d = -r; d <= r; ++d) acc += hs32[reflect101(y + d, h) * hw + p];  // two u16 lanes, max 255*49 each: no carry
-        const int x = 2 * p - rl;
-        if (x >= 0 && x < cw) img[yy * cw + x] = uint8_t(blur_round(int(acc & 0xFFFFu), k));
-        if (x + 1 >= 0 && x + 1 < cw) img[yy * cw + x + 1] = uint8_t(blur_round(int(acc >> 16), k));
-      }
-    }
-    __syncthreads();
+    if (k == 3) blur_view_words<1>(img, hs, w, h, rl, rt, cw, ch);
+    else if (k == 5) blur_view_words<2>(img, hs, w, h, rl, rt, cw, ch);
+    else blur_view_words<3>(img, hs, w, h, rl, rt, cw, ch);
     bl = img;
     bl_stride = cw;
   } else if (k) {
