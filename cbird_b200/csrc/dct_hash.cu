@@ -584,15 +584,13 @@ __global__ void __launch_bounds__(256)
   if ((w & 3) == 0 && (row_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
     const int wq = w >> 2;
     uint32_t* img32 = reinterpret_cast<uint32_t*>(img);
-    for (int i = tid; i < h * wq; i += 256) {
-      const int y = i / wq, xq = i - y * wq;
-      img32[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (long long)y * row_stride) + xq);
+    for (int y = tid >> 5; y < h; y += 8) {
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (long long)y * row_stride);
+      for (int xq = tid & 31; xq < wq; xq += 32) img32[y * wq + xq] = __ldg(srow + xq);
     }
   } else {
-    for (int i = tid; i < h * w; i += 256) {
-      const int y = i / w, x = i - y * w;
-      img[i] = src[(long long)y * row_stride + x];
-    }
+    for (int y = tid >> 5; y < h; y += 8)
+      for (int x = tid & 31; x < w; x += 32) img[y * w + x] = src[(long long)y * row_stride + x];
   }
   __syncthreads();
 
