@@ -9,8 +9,9 @@
 //                         same order (no FMA contraction), round half to even
 //   dct_hash32_kernel     u8 32x32 tile -> hash.  One CTA = 32 frames, 256 threads:
 //     stage 1  lane = image row: the row (32 B, two LDG.128) stays in registers; 9 lowest DCT outputs
-//              by a decimated butterfly network (61 FADD + 86 FFMA) against the DCT basis in
-//              __constant__ memory (operand straight from the constant bank)
+//              by a decimated butterfly network whose first level and multiply-add chains are packed
+//              f32x2 instructions (FADD2 / FFMA2, sm_100: IEEE per half, half the issue slots) against
+//              the DCT basis in __constant__ memory
 //              -> T[y][0..8] to shared memory (stride 297 floats per frame: conflict free both ways)
 //     stage 2  thread = (frame, column u): same butterfly + 9 chains down the column -> F[0..8][u]
 //     stage 3  warp = frame: zig-zag gather of the 64 kept coefficients (2 per lane), f64 butterfly
@@ -67,56 +68,74 @@ int upload_tables() {
 
 constexpr int kTStride = 297;  // 9*33: (9*frame + 9*y + u) mod 32 is a permutation for 32 consecutive tasks
 
-// acc = 0; acc = fma(C[U][x], v[x], acc) for x ascending — the oracle's order (oracle: chain())
-template <int U, int N>
-__device__ __forceinline__ float chain(const float (&v)[N]) {
-  float acc = 0.f;
+// dot product of basis row U with v[0..2*NP) in the oracle's order (oracle: chain()): two running sums,
+// one over the even and one over the odd indices, each a chain of fused multiply-adds in ascending
+// index starting from 0, added at the end. The two sums are the halves of one packed FFMA2 (sm_100
+// f32x2: IEEE fma per half, one issue slot for two lanes).
+template <int U, int NP>
+__device__ __forceinline__ float chain2(const float2 (&v)[NP]) {
+  float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int x = 0; x < N; ++x) acc = __fmaf_rn(c_basis[U][x], v[x], acc);
-  return acc;
+  for (int p = 0; p < NP; ++p) acc = __ffma2_rn(make_float2(c_basis[U][2 * p], c_basis[U][2 * p + 1]), v[p], acc);
+  return __fadd_rn(acc.x, acc.y);
 }
 
 // 9 lowest outputs of the 32-point DCT-II as a decimated butterfly network (oracle: dct9_of_32):
 // even outputs come from recursively folded sums/differences, so constant input gives exact zeros for
-// u>0 like cv::dct's FFT butterflies; 61 FADD + 86 FFMA + 1 FMUL per transform.
-__device__ __forceinline__ void dct9_of_32(const float (&in)[32], float (&out)[9]) {
-  float s1[16], d1[16], s2[8], d2[8], s3[4], d3[4], s4[2], d4[2];
+// u>0 like cv::dct's FFT butterflies. Inputs arrive as pairs: fwd[i] = (x[2i], x[2i+1]),
+// rev[i] = (x[31-2i], x[30-2i]), so the first butterfly level is 16 packed FADD2.
+__device__ __forceinline__ void dct9_of_32(const float2 (&fwd)[8], const float2 (&rev)[8], float (&out)[9]) {
+  float2 s1[8], d1[8];
 #pragma unroll
-  for (int x = 0; x < 16; ++x) {
-    s1[x] = __fadd_rn(in[x], in[31 - x]);
-    d1[x] = __fsub_rn(in[x], in[31 - x]);
+  for (int i = 0; i < 8; ++i) {
+    s1[i] = __fadd2_rn(fwd[i], rev[i]);                                // (s1[2i], s1[2i+1])
+    d1[i] = __fadd2_rn(fwd[i], make_float2(-rev[i].x, -rev[i].y));     // (d1[2i], d1[2i+1])
   }
-  out[1] = chain<1, 16>(d1);
-  out[3] = chain<3, 16>(d1);
-  out[5] = chain<5, 16>(d1);
-  out[7] = chain<7, 16>(d1);
+  out[1] = chain2<1, 8>(d1);
+  out[3] = chain2<3, 8>(d1);
+  out[5] = chain2<5, 8>(d1);
+  out[7] = chain2<7, 8>(d1);
+  auto S1 = [&](int x) { return (x & 1) ? s1[x >> 1].y : s1[x >> 1].x; };
+  float s2[8];
+  float2 d2[4];
 #pragma unroll
-  for (int x = 0; x < 8; ++x) {
-    s2[x] = __fadd_rn(s1[x], s1[15 - x]);
-    d2[x] = __fsub_rn(s1[x], s1[15 - x]);
+  for (int x = 0; x < 8; x += 2) {
+    s2[x] = __fadd_rn(S1(x), S1(15 - x));
+    s2[x + 1] = __fadd_rn(S1(x + 1), S1(14 - x));
+    d2[x >> 1] = make_float2(__fsub_rn(S1(x), S1(15 - x)), __fsub_rn(S1(x + 1), S1(14 - x)));
   }
-  out[2] = chain<2, 8>(d2);
-  out[6] = chain<6, 8>(d2);
+  out[2] = chain2<2, 4>(d2);
+  out[6] = chain2<6, 4>(d2);
+  float s3[4];
+  float2 d3[2];
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
+  for (int x = 0; x < 4; x += 2) {
     s3[x] = __fadd_rn(s2[x], s2[7 - x]);
-    d3[x] = __fsub_rn(s2[x], s2[7 - x]);
+    s3[x + 1] = __fadd_rn(s2[x + 1], s2[6 - x]);
+    d3[x >> 1] = make_float2(__fsub_rn(s2[x], s2[7 - x]), __fsub_rn(s2[x + 1], s2[6 - x]));
   }
-  out[4] = chain<4, 4>(d3);
-#pragma unroll
-  for (int x = 0; x < 2; ++x) {
-    s4[x] = __fadd_rn(s3[x], s3[3 - x]);
-    d4[x] = __fsub_rn(s3[x], s3[3 - x]);
-  }
-  out[8] = chain<8, 2>(d4);
-  out[0] = __fmul_rn(__fadd_rn(s4[0], s4[1]), c_basis[0][0]);
+  out[4] = chain2<4, 2>(d3);
+  const float s40 = __fadd_rn(s3[0], s3[3]), s41 = __fadd_rn(s3[1], s3[2]);
+  const float2 d4[1] = {make_float2(__fsub_rn(s3[0], s3[3]), __fsub_rn(s3[1], s3[2]))};
+  out[8] = chain2<8, 1>(d4);
+  out[0] = __fmul_rn(__fadd_rn(s40, s41), c_basis[0][0]);
 }
 
 // u8 -> f32 without the (quarter-rate, XU pipe) I2F: PRMT drops the byte into the mantissa of 2^23,
 // one FADD removes the bias. Exact for 0..255.
-__device__ __forceinline__ float byte_of(const uint32_t (&w)[8], int x) {
-  const uint32_t bits = __byte_perm(w[x >> 2], 0x4B000000u, 0x7540u | uint32_t(x & 3));
-  return __fsub_rn(__uint_as_float(bits), 8388608.f);
+__device__ __forceinline__ float2 bytes_of(const uint32_t (&w)[8], int x0, int x1) {
+  const uint32_t b0 = __byte_perm(w[x0 >> 2], 0x4B000000u, 0x7540u | uint32_t(x0 & 3));
+  const uint32_t b1 = __byte_perm(w[x1 >> 2], 0x4B000000u, 0x7540u | uint32_t(x1 & 3));
+  return __fadd2_rn(make_float2(__uint_as_float(b0), __uint_as_float(b1)), make_float2(-8388608.f, -8388608.f));
+}
+
+// (x[2i], x[2i+1]) and (x[31-2i], x[30-2i]) pairs of one image row held as 8 words
+__device__ __forceinline__ void row_pairs(const uint32_t (&w)[8], float2 (&fwd)[8], float2 (&rev)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    fwd[i] = bytes_of(w, 2 * i, 2 * i + 1);
+    rev[i] = bytes_of(w, 31 - 2 * i, 30 - 2 * i);
+  }
 }
 
 template <int kFramesPerCta, int kHashThreads, int kMinBlocks>
@@ -145,10 +164,10 @@ __global__ void __launch_bounds__(kHashThreads, kMinBlocks)
         w[i] = uint32_t(row[4 * i]) | (uint32_t(row[4 * i + 1]) << 8) | (uint32_t(row[4 * i + 2]) << 16) |
                (uint32_t(row[4 * i + 3]) << 24);
     }
-    float px[32], t[9];
-#pragma unroll
-    for (int x = 0; x < 32; ++x) px[x] = byte_of(w, x);
-    dct9_of_32(px, t);
+    float2 fwd[8], rev[8];
+    float t[9];
+    row_pairs(w, fwd, rev);
+    dct9_of_32(fwd, rev, t);
     float* dst = sT + fl * kTStride + lane * 9;
 #pragma unroll
     for (int u = 0; u < 9; ++u) dst[u] = t[u];
@@ -159,10 +178,14 @@ __global__ void __launch_bounds__(kHashThreads, kMinBlocks)
   for (int task = threadIdx.x; task < nf * 9; task += kHashThreads) {
     const int fl = task / 9, u = task - 9 * fl;
     const float* col = sT + fl * kTStride + u;
-    float cv[32], f[9];
+    float2 fwd[8], rev[8];
+    float f[9];
 #pragma unroll
-    for (int y = 0; y < 32; ++y) cv[y] = col[9 * y];
-    dct9_of_32(cv, f);
+    for (int i = 0; i < 8; ++i) {
+      fwd[i] = make_float2(col[9 * (2 * i)], col[9 * (2 * i + 1)]);
+      rev[i] = make_float2(col[9 * (31 - 2 * i)], col[9 * (30 - 2 * i)]);
+    }
+    dct9_of_32(fwd, rev, f);
     float* dst = sF + fl * 81 + u;
 #pragma unroll
     for (int v = 0; v < 9; ++v) dst[9 * v] = f[v];  // row v = vertical frequency (cv::dct layout)
@@ -464,20 +487,24 @@ __device__ uint64_t hash_tile_cta(const uint8_t* tile, float* sT, float* sF) {
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = row[i];
-    float px[32], t[9];
-#pragma unroll
-    for (int x = 0; x < 32; ++x) px[x] = byte_of(w, x);
-    dct9_of_32(px, t);
+    float2 fwd[8], rev[8];
+    float t[9];
+    row_pairs(w, fwd, rev);
+    dct9_of_32(fwd, rev, t);
 #pragma unroll
     for (int u = 0; u < 9; ++u) sT[lane * 9 + u] = t[u];
   }
   __syncthreads();
   if (threadIdx.x < 9) {
     const int u = threadIdx.x;
-    float cv[32], f[9];
+    float2 fwd[8], rev[8];
+    float f[9];
 #pragma unroll
-    for (int y = 0; y < 32; ++y) cv[y] = sT[9 * y + u];
-    dct9_of_32(cv, f);
+    for (int i = 0; i < 8; ++i) {
+      fwd[i] = make_float2(sT[9 * (2 * i) + u], sT[9 * (2 * i + 1) + u]);
+      rev[i] = make_float2(sT[9 * (31 - 2 * i) + u], sT[9 * (30 - 2 * i) + u]);
+    }
+    dct9_of_32(fwd, rev, f);
 #pragma unroll
     for (int v = 0; v < 9; ++v) sF[9 * v + u] = f[v];
   }

@@ -196,10 +196,15 @@ int orc_preprocess32(const uint8_t* img, int w, int h, int stride, uint8_t* out3
 // constant input gives EXACTLY zero for u>0 (as cv::dct's FFT butterflies do) instead of rounding
 // noise.  basis symmetry: C[u][N-1-x] = (-1)^(u/(64/ (2N))) C[u][x] on the folded length N.
 // The operation order below is fixed; the CUDA kernel follows it instruction for instruction.
+// two running sums (even / odd indices), each a chain of fused multiply-adds in ascending index
+// starting from 0, added at the end — the two halves of the GPU's packed f32x2 FFMA
 static inline float chain(const float* c, const float* v, int n) {
-  float acc = 0.f;
-  for (int x = 0; x < n; ++x) acc = fmaf(c[x], v[x], acc);
-  return acc;
+  float acc_e = 0.f, acc_o = 0.f;
+  for (int x = 0; x < n; x += 2) {
+    acc_e = fmaf(c[x], v[x], acc_e);
+    acc_o = fmaf(c[x + 1], v[x + 1], acc_o);
+  }
+  return acc_e + acc_o;
 }
 static void dct9_of_32(const float C[9][32], const float in[32], float out[9]) {
   float s1[16], d1[16], s2[8], d2[8], s3[4], d3[4], s4[2], d4[2];
