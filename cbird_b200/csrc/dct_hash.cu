@@ -911,9 +911,9 @@ int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long l
 int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long t_frame, uint64_t* d_out,
                   cudaStream_t stream) {
   const int aligned16 = ((reinterpret_cast<uintptr_t>(tiles) | uintptr_t(t_row) | uintptr_t(t_frame)) & 15) == 0;
-  // CTA shape: measured on B200 (tools/hash_bench.py) 8 frames x 64 threads 0.481 ms, 16x128 0.492,
-  // 32x256 0.513, 32x128 0.572 per 2^20 frames — the kernel is issue-bound, the shape hardly matters.
-  static const int variant = getenv("CB_HASH_VARIANT") ? atoi(getenv("CB_HASH_VARIANT")) : 2;
+  // CTA shape: measured on B200 (tools/hash_bench.py, packed f32x2 build) 16 frames x 128 threads 0.417 ms,
+  // 8x64 0.423, 32x256 0.444 per 2^20 frames — the kernel is issue-bound, the shape hardly matters.
+  static const int variant = getenv("CB_HASH_VARIANT") ? atoi(getenv("CB_HASH_VARIANT")) : 1;
   switch (variant) {
     case 1:
       dct_hash32_kernel<16, 128, 8><<<unsigned((n + 15) / 16), 128, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
