@@ -193,9 +193,12 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+ROWS_OVERRIDE = 0
+
+
 def rows_for(world):
     # weak scaling: every GPU keeps BASE_ROWS^2 pair tests per step -> rows = BASE_ROWS * sqrt(world)
-    n = int(round(BASE_ROWS * (world ** 0.5)))
+    n = ROWS_OVERRIDE or int(round(BASE_ROWS * (world ** 0.5)))
     return (n + 4095) // 4096 * 4096
 
 
@@ -217,8 +220,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip dct_hash / single-needle / cpu_baseline legs")
+    ap.add_argument("--rows", type=int, default=0, help="override the index size (e.g. 10000000 = BASELINE configs[2]); "
+                                                        "default 2^20 * sqrt(gpus) (weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    global ROWS_OVERRIDE
+    ROWS_OVERRIDE = max(0, args.rows)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -504,7 +511,7 @@ def main():
         line = {
             "metric": "hamming_comparisons_per_sec", "value": value, "unit": "comparisons/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": "strong" if ROWS_OVERRIDE else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(world, n_rows),
             "hits_per_step": n_hits, "kernel_ms_per_step": kern_ms, "wall_s_timed_region": wall,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
