@@ -120,7 +120,11 @@ struct DctIndex {
     if (!n_q || !n_rows || threshold <= 0) return CB_OK;
     // the register side of the scan wants the long array
     const bool swapped = n_q < n_rows;
-    unsigned long long cap = d_pairs.cap ? d_pairs.cap : (1ull << 20);
+    // first guess of the hit-list size: every needle that is also a row finds at least itself, planted
+    // near-duplicates add a small multiple; an overflow costs a second scan, so be generous up front
+    unsigned long long guess = symmetric_self ? 3ull * n_rows : 2ull * n_q + (1ull << 16);
+    guess = std::min<unsigned long long>(std::max<unsigned long long>(guess, 1ull << 20), 1ull << 28);
+    unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, guess);
     for (int attempt = 0; attempt < 3; ++attempt) {
       int rc = d_pairs.reserve(cap);
       if (rc != CB_OK) return rc;

@@ -258,7 +258,8 @@ struct OrbIndex {
     rc = d_q.reserve(size_t(nq) * 32 + 32);
     if (rc != CB_OK) return rc;
     CB_CUDA(cudaMemcpyAsync(d_q.p, q, size_t(nq) * 32, cudaMemcpyHostToDevice, stream));
-    unsigned long long cap = d_pairs.cap ? d_pairs.cap : (1ull << 18);
+    // an overflow of the hit list costs a second scan: size the first guess from the needle count
+    unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, std::min<unsigned long long>(4ull * nq + (1ull << 18), 1ull << 28));
     for (int attempt = 0; attempt < 3; ++attempt) {
       rc = d_pairs.reserve(cap);
       if (rc != CB_OK) return rc;

@@ -253,7 +253,7 @@ struct VideoIndex {
       if (rc != CB_OK) return rc;
       CB_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(cb_scan_tile), cudaMemcpyHostToDevice, stream));
     }
-    unsigned long long cap = d_pairs.cap ? d_pairs.cap : (1ull << 20);
+    unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, std::min<unsigned long long>(8ull * nq + (1ull << 20), 1ull << 28));
     for (int attempt = 0; attempt < 3; ++attempt) {
       rc = d_pairs.reserve(cap);
       if (rc != CB_OK) return rc;
