@@ -64,7 +64,9 @@ __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds
   asm volatile("" : "+r"(alo), "+r"(ahi));
   const uint32_t xlo = alo ^ blo;
   const int d = __popc(xlo) + __popc(ahi ^ bhi);
-  if (d < P.threshold && ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
+  // most entries are false positives of the pre-filter: leave through the cheapest test first
+  if (d >= P.threshold) return;
+  if (ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
     const unsigned long long pos = atomicAdd(P.count, mirror ? 2ull : 1ull);
     if (pos < P.cap) *reinterpret_cast<uint4*>(P.out + pos) = make_uint4(ai, bi, uint32_t(d), 0u);
     if (mirror && pos + 1 < P.cap) *reinterpret_cast<uint4*>(P.out + pos + 1) = make_uint4(bi, ai, uint32_t(d), 0u);

@@ -6,6 +6,7 @@ this module; the product package (cbird_b200/) never does.
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -19,7 +20,7 @@ _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
 def build():
     """compile the restatement (always) and the reference headers (only where /root/reference exists)."""
-    subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True)
+    subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True, stdout=sys.stderr)  # keep callers' stdout clean
 
 
 _oracle = None
