@@ -3,10 +3,13 @@
 //
 // Pipeline per frame:
 //   [only when the frame is not already 32x32]
-//     box_blur_kernel     cv::blur k=3/5/7 chosen by input area, BORDER_REFLECT_101, integer exact
-//     area_resize_kernel  cv::resize(32x32, INTER_AREA): (s+2)>>2 for 2x2, rint(sum*f32(1/area)) for
-//                         other integer factors, else OpenCV's f32 coverage-weight accumulation in the
-//                         same order (no FMA contraction), round half to even
+//     frame_hash_fused_kernel   one CTA per frame, everything staged through shared memory (frames that
+//                               fit: video frames): cv::blur k=3/5/7 by area (BORDER_REFLECT_101, integer
+//                               exact), cv::resize(32x32, INTER_AREA) ((s+2)>>2 for 2x2, rint(sum*f32(1/area))
+//                               for other integer factors, else OpenCV's f32 coverage-weight accumulation in
+//                               the same order, no FMA contraction, round half to even), then the hash
+//     box_blur_rect_kernel + area_resize_rect_kernel   the same arithmetic through global memory for
+//                               frames too large for one CTA's shared memory
 //   dct_hash32_kernel     u8 32x32 tile -> hash.  One CTA = 32 frames, 256 threads:
 //     stage 1  lane = image row: the row (32 B, two LDG.128) stays in registers; 9 lowest DCT outputs
 //              by a decimated butterfly network whose first level and multiply-add chains are packed
@@ -218,59 +221,6 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
-__global__ void box_blur_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int w,
-                                int h, int k, uint8_t* __restrict__ dst) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
-  const uint8_t* f = src + (long long)blockIdx.z * frame_stride;
-  const int r = k >> 1, area = k * k;
-  int s = 0;
-  for (int dy = -r; dy <= r; ++dy) {
-    const uint8_t* row = f + (long long)reflect101(y + dy, h) * row_stride;
-    for (int dx = -r; dx <= r; ++dx) s += row[reflect101(x + dx, w)];
-  }
-  dst[((long long)blockIdx.z * h + y) * w + x] = uint8_t((2 * s + area) / (2 * area));
-}
-
-struct AreaTap {
-  int si;
-  float alpha;
-};
-
-// mode 0: 2x2 integer;  1: integer factors (ix, iy);  2: general f32 taps
-__global__ void __launch_bounds__(1024)
-    area_resize_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int mode, int ix,
-                       int iy, const AreaTap* __restrict__ xt, const int* __restrict__ xofs,
-                       const AreaTap* __restrict__ yt, const int* __restrict__ yofs, uint8_t* __restrict__ dst) {
-  const int dx = threadIdx.x & 31, dy = threadIdx.x >> 5;
-  const uint8_t* f = src + (long long)blockIdx.x * frame_stride;
-  uint8_t r;
-  if (mode == 0) {
-    const uint8_t* a = f + (long long)(2 * dy) * row_stride + 2 * dx;
-    const uint8_t* b = a + row_stride;
-    r = uint8_t((int(a[0]) + a[1] + b[0] + b[1] + 2) >> 2);
-  } else if (mode == 1) {
-    int s = 0;
-    for (int j = 0; j < iy; ++j) {
-      const uint8_t* row = f + (long long)(dy * iy + j) * row_stride + dx * ix;
-      for (int i = 0; i < ix; ++i) s += row[i];
-    }
-    const float v = __fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)));
-    r = uint8_t(min(255, max(0, __float2int_rn(v))));
-  } else {
-    float sum = 0.f;
-    for (int j = yofs[dy]; j < yofs[dy + 1]; ++j) {
-      const uint8_t* row = f + (long long)yt[j].si * row_stride;
-      float buf = 0.f;
-      for (int k = xofs[dx]; k < xofs[dx + 1]; ++k) buf = __fadd_rn(buf, __fmul_rn(float(row[xt[k].si]), xt[k].alpha));
-      const float t = __fmul_rn(yt[j].alpha, buf);
-      sum = (j == yofs[dy]) ? t : __fadd_rn(sum, t);
-    }
-    r = uint8_t(min(255, max(0, __float2int_rn(sum))));
-  }
-  dst[(long long)blockIdx.x * 1024 + threadIdx.x] = r;
-}
-
 // ---- per-frame crop rectangles: autocrop + dctHash64 of the cropped view ---------------------------
 // rect = {left, top, right, bottom} (right/bottom exclusive) inside the w x h parent frame.
 
@@ -348,7 +298,8 @@ __device__ __forceinline__ int blur_k_for(long long area) {  // src/cvutil.cpp:4
 // BORDER_ISOLATED) and reflects (101) only at the parent's own edges. Output: dense crop at stride w.
 __global__ void box_blur_rect_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride,
                                      int w, int h, const int32_t* __restrict__ rects, uint8_t* __restrict__ dst) {
-  const int32_t* rc = rects + 4 * (long long)blockIdx.z;
+  const int full[4] = {0, 0, w, h};
+  const int32_t* rc = rects ? rects + 4 * (long long)blockIdx.z : full;  // no rectangles: the whole frame
   const int cw = rc[2] - rc[0], ch = rc[3] - rc[1];
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= cw || y >= ch) return;
@@ -457,7 +408,8 @@ __device__ __forceinline__ uint8_t area_pixel(Px px, int cw, int ch, int dx, int
 __global__ void __launch_bounds__(1024)
     area_resize_rect_kernel(const uint8_t* __restrict__ src, int w, int h, const int32_t* __restrict__ rects,
                             uint8_t* __restrict__ dst, uint8_t* __restrict__ bad) {
-  const int32_t* rc = rects + 4 * (long long)blockIdx.x;
+  const int full[4] = {0, 0, w, h};
+  const int32_t* rc = rects ? rects + 4 * (long long)blockIdx.x : full;  // no rectangles: the whole frame
   const int cw = rc[2] - rc[0], ch = rc[3] - rc[1];
   const int dx = threadIdx.x & 31, dy = threadIdx.x >> 5;
   const uint8_t* f = src + (long long)blockIdx.x * h * w;
@@ -769,34 +721,15 @@ int launch_fused(const uint8_t* d_frames, long long n, int w, int h, long long r
   return CB_OK;
 }
 
-// OpenCV computeResizeAreaTab (third-party imgproc, restated): coverage weights in f32
-void area_taps(int ssize, double scale, std::vector<AreaTap>& tab, std::vector<int>& ofs) {
-  tab.clear();
-  ofs.assign(33, 0);
-  for (int dx = 0; dx < 32; ++dx) {
-    ofs[dx] = int(tab.size());
-    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
-    const double cell = std::min(scale, ssize - fsx1);
-    int sx1 = int(ceil(fsx1)), sx2 = int(floor(fsx2));
-    sx2 = std::min(sx2, ssize - 1);
-    sx1 = std::min(sx1, sx2);
-    if (sx1 - fsx1 > 1e-3) tab.push_back({sx1 - 1, float((sx1 - fsx1) / cell)});
-    for (int sx = sx1; sx < sx2; ++sx) tab.push_back({sx, float(1.0 / cell)});
-    if (fsx2 - sx2 > 1e-3) tab.push_back({sx2, float(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
-  }
-  ofs[32] = int(tab.size());
-}
-
 struct HashWorkspace {
   DevBuf<uint8_t> blurred, tiles, bad;
   DevBuf<int32_t> rects;
-  DevBuf<AreaTap> xt, yt;
-  DevBuf<int> xofs, yofs;
-  int tab_w = -1, tab_h = -1;
 };
 
 int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long t_frame, uint64_t* d_out,
                   cudaStream_t stream);
+int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride, long long frame_stride,
+                      const int32_t* d_rects, uint64_t* d_out, HashWorkspace* ws, cudaStream_t stream);
 
 // frames already on the device. ws may be null only for 32x32 input.
 int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long long row_stride,
@@ -809,56 +742,8 @@ int hash_frames_device(const uint8_t* d_frames, long long n, int w, int h, long 
   static const bool no_fused = getenv("CB_HASH_NO_FUSED") != nullptr;  // tuning / parity aid
   if (!(w == 32 && h == 32) && fused_ok(w, h) && !no_fused)
     return launch_fused(d_frames, n, w, h, row_stride, frame_stride, 0, 0, nullptr, d_out, stream);
-  if (!(w == 32 && h == 32)) {
-    const long long area = (long long)w * h;
-    int k = 7;  // src/cvutil.cpp:446-455
-    if (area <= 32 * 32) k = 0;
-    else if (area <= 64 * 64) k = 3;
-    else if (area <= 128 * 128) k = 5;
-    const uint8_t* src = d_frames;
-    long long s_row = row_stride, s_frame = frame_stride;
-    if (k) {
-      rc = ws->blurred.reserve(size_t(n) * w * h);
-      if (rc != CB_OK) return rc;
-      dim3 grid((w + 127) / 128, h, unsigned(n)), block(128);
-      box_blur_kernel<<<grid, block, 0, stream>>>(d_frames, row_stride, frame_stride, w, h, k, ws->blurred.p);
-      CB_CUDA(cudaGetLastError());
-      counters().launches += 1;
-      src = ws->blurred.p;
-      s_row = w;
-      s_frame = area;
-    }
-    rc = ws->tiles.reserve(size_t(n) * 1024);
-    if (rc != CB_OK) return rc;
-    const double sx = w / 32.0, sy = h / 32.0;
-    const int ix = int(lrint(sx)), iy = int(lrint(sy));
-    const bool fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
-    int mode = 2;
-    if (fast) mode = (ix == 2 && iy == 2) ? 0 : 1;
-    if (mode == 2 && (ws->tab_w != w || ws->tab_h != h)) {
-      std::vector<AreaTap> xt, yt;
-      std::vector<int> xo, yo;
-      area_taps(w, sx, xt, xo);
-      area_taps(h, sy, yt, yo);
-      CB_CUDA(cudaStreamSynchronize(stream));  // previous users of the tables are done
-      if ((rc = ws->xt.reserve(xt.size())) != CB_OK || (rc = ws->yt.reserve(yt.size())) != CB_OK ||
-          (rc = ws->xofs.reserve(33)) != CB_OK || (rc = ws->yofs.reserve(33)) != CB_OK)
-        return rc;
-      CB_CUDA(cudaMemcpy(ws->xt.p, xt.data(), xt.size() * sizeof(AreaTap), cudaMemcpyHostToDevice));
-      CB_CUDA(cudaMemcpy(ws->yt.p, yt.data(), yt.size() * sizeof(AreaTap), cudaMemcpyHostToDevice));
-      CB_CUDA(cudaMemcpy(ws->xofs.p, xo.data(), 33 * sizeof(int), cudaMemcpyHostToDevice));
-      CB_CUDA(cudaMemcpy(ws->yofs.p, yo.data(), 33 * sizeof(int), cudaMemcpyHostToDevice));
-      ws->tab_w = w;
-      ws->tab_h = h;
-    }
-    area_resize_kernel<<<unsigned(n), 1024, 0, stream>>>(src, s_row, s_frame, mode, ix, iy, ws->xt.p, ws->xofs.p,
-                                                          ws->yt.p, ws->yofs.p, ws->tiles.p);
-    CB_CUDA(cudaGetLastError());
-    counters().launches += 1;
-    tiles = ws->tiles.p;
-    t_row = 32;
-    t_frame = 1024;
-  }
+  if (!(w == 32 && h == 32))  // too large for one CTA's shared memory: blur + INTER_AREA through global memory
+    return hash_rects_device(d_frames, n, w, h, row_stride, frame_stride, nullptr, d_out, ws, stream);
   return launch_hash32(tiles, n, t_row, t_frame, d_out, stream);
 }
 
@@ -891,7 +776,8 @@ int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long l
   if (rc != CB_OK) return rc;
   static const bool no_fused = getenv("CB_HASH_NO_FUSED") != nullptr;
   if (fused_ok(w, h) && !no_fused)
-    return launch_fused(d_frames, n, w, h, row_stride, frame_stride, 1, 0, const_cast<int32_t*>(d_rects), d_out, stream);
+    return launch_fused(d_frames, n, w, h, row_stride, frame_stride, d_rects ? 1 : 0, 0, const_cast<int32_t*>(d_rects), d_out,
+                        stream);
   if ((rc = ws->blurred.reserve(size_t(n) * w * h)) != CB_OK || (rc = ws->tiles.reserve(size_t(n) * 1024)) != CB_OK ||
       (rc = ws->bad.reserve(size_t(n))) != CB_OK)
     return rc;
