@@ -56,6 +56,8 @@ SIGNATURES = {
     "cb_stats_reset": (None, []),
     "cb_free": (None, [_vp]),
     "cb_hash_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
+    "cb_gray_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp]),
+    "cb_hash_batch_color": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp]),
     "cb_hash_batch_dev": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp]),
     "cb_autocrop_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp]),
     "cb_hash_batch_rects": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp]),
@@ -123,6 +125,7 @@ SIGNATURES = {
     "cb_orb_index_save_cache": (C.c_int, [_vp, C.c_char_p]),
     "cb_orb_index_load_cache": (C.c_int, [_vp, C.c_char_p]),
     "cb_orb_index_knn_alloc": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cb_orb_radius_match_alloc": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
 }
 
 

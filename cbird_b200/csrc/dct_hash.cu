@@ -823,6 +823,77 @@ int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long 
   return CB_OK;
 }
 
+// grayscale() (src/cvutil.cpp:1265-1283): cv::cvtColor(BGR2GRAY / BGRA2GRAY) of 8-bit pixels is fixed point,
+//   OpenCV 2.4.x (the reference pins 2.4.13.7): (1868 B + 9617 G + 4899 R + 2^13) >> 14
+//   OpenCV 4.x (pinned here against cv2 4.13 over all 2^24 colours): (3735 B + 19235 G + 9798 R + 2^14) >> 15
+// Four pixels per thread: 12 or 16 source bytes as 32-bit words when the rows are word aligned, one packed
+// 32-bit store; the output is dense (w x h per frame).
+struct GrayCoef {
+  int cb, cg, cr, half, shift;
+};
+__host__ __device__ inline GrayCoef gray_coef(int mode) {
+  return mode == CB_GRAY_Q14 ? GrayCoef{1868, 9617, 4899, 1 << 13, 14} : GrayCoef{3735, 19235, 9798, 1 << 14, 15};
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256)
+    bgr_to_gray_kernel(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int w, int h,
+                       long long n, int mode, int word_aligned, uint8_t* __restrict__ dst) {
+  const GrayCoef c = gray_coef(mode);
+  const int qw = (w + 3) >> 2;
+  const long long total = n * h * qw;
+  for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += 256ll * gridDim.x) {
+    const int q = int(t % qw);
+    const long long row = t / qw;
+    const int y = int(row % h);
+    const long long f = row / h;
+    const int x0 = q * 4;
+    const uint8_t* sp = src + f * frame_stride + y * row_stride + (long long)x0 * CN;
+    uint8_t* dp = dst + (f * h + y) * (long long)w + x0;
+    const int m = min(4, w - x0);
+    uint32_t g[4];
+    if (word_aligned && m == 4) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(sp);
+      if (CN == 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t px = __ldg(wp + i);
+          g[i] = ((px & 255) * c.cb + ((px >> 8) & 255) * c.cg + ((px >> 16) & 255) * c.cr + c.half) >> c.shift;
+        }
+      } else {
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);  // B0G0R0B1 G1R1B2G2 R2B3G3R3
+        g[0] = ((w0 & 255) * c.cb + ((w0 >> 8) & 255) * c.cg + ((w0 >> 16) & 255) * c.cr + c.half) >> c.shift;
+        g[1] = ((w0 >> 24) * c.cb + (w1 & 255) * c.cg + ((w1 >> 8) & 255) * c.cr + c.half) >> c.shift;
+        g[2] = (((w1 >> 16) & 255) * c.cb + (w1 >> 24) * c.cg + (w2 & 255) * c.cr + c.half) >> c.shift;
+        g[3] = (((w2 >> 8) & 255) * c.cb + ((w2 >> 16) & 255) * c.cg + (w2 >> 24) * c.cr + c.half) >> c.shift;
+      }
+    } else {
+      for (int i = 0; i < m; ++i)
+        g[i] = (sp[i * CN] * c.cb + sp[i * CN + 1] * c.cg + sp[i * CN + 2] * c.cr + c.half) >> c.shift;
+    }
+    if (m == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(dp) = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
+    } else {
+      for (int i = 0; i < m; ++i) dp[i] = uint8_t(g[i]);
+    }
+  }
+}
+
+int gray_device(const uint8_t* d_src, long long n, int w, int h, int channels, long long row_stride,
+                long long frame_stride, int mode, uint8_t* d_dst, cudaStream_t stream) {
+  if (n <= 0) return CB_OK;
+  const long long total = n * h * ((w + 3) / 4);
+  const unsigned blocks = unsigned(std::min<long long>((total + 255) / 256, 148ll * 8 * 16));
+  const int aligned = ((reinterpret_cast<uintptr_t>(d_src) | uintptr_t(row_stride) | uintptr_t(frame_stride)) & 3) == 0;
+  if (channels == 3)
+    bgr_to_gray_kernel<3><<<blocks, 256, 0, stream>>>(d_src, row_stride, frame_stride, w, h, n, mode, aligned, d_dst);
+  else
+    bgr_to_gray_kernel<4><<<blocks, 256, 0, stream>>>(d_src, row_stride, frame_stride, w, h, n, mode, aligned, d_dst);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  return CB_OK;
+}
+
 int check_geometry(int w, int h, long long n, long long row_stride, long long frame_stride) {
   if (n < 0 || w <= 0 || h <= 0 || row_stride < w || (n > 1 && frame_stride < (long long)(h - 1) * row_stride + w)) {
     set_error("cb_hash_batch: invalid geometry n=%lld w=%d h=%d row_stride=%lld frame_stride=%lld", n, w, h, row_stride,
@@ -843,7 +914,7 @@ int check_geometry(int w, int h, long long n, long long row_stride, long long fr
 struct HostHashContext {
   std::mutex mu;
   HashWorkspace ws;
-  DevBuf<uint8_t> d_in;
+  DevBuf<uint8_t> d_in, d_gray;
   DevBuf<uint64_t> d_out;
   cudaStream_t stream = nullptr;
 };
@@ -955,6 +1026,105 @@ static int with_device_frames(const uint8_t* frames, int64_t n, int w, int h, in
   }
   return CB_OK;
 }
+
+// colour frames: copy in, convert to dense gray on the device, then `fn(ctx, d_gray, first frame, frames)`
+template <typename Fn>
+static int with_gray_frames(const char* who, const uint8_t* frames, int64_t n, int w, int h, int channels,
+                            int64_t row_stride, int64_t frame_stride, int gray_mode, Fn fn) {
+  if (channels != 3 && channels != 4) {  // grayscale(): anything else is qFatal (src/cvutil.cpp:1278-1280)
+    set_error("%s: unsupported channel count %d (8UC1, 8UC3 and 8UC4 are)", who, channels);
+    return CB_ERR_UNSUPPORTED;
+  }
+  if (gray_mode != CB_GRAY_Q14 && gray_mode != CB_GRAY_Q15) {
+    set_error("%s: unknown gray_mode %d", who, gray_mode);
+    return CB_ERR_INVALID;
+  }
+  const long long row_bytes = (long long)w * channels;
+  if (n < 0 || w <= 0 || h <= 0 || row_stride < row_bytes ||
+      (n > 1 && frame_stride < (long long)(h - 1) * row_stride + row_bytes) || (long long)w * h > 4096ll * 4096ll) {
+    set_error("%s: invalid geometry n=%lld w=%d h=%d channels=%d row_stride=%lld frame_stride=%lld", who, (long long)n, w,
+              h, channels, (long long)row_stride, (long long)frame_stride);
+    return CB_ERR_INVALID;
+  }
+  if (n == 0) return CB_OK;
+  if (!frames) {
+    set_error("%s: null pointer", who);
+    return CB_ERR_INVALID;
+  }
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  HostHashContext& ctx = g_ctx[current_device() & 15];
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  if (!ctx.stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  const long long frame_bytes = (long long)(h - 1) * row_stride + row_bytes;
+  const long long per_frame = n > 1 ? frame_stride : frame_bytes;
+  long long chunk = std::max(1ll, (256ll << 20) / std::max(1ll, per_frame));
+  chunk = std::min<long long>(chunk, n);
+  rc = ctx.d_in.reserve(size_t(chunk) * per_frame + 16);
+  if (rc == CB_OK) rc = ctx.d_gray.reserve(size_t(chunk) * w * h + 16);
+  if (rc != CB_OK) return rc;
+  for (long long i0 = 0; i0 < n; i0 += chunk) {
+    const long long m = std::min(chunk, n - i0);
+    CB_CUDA(cudaMemcpyAsync(ctx.d_in.p, frames + i0 * frame_stride, size_t(m - 1) * per_frame + frame_bytes,
+                            cudaMemcpyHostToDevice, ctx.stream));
+    rc = gray_device(ctx.d_in.p, m, w, h, channels, row_stride, per_frame, gray_mode, ctx.d_gray.p, ctx.stream);
+    if (rc == CB_OK) rc = fn(ctx, ctx.d_gray.p, i0, m);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  return CB_OK;
+}
+
+extern "C" {
+
+int cb_gray_batch(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride, int64_t frame_stride,
+                  int gray_mode, uint8_t* out) {
+  if (n > 0 && !out) {
+    set_error("cb_gray_batch: null output");
+    return CB_ERR_INVALID;
+  }
+  if (channels == 1) {  // 8UC1 passes through (:1275-1277): a dense copy, no device work needed
+    if (n < 0 || w <= 0 || h <= 0 || row_stride < w || (n > 1 && frame_stride < (long long)(h - 1) * row_stride + w) ||
+        (n > 0 && !frames)) {
+      set_error("cb_gray_batch: invalid argument");
+      return CB_ERR_INVALID;
+    }
+    for (int64_t f = 0; f < n; ++f)
+      for (int y = 0; y < h; ++y) memcpy(out + (f * h + y) * w, frames + f * frame_stride + y * row_stride, size_t(w));
+    return CB_OK;
+  }
+  const size_t px = size_t(w) * size_t(h);
+  return with_gray_frames("cb_gray_batch", frames, n, w, h, channels, row_stride, frame_stride, gray_mode,
+                          [&](HostHashContext& ctx, const uint8_t* d_gray, long long i0, long long m) -> int {
+                            CB_CUDA(cudaMemcpyAsync(out + size_t(i0) * px, d_gray, size_t(m) * px, cudaMemcpyDeviceToHost,
+                                                    ctx.stream));
+                            return CB_OK;
+                          });
+}
+
+int cb_hash_batch_color(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride,
+                        int64_t frame_stride, int gray_mode, uint64_t* out) {
+  if (channels == 1) return cb_hash_batch(frames, n, w, h, row_stride, frame_stride, out);
+  if (n > 0 && !out) {
+    set_error("cb_hash_batch_color: null output");
+    return CB_ERR_INVALID;
+  }
+  if (n >= 0 && w > 0 && h > 0 && (w < 32 || h < 32)) {
+    set_error("cb_hash_batch_color: %dx%d is smaller than 32x32; INTER_AREA up-scaling is not implemented", w, h);
+    return CB_ERR_UNSUPPORTED;
+  }
+  return with_gray_frames("cb_hash_batch_color", frames, n, w, h, channels, row_stride, frame_stride, gray_mode,
+                          [&](HostHashContext& ctx, const uint8_t* d_gray, long long i0, long long m) -> int {
+                            int rc = ctx.d_out.reserve(size_t(m));
+                            if (rc != CB_OK) return rc;
+                            rc = hash_frames_device(d_gray, m, w, h, w, (long long)w * h, ctx.d_out.p, &ctx.ws, ctx.stream);
+                            if (rc != CB_OK) return rc;
+                            CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+                            return CB_OK;
+                          });
+}
+
+}  // extern "C"
 
 extern "C" {
 

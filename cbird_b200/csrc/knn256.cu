@@ -443,6 +443,33 @@ int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows
   return CB_OK;
 }
 
+int cb_orb_radius_match_alloc(const uint8_t* train, int64_t n_train, const uint8_t* query, int64_t n_query,
+                              int max_distance, cb_pair** out, int64_t* n_out) {
+  if (!out || !n_out || n_train < 0 || n_query < 0 || (n_train && !train) || (n_query && !query) ||
+      n_train > 0xffffffffll || n_query > 0xffffffffll) {
+    set_error("cb_orb_radius_match_alloc: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  *out = nullptr;
+  *n_out = 0;
+  std::vector<cb_pair> hits;
+  if (n_train && n_query && max_distance >= 0) {
+    OrbIndex I;  // the reference builds a BFMatcher per template too (:134-139)
+    I.desc.assign(train, train + size_t(n_train) * 32);
+    const int thr = max_distance >= 256 ? 257 : max_distance + 1;  // d <= r  <=>  d < r + 1
+    int rc = I.knn(query, n_query, thr, 0, hits);
+    if (rc != CB_OK) return rc;
+  }
+  *n_out = int64_t(hits.size());
+  *out = static_cast<cb_pair*>(malloc(std::max<size_t>(1, hits.size()) * sizeof(cb_pair)));
+  if (!*out) {
+    set_error("out of host memory");
+    return CB_ERR_INVALID;
+  }
+  if (!hits.empty()) memcpy(*out, hits.data(), hits.size() * sizeof(cb_pair));
+  return CB_OK;
+}
+
 int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uint32_t needle_id, const cb_params* p,
                       cb_match* out, int64_t cap, int64_t* n_out) {
   if (!ix || !p || !n_out || n_rows < 0) {

@@ -24,6 +24,35 @@ def dct_hash64(gray: np.ndarray) -> int:
     return int(dct_hash64_batch(gray[None])[0])
 
 
+GRAY_Q14, GRAY_Q15 = 0, 1  # OpenCV 2.4.x (the reference's pinned build) / OpenCV 4.x fixed-point weights
+
+
+def _color_arg(frames):
+    if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] not in (1, 3, 4):
+        raise ValueError("frames must be uint8 with shape (n, h, w, channels) and 1, 3 or 4 channels")
+    return np.ascontiguousarray(frames)
+
+
+def grayscale(frames: np.ndarray, gray_mode: int = GRAY_Q15) -> np.ndarray:
+    """grayscale() of src/cvutil.cpp:1265-1283 for interleaved BGR / BGRA / gray frames (n, h, w, c) -> (n, h, w)."""
+    frames = _color_arg(frames)
+    n, h, w, c = frames.shape
+    out = np.zeros((n, h, w), np.uint8)
+    if n:
+        check(lib().cb_gray_batch(frames.ctypes.data, n, w, h, c, w * c, w * h * c, int(gray_mode), out.ctypes.data))
+    return out
+
+
+def dct_hash64_color(frames: np.ndarray, gray_mode: int = GRAY_Q15) -> np.ndarray:
+    """dctHash64 of decoded BGR / BGRA images (n, h, w, c): grayscale + hash in one device pass."""
+    frames = _color_arg(frames)
+    n, h, w, c = frames.shape
+    out = np.zeros(n, np.uint64)
+    if n:
+        check(lib().cb_hash_batch_color(frames.ctypes.data, n, w, h, c, w * c, w * h * c, int(gray_mode), out.ctypes.data))
+    return out
+
+
 def hash_tables():
     """(basis f32[9,32], zigzag i32[81]) as used by the kernel."""
     basis = np.zeros((9, 32), np.float32)

@@ -402,6 +402,17 @@ class CvFeaturesIndex:
         return _lib.take_array(ptr.value, n.value, _lib.PAIR_DTYPE)
 
 
+def radiusMatch(query, train, maxDistance) -> np.ndarray:
+    """cv::BFMatcher(NORM_HAMMING).radiusMatch as TemplateMatcher::match uses it (templatematcher.cpp:134-139,
+    217-218): all (queryIdx b, trainIdx a, dist) with dist <= maxDistance, sorted by (queryIdx, dist, trainIdx)."""
+    q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train, dtype=np.uint8).reshape(-1, 32)
+    ptr, n = C.c_void_p(), C.c_int64(0)
+    check(lib().cb_orb_radius_match_alloc(t.ctypes.data, len(t), q.ctypes.data, len(q), int(maxDistance), C.byref(ptr),
+                                          C.byref(n)))
+    return _lib.take_array(ptr.value, n.value, _lib.PAIR_DTYPE)
+
+
 def _video_set_file(self, media_id, path):
     """read <dataPath>/<mediaId>.vdx like insertHashes (dctvideoindex.cpp:64-72)."""
     check(self._L.cb_video_index_set_video_file(self._h, int(media_id), str(path).encode()))

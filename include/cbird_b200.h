@@ -113,6 +113,21 @@ int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_st
 /* device-resident variant on a caller stream (cudaStream_t passed as void*); asynchronous */
 int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                       uint64_t* d_out, void* stream);
+/* grayscale() (src/cvutil.cpp:1265-1283), the first step of dctHash64 for decoded images (src/scanner.cpp:862):
+ * cv::cvtColor(BGR2GRAY | BGRA2GRAY) of interleaved 8-bit pixels, B first.  channels: 1 (pass-through), 3, 4;
+ * anything else is CB_ERR_UNSUPPORTED (the reference qFatal()s).  Strides are in BYTES.  OpenCV's fixed-point
+ * weights changed between the release the reference pins and current ones, so the caller says which one the
+ * database was written with (a binding passes CV_MAJOR_VERSION < 3 ? CB_GRAY_Q14 : CB_GRAY_Q15):
+ *   CB_GRAY_Q14  OpenCV 2.4.x (cbird.pri:148 pins 2.4.13.7): (1868 B + 9617 G + 4899 R + 2^13) >> 14
+ *   CB_GRAY_Q15  OpenCV 4.x: (3735 B + 19235 G + 9798 R + 2^14) >> 15  (pinned against cv2 4.13, all 2^24 colours)
+ * cb_gray_batch writes dense n x h x w gray frames to host memory; cb_hash_batch_color is grayscale + dctHash64
+ * without the gray frames leaving the device. */
+enum { CB_GRAY_Q14 = 0, CB_GRAY_Q15 = 1 };
+int cb_gray_batch(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride,
+                  int64_t frame_stride, int gray_mode, uint8_t* out);
+int cb_hash_batch_color(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride,
+                        int64_t frame_stride, int gray_mode, uint64_t* out);
+
 /* autocrop(img, range) of every frame — src/cvutil.cpp:1285-1401 (de-letterbox before hashing video
  * frames, src/media.cpp:963,994): rects[4*i..] = {left, top, right, bottom}, right/bottom exclusive;
  * the full frame when no crop applies. */
@@ -303,6 +318,14 @@ int cb_orb_index_load_cache(cb_orb_index* ix, const char* cache_dir);
  * Building block for sharded search: per-shard lists are merged by (dist, row) and cut at k. */
 int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, int k, int threshold,
                            cb_pair** out, int64_t* n_out);
+/* TemplateMatcher's descriptor match (src/templatematcher.cpp:134-139,217-218):
+ * cv::BFMatcher(NORM_HAMMING).radiusMatch(query, train, maxDistance) -- every (query row, train row) with
+ * distance <= max_distance (OpenCV's radius is inclusive, unlike the strict `<` of find()).
+ * cb_pair{a = trainIdx, b = queryIdx, dist}, sorted by (queryIdx, dist, trainIdx).  Stateless: both
+ * descriptor sets (rows x 32 bytes, host memory) are given per call, as the reference rebuilds its
+ * matcher per template. */
+int cb_orb_radius_match_alloc(const uint8_t* train, int64_t n_train, const uint8_t* query, int64_t n_query,
+                              int max_distance, cb_pair** out, int64_t* n_out);
 
 #ifdef __cplusplus
 }

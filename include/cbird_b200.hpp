@@ -289,4 +289,24 @@ inline uint64_t dctHash64(const uint8_t* gray, int cols, int rows, int64_t step)
   return ok(cb_hash_batch(gray, 1, cols, rows, step, 0, &h), "dctHash64") ? h : 0;
 }
 
+/// dctHash64(cvImg) for decoded 8UC3 (BGR) / 8UC4 (BGRA) / 8UC1 images: grayscale() (:1265-1283) + hash.
+/// grayMode: CB_GRAY_Q14 for a cbird built against OpenCV 2.4.x (the pinned 2.4.13.7), CB_GRAY_Q15 for 4.x.
+inline uint64_t dctHash64(const uint8_t* pixels, int cols, int rows, int channels, int64_t step, int grayMode) {
+  uint64_t h = 0;
+  return ok(cb_hash_batch_color(pixels, 1, cols, rows, channels, step, 0, grayMode, &h), "dctHash64") ? h : 0;
+}
+
+/// cv::BFMatcher(NORM_HAMMING).radiusMatch(query, train, maxDistance) as TemplateMatcher::match uses it
+/// (src/templatematcher.cpp:134-139,217-218): {a = trainIdx, b = queryIdx, dist <= maxDistance}, sorted by
+/// (queryIdx, dist, trainIdx); empty on failure.
+inline std::vector<cb_pair> radiusMatch(const uint8_t* query, int64_t nQuery, const uint8_t* train, int64_t nTrain,
+                                        int maxDistance) {
+  cb_pair* p = nullptr;
+  int64_t n = 0;
+  std::vector<cb_pair> out;
+  if (ok(cb_orb_radius_match_alloc(train, nTrain, query, nQuery, maxDistance, &p, &n), "radiusMatch")) out.assign(p, p + n);
+  cb_free(p);
+  return out;
+}
+
 }  // namespace cbird_b200

@@ -297,6 +297,23 @@ double orc_dct_hash64_batch(const uint8_t* frames, long long n, int w, int h, in
   return std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
 
+// grayscale() — src/cvutil.cpp:1265-1283: cv::cvtColor(BGR2GRAY / BGRA2GRAY) of interleaved 8-bit pixels (B first),
+// 8UC1 passes through.  OpenCV's RGB2Gray<uchar> is fixed point; q15 = 0 restates OpenCV 2.4.x (the pinned
+// 2.4.13.7: R2Y=4899, G2Y=9617, B2Y=1868, yuv_shift=14 -- parity unpinned, no 2.4 build here), q15 = 1 OpenCV 4.x
+// (RY15=9798, GY15=19235, BY15=3735, shift 15 -- pinned against cv2 4.13, tests/golden/gray_cv2.npz).
+// Returns 0, or -1 for an unsupported channel count (the reference qFatal()s).
+int orc_grayscale(const uint8_t* src, int w, int h, int channels, long long stride, int q15, uint8_t* dst) {
+  if (channels != 1 && channels != 3 && channels != 4) return -1;
+  const int cb = q15 ? 3735 : 1868, cg = q15 ? 19235 : 9617, cr = q15 ? 9798 : 4899, shift = q15 ? 15 : 14;
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* s = src + (size_t)y * stride;
+    uint8_t* d = dst + (size_t)y * w;
+    for (int x = 0; x < w; ++x, s += channels)
+      d[x] = channels == 1 ? s[0] : uint8_t((s[0] * cb + s[1] * cg + s[2] * cr + (1 << (shift - 1))) >> shift);
+  }
+  return 0;
+}
+
 // autocrop(cvImg, range) — src/cvutil.cpp:1285-1401, loop for loop. rect = {left, top, right, bottom}
 // (right/bottom exclusive); the full frame when the final sanity checks refuse the crop.
 void orc_autocrop(const uint8_t* img, int cols, int rows, int stride, int range, int* rect) {
@@ -887,6 +904,32 @@ void orc_knn256(const uint8_t* db, long long n_db, const uint8_t* q, long long n
       out_dist[i * k + j] = j < int(kk) ? all[j].first : 0;
     }
   }
+}
+
+// cv::BFMatcher(NORM_HAMMING).radiusMatch as src/templatematcher.cpp:134-139,217-218 calls it: every pair
+// with distance <= max_distance (inclusive), per query ordered by (dist, trainIdx).  out = (query, train,
+// dist) triples; returns the total count (only the first `cap` are written).
+long long orc_radius_match256(const uint8_t* train, long long n_train, const uint8_t* query, long long n_query,
+                              int max_distance, int* out, long long cap) {
+  long long n = 0;
+  std::vector<std::pair<int, int>> row;
+  for (long long i = 0; i < n_query; ++i) {
+    row.clear();
+    for (long long r = 0; r < n_train; ++r) {
+      const int d = hamm256(query + i * 32, train + r * 32);
+      if (d <= max_distance) row.push_back({d, int(r)});
+    }
+    std::sort(row.begin(), row.end());
+    for (auto& e : row) {
+      if (n < cap) {
+        out[n * 3 + 0] = int(i);
+        out[n * 3 + 1] = e.second;
+        out[n * 3 + 2] = e.first;
+      }
+      ++n;
+    }
+  }
+  return n;
 }
 
 // find() :438-604. needle descriptors given explicitly, or (desc==NULL) taken from the index by

@@ -9,6 +9,9 @@
 * knn256_cv2.npz  : cv2.BFMatcher(NORM_HAMMING).knnMatch(k=10) on seeded 256-bit descriptors
                     (the exact-kNN pin for the CvFeaturesIndex path; the reference's own flann LSH is
                     randomised per build and cannot be pinned).
+* radius_match_cv2.npz : cv2.BFMatcher(NORM_HAMMING, crossCheck).radiusMatch as TemplateMatcher calls it,
+                    rows (queryIdx, trainIdx, dist) sorted by (queryIdx, dist, trainIdx).
+* gray_cv2.npz    : cv2.cvtColor(BGR2GRAY/BGRA2GRAY) of seeded colour images and the dctHash64 of the result.
 The script needs cv2 and (for zigzag) /root/reference; the fixtures it writes need neither.
 """
 import os
@@ -83,6 +86,38 @@ def main():
     idx = np.array([[x.trainIdx for x in row] for row in m], dtype=np.int32)
     dist = np.array([[int(x.distance) for x in row] for row in m], dtype=np.int32)
     np.savez_compressed(os.path.join(OUT, "knn256_cv2.npz"), db=db, q=q, idx=idx, dist=dist)
+    # TemplateMatcher's radiusMatch (templatematcher.cpp:134-139,217-218): template = train, candidate = query.
+    # A separate rng so the older fixtures stay byte-identical.
+    r2 = np.random.default_rng(20261018)
+    train = r2.integers(0, 256, size=(400, 32), dtype=np.uint8)
+    query = r2.integers(0, 256, size=(900, 32), dtype=np.uint8)
+    for i in range(0, 900, 3):  # candidate features that are noisy copies of template features
+        src = train[r2.integers(0, 400)].copy()
+        for b in r2.integers(0, 256, size=r2.integers(0, 70)):
+            src[b >> 3] ^= np.uint8(1 << (b & 7))
+        query[i] = src
+    rm = {"train": train, "query": query}
+    bf2 = cv2.BFMatcher(cv2.NORM_HAMMING, True)  # crossCheck as the reference constructs it
+    for radius in (1, 25, 60, 100):  # OpenCV asserts maxDistance > 0
+        res = bf2.radiusMatch(query, train, radius)
+        rows = sorted((x.queryIdx, int(x.distance), x.trainIdx) for row in res for x in row)
+        rm["r%d" % radius] = np.array([(a, c, b) for a, b, c in rows], dtype=np.int32).reshape(-1, 3)
+    np.savez_compressed(os.path.join(OUT, "radius_match_cv2.npz"), **rm)
+    # grayscale() + dctHash64 of decoded colour images (src/cvutil.cpp:1265-1283 then :435-545), cv2 4.13
+    r3 = np.random.default_rng(20261019)
+    gd = {}
+    for key, (w, h, c, n) in {"bgr_64x48": (64, 48, 3, 6), "bgra_100x75": (100, 75, 4, 6), "bgr_161x120": (161, 120, 3, 3),
+                              "bgr_480x270": (480, 270, 3, 1)}.items():
+        planes = [natural(r3, n, w, h) for _ in range(c)]
+        img = np.stack(planes, axis=3)
+        gray = np.stack([cv2.cvtColor(im, cv2.COLOR_BGR2GRAY if c == 3 else cv2.COLOR_BGRA2GRAY) for im in img])
+        gd["img_" + key] = img
+        gd["gray_" + key] = gray
+        gd["hash_" + key] = np.array([dc.hash_from_tile32_cv2(dc.preprocess32_cv2(g)) for g in gray], dtype=np.uint64)
+    noise = r3.integers(0, 256, size=(2, 37, 53, 3), dtype=np.uint8)
+    gd["img_noise"] = noise
+    gd["gray_noise"] = np.stack([cv2.cvtColor(im, cv2.COLOR_BGR2GRAY) for im in noise])
+    np.savez_compressed(os.path.join(OUT, "gray_cv2.npz"), **gd)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -84,6 +84,8 @@ def oracle():
         L.orc_orb_count.argtypes = [C.c_void_p]
         L.orc_orb_count.restype = C.c_longlong
         L.orc_knn256.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, _i32p, _i32p]
+        L.orc_radius_match256.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, _i32p, C.c_longlong]
+        L.orc_radius_match256.restype = C.c_longlong
         L.orc_orb_find.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint32, C.c_int, C.c_void_p, C.c_longlong]
         L.orc_orb_find.restype = C.c_longlong
         _oracle = L
@@ -269,6 +271,19 @@ class OracleVideoIndex:
         return idx[:n], fr[:n], d[:n]
 
 
+def grayscale(frames, q15=True):
+    """grayscale() of (n, h, w, c) interleaved BGR/BGRA/gray frames -> (n, h, w)."""
+    f = np.ascontiguousarray(frames, np.uint8)
+    n, h, w, c = f.shape
+    out = np.zeros((n, h, w), np.uint8)
+    L = oracle()
+    L.orc_grayscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
+    for i in range(n):
+        if L.orc_grayscale(f[i].ctypes.data, w, h, c, w * c, 1 if q15 else 0, out[i].ctypes.data) != 0:
+            raise ValueError("unsupported channel count %d" % c)
+    return out
+
+
 def knn256(db, q, k=10):
     db = np.ascontiguousarray(db, np.uint8)
     q = np.ascontiguousarray(q, np.uint8)
@@ -276,6 +291,19 @@ def knn256(db, q, k=10):
     dist = np.zeros(len(q) * k, np.int32)
     oracle().orc_knn256(db.ctypes.data, len(db), q.ctypes.data, len(q), k, idx, dist)
     return idx.reshape(len(q), k), dist.reshape(len(q), k)
+
+
+def radius_match256(train, query, max_distance):
+    """(queryIdx, trainIdx, dist) rows with dist <= max_distance, ordered by (queryIdx, dist, trainIdx)."""
+    t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap * 3, np.int32)
+        n = oracle().orc_radius_match256(t.ctypes.data, len(t), q.ctypes.data, len(q), int(max_distance), out, cap)
+        if n <= cap:
+            return out[: n * 3].reshape(-1, 3)
+        cap = int(n)
 
 
 class OracleOrbIndex:

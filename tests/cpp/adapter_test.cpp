@@ -135,6 +135,20 @@ int main() {
   // dctHash64: constant frame -> 1 (src/cvutil.cpp:542)
   std::vector<uint8_t> flat(64 * 64, 90);
   assert(dctHash64(flat.data(), 64, 64, 64) == 1);
+  // a gray BGR image hashes like its gray plane (all three weights sum to 1 in both fixed-point variants)
+  std::vector<uint8_t> gray(64 * 64), bgr(64 * 64 * 3);
+  for (int i = 0; i < 64 * 64; ++i) {
+    gray[i] = uint8_t((i * 7 + (i >> 6) * 13) & 255);
+    bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = gray[i];
+  }
+  const uint64_t hg = dctHash64(gray.data(), 64, 64, 64);
+  assert(hg != 0 && dctHash64(bgr.data(), 64, 64, 3, 64 * 3, CB_GRAY_Q15) == hg);
+  assert(dctHash64(bgr.data(), 64, 64, 3, 64 * 3, CB_GRAY_Q14) == hg);
+  // TemplateMatcher's radius match: media[7]'s descriptors against themselves at radius 0 -> the diagonal
+  const std::vector<uint8_t>& d7 = media[7].descriptors;
+  std::vector<cb_pair> rm = radiusMatch(d7.data(), int64_t(d7.size() / 32), d7.data(), int64_t(d7.size() / 32), 0);
+  assert(rm.size() >= d7.size() / 32);
+  for (const cb_pair& pr : rm) assert(pr.dist == 0);
   printf("OK %ld matches, %ld grouped, %d warnings\n", total, grouped, g_warnings);
   return 0;
 }

@@ -83,3 +83,40 @@ def test_full_size_properties(cb):
     assert np.all(a != 0) and np.all((a & np.uint64(1)) == 0)
     perm = np.random.default_rng(1).permutation(len(fr))[:4096]
     assert np.array_equal(cb.dct_hash64_batch(fr[perm]), a[perm])  # batch position does not matter
+
+
+def test_colour_frames_gray_and_hash(cb, po):
+    # grayscale() + dctHash64 for decoded BGR / BGRA images (src/cvutil.cpp:1265-1283, src/scanner.cpp:862)
+    g = np.load(os.path.join(GOLD, "gray_cv2.npz"))
+    for key in ["bgr_64x48", "bgra_100x75", "bgr_161x120", "bgr_480x270", "noise"]:
+        img = g["img_" + key]
+        assert np.array_equal(cb.grayscale(img), g["gray_" + key]), key              # == cv2 4.13
+        assert np.array_equal(cb.grayscale(img, cb.GRAY_Q14), po.grayscale(img, q15=False)), key
+        if key != "noise":
+            want, _ = po.dct_hash64_batch(g["gray_" + key])
+            assert np.array_equal(cb.dct_hash64_color(img), want), key                # fused path / global path
+            flips = sum(bin(int(a) ^ int(b)).count("1") for a, b in zip(want, g["hash_" + key]))
+            assert flips <= 1
+            w14, _ = po.dct_hash64_batch(po.grayscale(img, q15=False))
+            assert np.array_equal(cb.dct_hash64_color(img, cb.GRAY_Q14), w14), key
+    # ragged widths (scalar tail + unaligned rows), 1-channel pass-through, larger batch
+    rng = np.random.default_rng(4)
+    for w, h, c, n in [(33, 32, 3, 5), (35, 41, 4, 3), (130, 97, 3, 70), (32, 32, 3, 1000), (1, 1, 3, 2)]:
+        img = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+        assert np.array_equal(cb.grayscale(img), po.grayscale(img)), (w, h, c)
+        if w >= 32 and h >= 32:
+            want, _ = po.dct_hash64_batch(po.grayscale(img))
+            assert np.array_equal(cb.dct_hash64_color(img), want), (w, h, c)
+    mono = rng.integers(0, 256, size=(4, 40, 48, 1), dtype=np.uint8)
+    assert np.array_equal(cb.grayscale(mono), mono[..., 0])
+    assert np.array_equal(cb.dct_hash64_color(mono), cb.dct_hash64_batch(mono[..., 0]))
+    assert len(cb.grayscale(np.zeros((0, 8, 8, 3), np.uint8))) == 0
+    with pytest.raises(ValueError):
+        cb.grayscale(np.zeros((1, 8, 8, 2), np.uint8))
+    with pytest.raises(cb.CbirdError):
+        cb.dct_hash64_color(np.zeros((1, 16, 16, 3), np.uint8))  # < 32x32: unsupported, loudly
+    # the C ABI itself refuses other channel counts like the reference's qFatal
+    buf = np.zeros((1, 8, 8, 2), np.uint8)
+    out = np.zeros((1, 8, 8), np.uint8)
+    assert cb.lib().cb_gray_batch(buf.ctypes.data, 1, 8, 8, 2, 16, 128, 1, out.ctypes.data) == -5
+    assert b"channel" in cb.lib().cb_last_error()

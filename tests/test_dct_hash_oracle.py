@@ -82,3 +82,30 @@ def test_degenerate_frames(po):
     assert po.dct_hash64(np.full((64, 64), 200, np.uint8)) == 1
     with pytest.raises(ValueError):
         po.preprocess32(np.zeros((16, 64), np.uint8))  # up-scaling path not restated
+
+
+GRAY_KEYS = ["bgr_64x48", "bgra_100x75", "bgr_161x120", "bgr_480x270"]
+
+
+def test_grayscale_vs_cv2(po):
+    # grayscale() (src/cvutil.cpp:1265-1283): OpenCV 4.x fixed point is pinned byte for byte; the 2.4.x weights the
+    # reference's pinned build used differ by at most one gray level
+    g = np.load(os.path.join(GOLD, "gray_cv2.npz"))
+    for key in GRAY_KEYS + ["noise"]:
+        img = g["img_" + key]
+        assert np.array_equal(po.grayscale(img, q15=True), g["gray_" + key]), key
+        d = po.grayscale(img, q15=False).astype(np.int32) - g["gray_" + key].astype(np.int32)
+        assert np.abs(d).max() <= 1 and (d != 0).mean() < 0.01, key
+    mono = g["gray_noise"][..., None]
+    assert np.array_equal(po.grayscale(mono), g["gray_noise"])  # 8UC1 passes through
+    with pytest.raises(ValueError):
+        po.grayscale(np.zeros((1, 4, 4, 2), np.uint8))
+
+
+def test_colour_hash_vs_cv2(po):
+    g = np.load(os.path.join(GOLD, "gray_cv2.npz"))
+    bits = 0
+    for key in GRAY_KEYS:
+        got, _ = po.dct_hash64_batch(po.grayscale(g["img_" + key]))
+        bits += sum(bin(int(a) ^ int(b)).count("1") for a, b in zip(got, g["hash_" + key]))
+    assert bits <= 1  # same near-tie allowance as test_hash_vs_cv2

@@ -192,3 +192,31 @@ def test_cache_files_round_trip_and_layout(cb, po, tmp_path):
     assert g2.findIndexData(m) and np.array_equal(m.descriptors, descs[7])  # removed media keep their rows
     with pytest.raises(cb.CbirdError):
         cb.CvFeaturesIndex().loadCache(tmp_path / "nowhere")
+
+
+def test_radius_match_equals_bfmatcher_golden(cb, po):
+    # TemplateMatcher's radiusMatch (src/templatematcher.cpp:134-139,217-218): distance <= radius, inclusive
+    g = np.load(os.path.join(GOLD, "radius_match_cv2.npz"))
+    train, query = g["train"], g["query"]
+
+    def triples(p):
+        return np.stack([p["b"], p["a"], p["dist"]], axis=1).astype(np.int32).reshape(-1, 3)
+
+    for r in (1, 25, 60, 100):
+        assert np.array_equal(triples(cb.radiusMatch(query, train, r)), g["r%d" % r]), r
+    # OpenCV asserts radius > 0; the library answers radius 0 (exact duplicates) and a radius covering everything
+    q0 = np.concatenate([train[5:7], query[:3]])
+    assert np.array_equal(triples(cb.radiusMatch(q0, train, 0)), po.radius_match256(train, q0, 0))
+    assert len(cb.radiusMatch(q0, train, 0)) == 2
+    full = cb.radiusMatch(query[:40], train, 256)
+    assert len(full) == 40 * len(train)
+    assert np.array_equal(triples(full), po.radius_match256(train, query[:40], 256))
+    assert len(cb.radiusMatch(query, train, -1)) == 0
+    assert len(cb.radiusMatch(query[:0], train, 25)) == 0 and len(cb.radiusMatch(query, train[:0], 25)) == 0
+    # a candidate-sized query against a large "template": folds 2/4/8 still exact
+    rng = np.random.default_rng(8)
+    big = rng.integers(0, 256, size=(30000, 32), dtype=np.uint8)
+    qs = big[rng.integers(0, len(big), 500)].copy()
+    qs[:, :8] ^= rng.integers(0, 256, size=(500, 8), dtype=np.uint8)
+    for r in (30, 64, 110):
+        assert np.array_equal(triples(cb.radiusMatch(qs, big, r)), po.radius_match256(big, qs, r)), r

@@ -44,3 +44,13 @@ def test_find_scoring(po):
     assert int(res[0]["mediaId"]) == 20 and int(res[0]["score"]) == 0
     ox.add([40], [m1])
     assert ox.count() == 13 and 40 in {int(r["mediaId"]) for r in ox.find(base, 0, odt=25)}
+
+
+def test_radius_match_equals_bfmatcher(po):
+    # TemplateMatcher's descriptor match (src/templatematcher.cpp:134-139,217-218): inclusive radius
+    g = np.load(os.path.join(GOLD, "radius_match_cv2.npz"))
+    for r in (1, 25, 60, 100):
+        got = po.radius_match256(g["train"], g["query"], r)
+        assert np.array_equal(got, g["r%d" % r]), r
+    assert len(po.radius_match256(g["train"][:0], g["query"], 25)) == 0
+    assert len(po.radius_match256(g["train"], g["query"][:0], 25)) == 0
