@@ -12,6 +12,7 @@
 // by a merge sort + head flags (first-wins ties == lowest row position); only the tiny reduced list
 // goes back to the host, where the integer range scoring of :595-654 runs unchanged.
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
@@ -89,6 +90,68 @@ __global__ void video_heads_kernel(const VHit* __restrict__ hits, unsigned long 
   flags[i] = head ? 1 : 0;
 }
 
+// ---- bucket layout build on the device (DctVideoIndex::buildTree + insertHashes, dctvideoindex.cpp:61-170) ----
+struct TableDesc {  // one .vdx table inside the concatenated raw rows
+  uint32_t start;   // first raw row
+  uint32_t vidx;    // index into _mediaId
+  uint32_t media;
+  int32_t lastFrame;
+};
+
+__device__ __forceinline__ uint32_t table_of_row(const TableDesc* __restrict__ tabs, uint32_t n_tabs, uint32_t row) {
+  uint32_t lo = 0, hi = n_tabs;  // last table with start <= row
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (tabs[mid].start <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// sort key of every raw row: its radix bucket (radix.h:135-141), or `drop_key` (sorts last) when insertHashes
+// filters the row out (:89 too few/many set bits, :93-95 vtrim at both ends)
+__global__ void video_row_keys_kernel(const uint64_t* __restrict__ hash, const int32_t* __restrict__ frame, uint32_t n_raw,
+                                      const TableDesc* __restrict__ tabs, uint32_t n_tabs, int skip, uint32_t mask,
+                                      uint32_t drop_key, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_raw) return;
+  const uint64_t h = hash[i];
+  const int ones = __popcll(h);
+  bool keep = !(ones < 5 || 64 - ones < 5);
+  if (keep && skip) {
+    const int last = tabs[table_of_row(tabs, n_tabs, i)].lastFrame, f = frame[i];
+    if (last / 2 > skip && (f < skip || f > last - skip)) keep = false;
+  }
+  key[i] = keep ? uint32_t((h >> 1) & mask) : drop_key;
+  val[i] = i;
+}
+
+__global__ void video_row_gather_kernel(const uint32_t* __restrict__ order, uint32_t n_raw, const uint64_t* __restrict__ hash,
+                                        const int32_t* __restrict__ frame, const TableDesc* __restrict__ tabs,
+                                        uint32_t n_tabs, uint64_t* __restrict__ row_hash, uint32_t* __restrict__ row_media,
+                                        int32_t* __restrict__ row_frame, uint32_t* __restrict__ row_vidx) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_raw) return;
+  const uint32_t r = order[pos];
+  const TableDesc t = tabs[table_of_row(tabs, n_tabs, r)];
+  row_hash[pos] = hash[r];
+  row_media[pos] = t.media;
+  row_frame[pos] = frame[r];
+  row_vidx[pos] = t.vidx;
+}
+
+// bucket_ofs[b] = first sorted position whose key is >= b, for b in [0, nb]; ofs[nb] = rows kept
+__global__ void video_bucket_ofs_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n_raw, uint32_t nb,
+                                        uint32_t* __restrict__ ofs) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  uint32_t lo = 0, hi = n_raw;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (sorted_key[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  ofs[b] = lo;
+}
+
 struct Table {
   std::vector<int32_t> frames;
   std::vector<uint64_t> hashes;
@@ -153,57 +216,76 @@ struct VideoIndex {
     int rc = init_device();
     if (rc != CB_OK) return rc;
     CB_CUDA(cudaSetDevice(device));
-    const uint64_t mask = (1ull << radix) - 1;
-    const size_t nb = size_t(1) << radix;
-    std::vector<uint64_t> hashes;
-    std::vector<uint32_t> vidx;
-    std::vector<int32_t> frames;
+    const uint32_t mask = (1u << radix) - 1;
+    const uint32_t nb = 1u << radix;
+    // concatenate the raw tables (memcpy speed); filtering, bucketing and the stable sort run on the device
+    std::vector<TableDesc> tabs;
+    size_t n_raw = 0;
     for (size_t i = 0; i < mediaId.size(); ++i) {
       auto it = tables.find(mediaId[i]);
       if (it == tables.end()) continue;  // "index file missing" :65-68
       const Table& t = it->second;
       if (t.frames.empty()) continue;
-      const int lastFrame = t.frames.back();
-      for (size_t j = 0; j < t.hashes.size(); ++j) {
-        const uint64_t h = t.hashes[j];
-        const int ones = __builtin_popcountll(h);
-        if (ones < 5 || 64 - ones < 5) continue;  // :89
-        const int frame = t.frames[j];
-        if (skip && lastFrame / 2 > skip && (frame < skip || frame > lastFrame - skip)) continue;  // :93-95
-        hashes.push_back(h);
-        vidx.push_back(uint32_t(i));
-        frames.push_back(frame);
-      }
+      tabs.push_back(TableDesc{uint32_t(n_raw), uint32_t(i), mediaId[i], t.frames.back()});
+      n_raw += t.hashes.size();
     }
-    n_rows = hashes.size();
-    if (n_rows > 0xFFFFF000ull) {
-      set_error("video index: %zu frame hashes exceed the 32-bit row index", n_rows);
+    if (n_raw > 0xFFFFF000ull) {
+      set_error("video index: %zu frame hashes exceed the 32-bit row index", n_raw);
       return CB_ERR_UNSUPPORTED;
     }
-    // stable counting sort by bucket (radix.h:135-155 keeps insertion order inside a bucket)
-    bucket_ofs.assign(nb + 1, 0);
-    for (size_t r = 0; r < n_rows; ++r) bucket_ofs[((hashes[r] >> 1) & mask) + 1]++;
-    for (size_t b = 0; b < nb; ++b) bucket_ofs[b + 1] += bucket_ofs[b];
-    std::vector<uint32_t> cursor(bucket_ofs.begin(), bucket_ofs.end() - 1);
-    std::vector<uint64_t> s_hash(n_rows);
-    std::vector<uint32_t> s_media(n_rows);
-    std::vector<int32_t> s_frame(n_rows);
-    h_row_vidx.resize(n_rows);
-    for (size_t r = 0; r < n_rows; ++r) {
-      const uint32_t pos = cursor[(hashes[r] >> 1) & mask]++;
-      s_hash[pos] = hashes[r];
-      s_media[pos] = mediaId[vidx[r]];
-      s_frame[pos] = frames[r];
-      h_row_vidx[pos] = vidx[r];
-    }
-    if ((rc = d_row_hash.reserve(n_rows + 2)) != CB_OK || (rc = d_row_media.reserve(n_rows + 2)) != CB_OK ||
-        (rc = d_row_frame.reserve(n_rows + 2)) != CB_OK)
-      return rc;
-    if (n_rows) {
-      CB_CUDA(cudaMemcpyAsync(d_row_hash.p, s_hash.data(), n_rows * 8, cudaMemcpyHostToDevice, stream));
-      CB_CUDA(cudaMemcpyAsync(d_row_media.p, s_media.data(), n_rows * 4, cudaMemcpyHostToDevice, stream));
-      CB_CUDA(cudaMemcpyAsync(d_row_frame.p, s_frame.data(), n_rows * 4, cudaMemcpyHostToDevice, stream));
+    bucket_ofs.assign(size_t(nb) + 1, 0);
+    h_row_vidx.clear();
+    n_rows = 0;
+    if (n_raw) {
+      std::vector<uint64_t> raw_hash(n_raw);
+      std::vector<int32_t> raw_frame(n_raw);
+      for (const TableDesc& d : tabs) {
+        const Table& t = tables.find(d.media)->second;
+        memcpy(raw_hash.data() + d.start, t.hashes.data(), t.hashes.size() * 8);
+        memcpy(raw_frame.data() + d.start, t.frames.data(), t.hashes.size() * 4);
+      }
+      DevBuf<uint64_t> d_raw_hash;
+      DevBuf<int32_t> d_raw_frame;
+      DevBuf<TableDesc> d_tabs;
+      DevBuf<uint32_t> d_key, d_val, d_key2, d_val2, d_vidx, d_ofs;
+      if ((rc = d_raw_hash.reserve(n_raw)) != CB_OK || (rc = d_raw_frame.reserve(n_raw)) != CB_OK ||
+          (rc = d_tabs.reserve(tabs.size())) != CB_OK || (rc = d_key.reserve(n_raw)) != CB_OK ||
+          (rc = d_val.reserve(n_raw)) != CB_OK || (rc = d_key2.reserve(n_raw)) != CB_OK ||
+          (rc = d_val2.reserve(n_raw)) != CB_OK || (rc = d_vidx.reserve(n_raw)) != CB_OK ||
+          (rc = d_ofs.reserve(size_t(nb) + 1)) != CB_OK || (rc = d_row_hash.reserve(n_raw + 2)) != CB_OK ||
+          (rc = d_row_media.reserve(n_raw + 2)) != CB_OK || (rc = d_row_frame.reserve(n_raw + 2)) != CB_OK)
+        return rc;
+      CB_CUDA(cudaMemcpyAsync(d_raw_hash.p, raw_hash.data(), n_raw * 8, cudaMemcpyHostToDevice, stream));
+      CB_CUDA(cudaMemcpyAsync(d_raw_frame.p, raw_frame.data(), n_raw * 4, cudaMemcpyHostToDevice, stream));
+      CB_CUDA(cudaMemcpyAsync(d_tabs.p, tabs.data(), tabs.size() * sizeof(TableDesc), cudaMemcpyHostToDevice, stream));
+      const unsigned blocks = unsigned((n_raw + 255) / 256);
+      video_row_keys_kernel<<<blocks, 256, 0, stream>>>(d_raw_hash.p, d_raw_frame.p, uint32_t(n_raw), d_tabs.p,
+                                                        uint32_t(tabs.size()), skip, mask, nb, d_key.p, d_val.p);
+      CB_CUDA(cudaGetLastError());
+      // LSD radix sort is stable: a bucket keeps insertion order (ascending video index, then .vdx order),
+      // which the first-wins tie rule of findVideo depends on (radix.h:143-155)
+      size_t tb = 0;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_val.p, d_val2.p, static_cast<long long>(n_raw), 0, radix + 1,
+                                              stream));
+      rc = d_temp.reserve(tb + 16);
+      if (rc != CB_OK) return rc;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, tb, d_key.p, d_key2.p, d_val.p, d_val2.p, static_cast<long long>(n_raw), 0, radix + 1,
+                                              stream));
+      video_row_gather_kernel<<<blocks, 256, 0, stream>>>(d_val2.p, uint32_t(n_raw), d_raw_hash.p, d_raw_frame.p, d_tabs.p,
+                                                          uint32_t(tabs.size()), d_row_hash.p, d_row_media.p, d_row_frame.p,
+                                                          d_vidx.p);
+      CB_CUDA(cudaGetLastError());
+      video_bucket_ofs_kernel<<<(nb + 256) / 256, 256, 0, stream>>>(d_key2.p, uint32_t(n_raw), nb, d_ofs.p);
+      CB_CUDA(cudaGetLastError());
+      counters().launches += 3;
+      CB_CUDA(cudaMemcpyAsync(bucket_ofs.data(), d_ofs.p, (size_t(nb) + 1) * 4, cudaMemcpyDeviceToHost, stream));
       CB_CUDA(cudaStreamSynchronize(stream));
+      n_rows = bucket_ofs[nb];
+      h_row_vidx.resize(n_rows);
+      if (n_rows) {
+        CB_CUDA(cudaMemcpyAsync(h_row_vidx.data(), d_vidx.p, n_rows * 4, cudaMemcpyDeviceToHost, stream));
+        CB_CUDA(cudaStreamSynchronize(stream));
+      }
     }
     built = true;
     built_radix = radix;
