@@ -14,6 +14,8 @@
 // (std::sort :103-108) and (distance, index, hash) here.  Divergence: leaves with fewer than 4
 // hashes hit an unsigned underflow in the reference's unrolled loop (`count - 4`, :264); this build
 // simply searches them.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <map>
 #include <unordered_set>
@@ -25,6 +27,27 @@ namespace cbird {
 namespace {
 constexpr uint32_t kLeafCapacity = 64 * 1024 / 8;  // CLUSTER_SIZE / sizeof(hash_t), hammingtree.h:57,377
 constexpr int kMaxSplitDepth = 30;                  // `1 << bit` is an int shift in the reference (:236,:246)
+constexpr int kKeyBits = kMaxSplitDepth + 1;
+
+// Pre-order position of a hash in the trie: bit 0 decides first, the set child ("left") comes before the
+// clear child, so the key is the complement of the low 31 bits with bit 0 most significant.
+__global__ void trie_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, uint32_t* __restrict__ key,
+                                 uint32_t* __restrict__ val) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = __brev(~uint32_t(hash[i])) >> 1;
+  val[i] = i;
+}
+
+__global__ void trie_gather_kernel(const uint32_t* __restrict__ order, uint32_t n, const uint64_t* __restrict__ hash,
+                                   const uint32_t* __restrict__ index, uint64_t* __restrict__ s_hash,
+                                   uint32_t* __restrict__ s_index) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = order[i];
+  s_hash[i] = hash[r];
+  s_index[i] = index[r];
+}
 }  // namespace
 
 struct HammingTree {
@@ -59,30 +82,32 @@ struct HammingTree {
     if (stream) cudaStreamDestroy(stream);
   }
 
-  int build_node(std::vector<uint32_t>& rows, int depth) {
+  // node over sorted rows [lo, hi) that share their `depth` low bits: internal iff more than 8192 hashes
+  // reached it (:377-405); the children are the runs with bit `depth` set / clear (a binary search, the rows
+  // are sorted by trie position)
+  int build_node(const std::vector<uint32_t>& keys, uint32_t lo, uint32_t hi, int depth) {
     const int id = int(nodes.size());
     nodes.push_back(Node());
     max_height = std::max(max_height, depth);
-    if (rows.size() > kLeafCapacity && depth <= kMaxSplitDepth) {
-      std::vector<uint32_t> set_rows, clear_rows;
-      for (uint32_t r : rows) ((hash[r] >> depth) & 1 ? set_rows : clear_rows).push_back(r);
-      std::vector<uint32_t>().swap(rows);
+    if (hi - lo > kLeafCapacity && depth <= kMaxSplitDepth) {
+      const uint32_t bit = 1u << (kKeyBits - 1 - depth);  // key bit of hash bit `depth`; 0 there = hash bit set
+      const uint32_t split = uint32_t(std::partition_point(keys.begin() + lo, keys.begin() + hi,
+                                                           [bit](uint32_t k) { return !(k & bit); }) - keys.begin());
       nodes[id].bit = depth;
-      const int a = build_node(set_rows, depth + 1);
-      const int b = build_node(clear_rows, depth + 1);
+      const int a = build_node(keys, lo, split, depth + 1);
+      const int b = build_node(keys, split, hi, depth + 1);
       nodes[id].set_child = a;
       nodes[id].clear_child = b;
     } else {
-      nodes[id].row_begin = uint32_t(s_hash.size());
-      for (uint32_t r : rows) {
-        s_hash.push_back(hash[r]);
-        s_index.push_back(index[r]);
-      }
-      nodes[id].row_end = uint32_t(s_hash.size());
+      nodes[id].row_begin = lo;
+      nodes[id].row_end = hi;
     }
     return id;
   }
 
+  // The trie shape depends only on the multiset of hashes, so it is built from a sort: keys on the device, a
+  // stable radix sort (a leaf keeps insertion order like the reference's append), a gather into the
+  // leaf-contiguous layout, then the node table from binary searches over the sorted keys.
   int build() {
     if (built) return CB_OK;
     int rc = ensure_device();
@@ -97,14 +122,42 @@ struct HammingTree {
     s_hash.clear();
     s_index.clear();
     max_height = 0;
-    if (!hash.empty()) {
-      std::vector<uint32_t> rows(hash.size());
-      for (size_t i = 0; i < rows.size(); ++i) rows[i] = uint32_t(i);
-      build_node(rows, 0);
+    const size_t n = hash.size();
+    if (n > 0xFFFFF000ull) {
+      set_error("hamming tree: %zu hashes exceed the 32-bit row index", n);
+      return CB_ERR_UNSUPPORTED;
+    }
+    if (n) {
       CB_CUDA(cudaSetDevice(device));
-      if ((rc = d_hash.reserve(s_hash.size() + 2)) != CB_OK) return rc;
-      CB_CUDA(cudaMemcpyAsync(d_hash.p, s_hash.data(), s_hash.size() * 8, cudaMemcpyHostToDevice, stream));
+      DevBuf<uint64_t> d_raw;
+      DevBuf<uint32_t> d_index, d_sindex, d_key, d_key2, d_val, d_val2;
+      DevBuf<unsigned char> d_temp;
+      if ((rc = d_raw.reserve(n)) != CB_OK || (rc = d_index.reserve(n)) != CB_OK || (rc = d_sindex.reserve(n)) != CB_OK ||
+          (rc = d_key.reserve(n)) != CB_OK || (rc = d_key2.reserve(n)) != CB_OK || (rc = d_val.reserve(n)) != CB_OK ||
+          (rc = d_val2.reserve(n)) != CB_OK || (rc = d_hash.reserve(n + 2)) != CB_OK)
+        return rc;
+      CB_CUDA(cudaMemcpyAsync(d_raw.p, hash.data(), n * 8, cudaMemcpyHostToDevice, stream));
+      CB_CUDA(cudaMemcpyAsync(d_index.p, index.data(), n * 4, cudaMemcpyHostToDevice, stream));
+      const unsigned blocks = unsigned((n + 255) / 256);
+      trie_keys_kernel<<<blocks, 256, 0, stream>>>(d_raw.p, uint32_t(n), d_key.p, d_val.p);
+      CB_CUDA(cudaGetLastError());
+      size_t tb = 0;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_val.p, d_val2.p, static_cast<long long>(n), 0,
+                                              kKeyBits, stream));
+      if ((rc = d_temp.reserve(tb + 16)) != CB_OK) return rc;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, tb, d_key.p, d_key2.p, d_val.p, d_val2.p, static_cast<long long>(n), 0,
+                                              kKeyBits, stream));
+      trie_gather_kernel<<<blocks, 256, 0, stream>>>(d_val2.p, uint32_t(n), d_raw.p, d_index.p, d_hash.p, d_sindex.p);
+      CB_CUDA(cudaGetLastError());
+      counters().launches += 2;
+      std::vector<uint32_t> keys(n);
+      s_hash.resize(n);
+      s_index.resize(n);
+      CB_CUDA(cudaMemcpyAsync(keys.data(), d_key2.p, n * 4, cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaMemcpyAsync(s_hash.data(), d_hash.p, n * 8, cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaMemcpyAsync(s_index.data(), d_sindex.p, n * 4, cudaMemcpyDeviceToHost, stream));
       CB_CUDA(cudaStreamSynchronize(stream));
+      build_node(keys, 0, uint32_t(n), 0);
     }
     built = true;
     return CB_OK;
