@@ -697,6 +697,179 @@ __global__ void __launch_bounds__(256)
   if (tid == 0) out[blockIdx.x] = hsh;
 }
 
+// ---- banded path for frames too large for one CTA's shared memory (decoded images) ----------------------
+// The frame is cut into bands of kBandRows view rows x segments of whole destination cells (<= 1024 px wide);
+// one CTA streams its band row by row: raw row -> shared memory (word loads, reflect-101 at the parent's edges),
+// 4 horizontal box sums per thread (hsum4), a running vertical sum over the last K rows kept in a shared-memory
+// ring, blur rounding, and the blurred band stays in shared memory. INTER_AREA is then split the way OpenCV
+// itself accumulates: per source row the horizontal coverage sum of every destination cell (an f32 chain in x
+// order, or an exact integer sum for integer scales) goes to `rowcells[frame][row][32]`; rowcells_hash_kernel
+// adds the rows of every cell in order, rounds, and hashes the 32x32 tile. Same arithmetic as
+// area_pixel_taps / area_pixel_fast, so the result is bit-identical to the fused and global-memory paths.
+constexpr int kBandSegMax = 1024;  // pixels per segment incl. alignment slack: one 4-px group per thread
+
+struct BandGeom {
+  int cells_per_seg, band_rows;
+};
+
+template <int R>
+__device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long long row_stride, int w, int h, int rl, int rt,
+                                          int cw, int ch, int amode, int ix, BandGeom g, unsigned char* smem,
+                                          float* __restrict__ rowcells /* this frame: [h][32] */) {
+  constexpr int K = 2 * R + 1;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * g.cells_per_seg, c1 = min(32, c0 + g.cells_per_seg);
+  const int y0 = blockIdx.y * g.band_rows, y1 = min(ch, y0 + g.band_rows);
+  if (c0 >= 32 || y0 >= ch) return;
+  AxisTaps* s_taps = reinterpret_cast<AxisTaps*>(smem);  // 32 entries
+  if (amode == 3 && tid < c1 - c0) s_taps[tid] = make_taps(c0 + tid, cw, cw / 32.0);
+  __syncthreads();
+  int xs, xe;  // view columns [xs, xe) feed cells [c0, c1)
+  if (amode == 3) {
+    xs = s_taps[0].sx1 - s_taps[0].has_head;
+    xe = s_taps[c1 - c0 - 1].sx2 + s_taps[c1 - c0 - 1].has_tail;
+  } else {
+    xs = c0 * ix;
+    xe = c1 * ix;
+  }
+  const int xo = (rl + xs) & ~3;             // parent column of group 0 (word aligned in the parent row)
+  const int G = (rl + xe - xo + 3) >> 2;     // 4-px groups, <= 256
+  const int bl_stride = 4 * G;
+  uint32_t* raw = reinterpret_cast<uint32_t*>(s_taps + 32);          // 2 x (G + 2) words, parent px xo-4 ..
+  uint32_t* ring = raw + 2 * (kBandSegMax / 4 + 2);                   // K x G x 2 words of packed u16 row sums
+  uint8_t* bl = reinterpret_cast<uint8_t*>(ring + 7 * 2 * (kBandSegMax / 4));  // band_rows x bl_stride blurred px
+  int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  const int steps = (y1 - y0) + 2 * R;
+  for (int j = 0; j < steps; ++j) {
+    const uint8_t* row = src + (long long)reflect101(rt + y0 - R + j, h) * row_stride;
+    uint32_t* rw = raw + (j & 1) * (kBandSegMax / 4 + 2);
+    const bool row_aligned = (reinterpret_cast<uintptr_t>(row) & 3) == 0;
+    for (int i = tid; i < G + 2; i += 256) {
+      const int x = xo - 4 + 4 * i;
+      uint32_t word;
+      if (row_aligned && x >= 0 && x + 3 < w) {
+        word = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+      } else {
+        word = uint32_t(row[reflect101(x, w)]) | (uint32_t(row[reflect101(x + 1, w)]) << 8) |
+               (uint32_t(row[reflect101(x + 2, w)]) << 16) | (uint32_t(row[reflect101(x + 3, w)]) << 24);
+      }
+      rw[i] = word;
+    }
+    __syncthreads();
+    if (tid < G) {
+      int s0, s1, s2, s3;
+      hsum4<R>(rw[tid], rw[tid + 1], rw[tid + 2], s0, s1, s2, s3);
+      uint32_t* slot = ring + ((j % K) * (kBandSegMax / 4) + tid) * 2;
+      if (j >= K) {  // drop the row that leaves the window
+        const uint32_t o01 = slot[0], o23 = slot[1];
+        v0 -= int(o01 & 0xFFFFu); v1 -= int(o01 >> 16); v2 -= int(o23 & 0xFFFFu); v3 -= int(o23 >> 16);
+      }
+      v0 += s0; v1 += s1; v2 += s2; v3 += s3;
+      slot[0] = uint32_t(s0) | (uint32_t(s1) << 16);
+      slot[1] = uint32_t(s2) | (uint32_t(s3) << 16);
+      if (j >= 2 * R) {
+        uint32_t px;
+        if (R == 0) px = rw[tid + 1];
+        else px = uint32_t(blur_round(v0, K)) | (uint32_t(blur_round(v1, K)) << 8) | (uint32_t(blur_round(v2, K)) << 16) |
+                  (uint32_t(blur_round(v3, K)) << 24);
+        reinterpret_cast<uint32_t*>(bl + (j - 2 * R) * bl_stride)[tid] = px;
+      }
+    }
+  }
+  __syncthreads();
+  // horizontal INTER_AREA coverage of every (band row, cell): item = row * cells + cell
+  const int cells = c1 - c0, items = (y1 - y0) * cells;
+  const int shift = rl - xo;  // view column x sits at bl[.. + x + shift]
+  for (int it = tid; it < items; it += 256) {
+    const int r = it / cells, c = it - r * cells;
+    const uint8_t* brow = bl + r * bl_stride + shift;
+    float* dst = rowcells + (long long)(y0 + r) * 32 + c0 + c;
+    if (amode == 3) {
+      const AxisTaps tx = s_taps[c];
+      float buf = 0.f;
+      if (tx.has_head) buf = __fadd_rn(buf, __fmul_rn(float(brow[tx.sx1 - 1]), tx.head_alpha));
+      const float ba = tx.body_alpha;
+      for (int k = tx.sx1; k < tx.sx2; ++k) buf = __fadd_rn(buf, __fmul_rn(float(brow[k]), ba));
+      if (tx.has_tail) buf = __fadd_rn(buf, __fmul_rn(float(brow[tx.sx2]), tx.tail_alpha));
+      *dst = buf;
+    } else {
+      int sum = 0;
+      const int xb = (c0 + c) * ix;
+      for (int i = 0; i < ix; ++i) sum += brow[xb + i];
+      *dst = __int_as_float(sum);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    band_rowcells_kernel(const uint8_t* __restrict__ frames, long long row_stride, long long frame_stride, int w, int h,
+                         const int32_t* __restrict__ rects, BandGeom g, float* __restrict__ rowcells) {
+  extern __shared__ __align__(16) unsigned char band_smem[];
+  const int full[4] = {0, 0, w, h};
+  const int32_t* rc = rects ? rects + 4 * (long long)blockIdx.z : full;
+  const int rl = rc[0], rt = rc[1], cw = rc[2] - rc[0], ch = rc[3] - rc[1];
+  if (cw < 32 || ch < 32) return;  // rowcells_hash_kernel writes "no hash"
+  int ix, iy;
+  const int amode = area_mode(cw, ch, &ix, &iy);
+  const uint8_t* src = frames + (long long)blockIdx.z * frame_stride;
+  float* rcells = rowcells + (long long)blockIdx.z * h * 32;
+  switch (blur_k_for((long long)cw * ch)) {
+    case 0: band_body<0>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
+    case 3: band_body<1>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
+    case 5: band_body<2>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
+    default: band_body<3>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
+  }
+}
+
+size_t band_smem_bytes(int band_rows) {
+  return 32 * sizeof(AxisTaps) + 2 * (kBandSegMax / 4 + 2) * 4 + 7 * 2 * (kBandSegMax / 4) * 4 + size_t(band_rows) * kBandSegMax;
+}
+
+// vertical half of INTER_AREA + rounding + DCT hash: one CTA per frame, one thread per destination cell
+__global__ void __launch_bounds__(1024)
+    rowcells_hash_kernel(const float* __restrict__ rowcells, int w, int h, const int32_t* __restrict__ rects,
+                         uint64_t* __restrict__ out) {
+  __shared__ float sT[288], sF[84];
+  __shared__ __align__(16) uint8_t tile[1024];
+  const int full[4] = {0, 0, w, h};
+  const int32_t* rc = rects ? rects + 4 * (long long)blockIdx.x : full;
+  const int cw = rc[2] - rc[0], ch = rc[3] - rc[1];
+  if (cw < 32 || ch < 32) {  // INTER_AREA up-scaling is not restated: "no hash"
+    if (threadIdx.x == 0) out[blockIdx.x] = 0;
+    return;
+  }
+  const float* cells = rowcells + (long long)blockIdx.x * h * 32;
+  const int dx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  int ix, iy;
+  const int amode = area_mode(cw, ch, &ix, &iy);
+  uint8_t px;
+  if (amode == 3) {
+    const AxisTaps ty = make_taps(dy, ch, ch / 32.0);
+    float sum = 0.f;
+    bool first = true;
+    auto acc = [&](int syi, float beta) {
+      const float t = __fmul_rn(beta, cells[syi * 32 + dx]);
+      sum = first ? t : __fadd_rn(sum, t);
+      first = false;
+    };
+    if (ty.has_head) acc(ty.sx1 - 1, ty.head_alpha);
+    const float bb = ty.body_alpha;
+    for (int k = ty.sx1; k < ty.sx2; ++k) acc(k, bb);
+    if (ty.has_tail) acc(ty.sx2, ty.tail_alpha);
+    px = uint8_t(min(255, max(0, __float2int_rn(sum))));
+  } else {
+    int s = 0;
+    for (int j = 0; j < iy; ++j) s += __float_as_int(cells[(dy * iy + j) * 32 + dx]);
+    if (amode == 0) px = uint8_t(s);
+    else if (amode == 1) px = uint8_t((s + 2) >> 2);
+    else px = uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(s), __fdiv_rn(1.f, float(ix * iy)))))));
+  }
+  tile[threadIdx.x] = px;
+  __syncthreads();
+  const uint64_t hsh = hash_tile_cta(tile, sT, sF);
+  if (threadIdx.x == 0) out[blockIdx.x] = hsh;
+}
+
 size_t fused_smem_bytes(int w, int h) {
   return (288 + 84) * 4 + 16 + 64 * sizeof(AxisTaps) + 1024 + size_t(2 * h + 2 * w) * 4 + ((size_t(h) * w + 1) / 2 * 2) * 2 + size_t(h) * w + 16;
 }
@@ -724,7 +897,42 @@ int launch_fused(const uint8_t* d_frames, long long n, int w, int h, long long r
 struct HashWorkspace {
   DevBuf<uint8_t> blurred, tiles, bad;
   DevBuf<int32_t> rects;
+  DevBuf<float> rowcells;
 };
+
+// frames too large for the fused kernel: banded blur + INTER_AREA row sums, then per-frame reduction + hash
+int launch_banded(const uint8_t* d_frames, long long n, int w, int h, long long row_stride, long long frame_stride,
+                  const int32_t* d_rects, uint64_t* d_out, HashWorkspace* ws, cudaStream_t stream) {
+  int rc = ws->rowcells.reserve(size_t(n) * h * 32);
+  if (rc != CB_OK) return rc;
+  BandGeom g;
+  const double scale = w / 32.0;  // a crop is never wider than its parent
+  g.cells_per_seg = std::max(1, std::min(32, int((kBandSegMax - 8) / scale)));
+  const unsigned segs = unsigned((32 + g.cells_per_seg - 1) / g.cells_per_seg);
+  g.band_rows = 32;  // halve the band (more halo re-reads) while a small batch leaves SMs idle
+  while (g.band_rows > 8 && (long long)segs * ((h + g.band_rows - 1) / g.band_rows) * n < 2 * 148) g.band_rows >>= 1;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(band_rowcells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(band_smem_bytes(32)));
+  });
+  if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(band_rowcells_kernel)", __FILE__, __LINE__);
+  for (long long f0 = 0; f0 < n; f0 += 65535) {  // gridDim.z limit
+    const long long m = std::min<long long>(65535, n - f0);
+    dim3 grid(segs, unsigned((h + g.band_rows - 1) / g.band_rows), unsigned(m));
+    band_rowcells_kernel<<<grid, 256, band_smem_bytes(g.band_rows), stream>>>(
+        d_frames + f0 * frame_stride, row_stride, frame_stride, w, h, d_rects ? d_rects + 4 * f0 : nullptr, g,
+        ws->rowcells.p + size_t(f0) * h * 32);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+  }
+  rowcells_hash_kernel<<<unsigned(n), 1024, 0, stream>>>(ws->rowcells.p, w, h, d_rects, d_out);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
+  counters().frames += uint64_t(n);
+  return CB_OK;
+}
 
 int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long t_frame, uint64_t* d_out,
                   cudaStream_t stream);
@@ -778,6 +986,8 @@ int hash_rects_device(const uint8_t* d_frames, long long n, int w, int h, long l
   if (fused_ok(w, h) && !no_fused)
     return launch_fused(d_frames, n, w, h, row_stride, frame_stride, d_rects ? 1 : 0, 0, const_cast<int32_t*>(d_rects), d_out,
                         stream);
+  static const bool no_banded = getenv("CB_HASH_NO_BANDED") != nullptr;  // parity aid: the three-kernel route
+  if (!no_banded) return launch_banded(d_frames, n, w, h, row_stride, frame_stride, d_rects, d_out, ws, stream);
   if ((rc = ws->blurred.reserve(size_t(n) * w * h)) != CB_OK || (rc = ws->tiles.reserve(size_t(n) * 1024)) != CB_OK ||
       (rc = ws->bad.reserve(size_t(n))) != CB_OK)
     return rc;

@@ -120,3 +120,33 @@ def test_colour_frames_gray_and_hash(cb, po):
     out = np.zeros((1, 8, 8), np.uint8)
     assert cb.lib().cb_gray_batch(buf.ctypes.data, 1, 8, 8, 2, 16, 128, 1, out.ctypes.data) == -5
     assert b"channel" in cb.lib().cb_last_error()
+
+
+def _textured(rng, n, w, h, cell=24):
+    base = rng.integers(0, 256, size=(n, h // cell + 2, w // cell + 2)).astype(np.float32)
+    fr = np.stack([np.kron(b, np.ones((cell, cell), np.float32))[:h, :w] for b in base])
+    return np.clip(fr + rng.normal(0, 6, fr.shape), 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h,n", [(640, 480, 5), (1000, 700, 3), (1920, 1080, 2), (641, 479, 3), (4000, 3000, 1),
+                                   (4096, 33, 2), (33, 2000, 2), (352, 288, 20)])
+def test_image_sized_frames(cb, po, w, h, n):
+    # decoded images (src/scanner.cpp:862) do not fit one CTA's shared memory: banded blur + INTER_AREA path.
+    # Integer scales (640x480: 20x15), fractional ones, several segments per row (w > 1000), unaligned rows.
+    fr = _textured(np.random.default_rng(w * 31 + h), n, w, h)
+    assert np.array_equal(cb.dct_hash64_batch(fr), po.dct_hash64_batch(fr)[0]), (w, h)
+
+
+def test_image_sized_rects_and_views(cb, po):
+    rng = np.random.default_rng(12)
+    fr = _textured(rng, 6, 700, 500)
+    rects = np.array([[0, 0, 700, 500], [10, 20, 650, 470], [3, 5, 35, 37], [100, 50, 420, 370], [1, 1, 699, 499],
+                      [50, 60, 70, 90]], np.int32)  # full, crop, 32x32 crop (k=0), 320x320 (scale 10), odd, too small
+    got = cb.dct_hash64_rects(fr, rects)
+    for i in range(5):
+        assert int(got[i]) == po.dct_hash64_rect(fr[i], rects[i]), i
+    assert int(got[5]) == 0  # a crop under 32 px has no hash
+    # strided views of a larger buffer (row stride != width, rows not word aligned)
+    big = _textured(rng, 3, 1001, 601)
+    view = big[:, 7:507, 13:913]
+    assert np.array_equal(cb.dct_hash64_batch(view), po.dct_hash64_batch(np.ascontiguousarray(view))[0])
