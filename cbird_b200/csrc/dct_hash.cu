@@ -738,40 +738,72 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
   uint32_t* raw = reinterpret_cast<uint32_t*>(s_taps + 32);          // 2 x (G + 2) words, parent px xo-4 ..
   uint32_t* ring = raw + 2 * (kBandSegMax / 4 + 2);                   // K x G x 2 words of packed u16 row sums
   uint8_t* bl = reinterpret_cast<uint8_t*>(ring + 7 * 2 * (kBandSegMax / 4));  // band_rows x bl_stride blurred px
-  int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
   const int steps = (y1 - y0) + 2 * R;
+  // word i of a raw row = parent pixels xo-4+4i .. +3 (reflect-101 at the parent's edges); G + 2 <= 258 words,
+  // so a thread owns word `tid` and threads 0/1 also own words 256/257
+  // Word-aligned geometry (the usual case): every in-frame word is one aligned 32-bit load and the two words
+  // that hang over the frame edge are synthesised by the consumer with one byte permute (reflect-101).
+  // Anything else goes byte by byte. One reflection is enough: the overshoot is < 8 and the frame >= 32.
+  const bool fast = ((reinterpret_cast<uintptr_t>(src) | uintptr_t(row_stride) | uintptr_t(w)) & 3) == 0;
+  auto refl = [](int p, int n) { p = abs(p); return min(p, 2 * (n - 1) - p); };
+  auto load_word = [&](const uint8_t* row, int x) -> uint32_t {
+    if (fast) return (x >= 0 && x + 3 < w) ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
+    return uint32_t(row[refl(x, w)]) | (uint32_t(row[refl(x + 1, w)]) << 8) | (uint32_t(row[refl(x + 2, w)]) << 16) |
+           (uint32_t(row[refl(x + 3, w)]) << 24);
+  };
+  auto row_ptr = [&](int j) { return src + (long long)refl(rt + y0 - R + j, h) * row_stride; };
+  const bool own_a = tid < G + 2, own_b = tid + 256 < G + 2;
+  const int xa = xo - 4 + 4 * tid, xb = xa + 1024;
+  const bool left_edge = fast && xa + 4 == 0, right_edge = fast && xa + 8 == w;  // my group touches a frame edge
+  uint32_t next_a = own_a ? load_word(row_ptr(0), xa) : 0, next_b = own_b ? load_word(row_ptr(0), xb) : 0;
+  // Running vertical sums of the 4 pixels as packed u16 pairs (s0,s2) and (s1,s3): every lane stays below
+  // 49*255 < 2^16 and "add the new row, then drop the old one" never borrows across lanes.
+  uint32_t va = 0, vb = 0;
+  constexpr uint32_t kM = K == 7 ? 342393u : (K == 5 ? 671089u : 1864136u);  // ceil(2^24 / K^2)
+  constexpr uint32_t kC = uint32_t(K * K / 2) * kM;  // nearest integer of s / K^2 == ((s + K^2/2) * kM) >> 24, exact for
+                                                    // s <= 255 K^2 (and the product fits 32 bits)
   for (int j = 0; j < steps; ++j) {
-    const uint8_t* row = src + (long long)reflect101(rt + y0 - R + j, h) * row_stride;
     uint32_t* rw = raw + (j & 1) * (kBandSegMax / 4 + 2);
-    const bool row_aligned = (reinterpret_cast<uintptr_t>(row) & 3) == 0;
-    for (int i = tid; i < G + 2; i += 256) {
-      const int x = xo - 4 + 4 * i;
-      uint32_t word;
-      if (row_aligned && x >= 0 && x + 3 < w) {
-        word = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-      } else {
-        word = uint32_t(row[reflect101(x, w)]) | (uint32_t(row[reflect101(x + 1, w)]) << 8) |
-               (uint32_t(row[reflect101(x + 2, w)]) << 16) | (uint32_t(row[reflect101(x + 3, w)]) << 24);
-      }
-      rw[i] = word;
+    if (own_a) rw[tid] = next_a;
+    if (own_b) rw[tid + 256] = next_b;
+    if (j + 1 < steps) {  // the next row's loads stay in flight behind this row's arithmetic
+      const uint8_t* nrow = row_ptr(j + 1);
+      if (own_a) next_a = load_word(nrow, xa);
+      if (own_b) next_b = load_word(nrow, xb);
     }
     __syncthreads();
     if (tid < G) {
-      int s0, s1, s2, s3;
-      hsum4<R>(rw[tid], rw[tid + 1], rw[tid + 2], s0, s1, s2, s3);
+      // q(i) = (pixel i, pixel i+2) as u16 lanes, pixel i = byte i of (wl, wc, wr); the group is bytes 4..7
+      uint32_t wl = rw[tid], wr = rw[tid + 2];
+      const uint32_t wc = rw[tid + 1];
+      if (left_edge) wl = __byte_perm(wc, wr, 0x1234);   // pixels -4..-1 = pixels 4, 3, 2, 1
+      if (right_edge) wr = __byte_perm(wl, wc, 0x3456);  // pixels w..w+3 = pixels w-2, w-3, w-4, w-5
+      const uint32_t w2 = __funnelshift_r(wl, wc, 16), w6 = __funnelshift_r(wc, wr, 16);
+      constexpr uint32_t kLanes = 0x00FF00FFu;
+      const uint32_t q[10] = {wl & kLanes, (wl >> 8) & kLanes, w2 & kLanes, (w2 >> 8) & kLanes, wc & kLanes,
+                              (wc >> 8) & kLanes, w6 & kLanes, (w6 >> 8) & kLanes, wr & kLanes, (wr >> 8) & kLanes};
+      uint32_t sa = 0;  // (s0, s2): box sums of pixels 4 and 6
+#pragma unroll
+      for (int i = 4 - R; i <= 4 + R; ++i) sa += q[i];
+      const uint32_t sb = sa + q[5 + R] - q[4 - R];  // (s1, s3)
       uint32_t* slot = ring + ((j % K) * (kBandSegMax / 4) + tid) * 2;
+      va += sa;
+      vb += sb;
       if (j >= K) {  // drop the row that leaves the window
-        const uint32_t o01 = slot[0], o23 = slot[1];
-        v0 -= int(o01 & 0xFFFFu); v1 -= int(o01 >> 16); v2 -= int(o23 & 0xFFFFu); v3 -= int(o23 >> 16);
+        va -= slot[0];
+        vb -= slot[1];
       }
-      v0 += s0; v1 += s1; v2 += s2; v3 += s3;
-      slot[0] = uint32_t(s0) | (uint32_t(s1) << 16);
-      slot[1] = uint32_t(s2) | (uint32_t(s3) << 16);
+      slot[0] = sa;
+      slot[1] = sb;
       if (j >= 2 * R) {
         uint32_t px;
-        if (R == 0) px = rw[tid + 1];
-        else px = uint32_t(blur_round(v0, K)) | (uint32_t(blur_round(v1, K)) << 8) | (uint32_t(blur_round(v2, K)) << 16) |
-                  (uint32_t(blur_round(v3, K)) << 24);
+        if (R == 0) {
+          px = wc;
+        } else {
+          const uint32_t p0 = (va & 0xFFFFu) * kM + kC, p2 = (va >> 16) * kM + kC;
+          const uint32_t p1 = (vb & 0xFFFFu) * kM + kC, p3 = (vb >> 16) * kM + kC;
+          px = __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);  // byte 3 of each
+        }
         reinterpret_cast<uint32_t*>(bl + (j - 2 * R) * bl_stride)[tid] = px;
       }
     }
