@@ -712,7 +712,7 @@ struct BandGeom {
   int cells_per_seg, band_rows;
 };
 
-template <int R>
+template <int R, bool FAST>
 __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long long row_stride, int w, int h, int rl, int rt,
                                           int cw, int ch, int amode, int ix, BandGeom g, unsigned char* smem,
                                           float* __restrict__ rowcells /* this frame: [h][32] */) {
@@ -741,35 +741,39 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
   const int steps = (y1 - y0) + 2 * R;
   // word i of a raw row = parent pixels xo-4+4i .. +3 (reflect-101 at the parent's edges); G + 2 <= 258 words,
   // so a thread owns word `tid` and threads 0/1 also own words 256/257
-  // Word-aligned geometry (the usual case): every in-frame word is one aligned 32-bit load and the two words
-  // that hang over the frame edge are synthesised by the consumer with one byte permute (reflect-101).
-  // Anything else goes byte by byte. One reflection is enough: the overshoot is < 8 and the frame >= 32.
-  const bool fast = ((reinterpret_cast<uintptr_t>(src) | uintptr_t(row_stride) | uintptr_t(w)) & 3) == 0;
+  // FAST = word-aligned geometry (frame base, row stride and width multiples of 4, the usual case): every
+  // in-frame word is one aligned 32-bit load and the two words that hang over the frame edge are synthesised
+  // by the consumer with one byte permute (reflect-101). Anything else goes byte by byte. One reflection is
+  // enough: the overshoot is < 8 and the frame >= 32.
   auto refl = [](int p, int n) { p = abs(p); return min(p, 2 * (n - 1) - p); };
-  auto load_word = [&](const uint8_t* row, int x) -> uint32_t {
-    if (fast) return (x >= 0 && x + 3 < w) ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
+  const int xa = xo - 4 + 4 * tid, xb = xa + 1024;
+  const bool own_a = tid < G + 2 && (!FAST || (xa >= 0 && xa + 3 < w));
+  const bool own_b = tid + 256 < G + 2 && (!FAST || (xb >= 0 && xb + 3 < w));
+  auto load_word = [&](long long roff, int x) -> uint32_t {
+    if (FAST) return __ldg(reinterpret_cast<const uint32_t*>(src + roff + x));
+    const uint8_t* row = src + roff;
     return uint32_t(row[refl(x, w)]) | (uint32_t(row[refl(x + 1, w)]) << 8) | (uint32_t(row[refl(x + 2, w)]) << 16) |
            (uint32_t(row[refl(x + 3, w)]) << 24);
   };
-  auto row_ptr = [&](int j) { return src + (long long)refl(rt + y0 - R + j, h) * row_stride; };
-  const bool own_a = tid < G + 2, own_b = tid + 256 < G + 2;
-  const int xa = xo - 4 + 4 * tid, xb = xa + 1024;
-  const bool left_edge = fast && xa + 4 == 0, right_edge = fast && xa + 8 == w;  // my group touches a frame edge
-  uint32_t next_a = own_a ? load_word(row_ptr(0), xa) : 0, next_b = own_b ? load_word(row_ptr(0), xb) : 0;
+  auto row_off = [&](int j) { return (long long)refl(rt + y0 - R + j, h) * row_stride; };
+  const bool left_edge = FAST && xa + 4 == 0, right_edge = FAST && xa + 8 == w;  // my group touches a frame edge
+  uint32_t next_a = own_a ? load_word(row_off(0), xa) : 0, next_b = own_b ? load_word(row_off(0), xb) : 0;
   // Running vertical sums of the 4 pixels as packed u16 pairs (s0,s2) and (s1,s3): every lane stays below
   // 49*255 < 2^16 and "add the new row, then drop the old one" never borrows across lanes.
   uint32_t va = 0, vb = 0;
   constexpr uint32_t kM = K == 7 ? 342393u : (K == 5 ? 671089u : 1864136u);  // ceil(2^24 / K^2)
   constexpr uint32_t kC = uint32_t(K * K / 2) * kM;  // nearest integer of s / K^2 == ((s + K^2/2) * kM) >> 24, exact for
                                                     // s <= 255 K^2 (and the product fits 32 bits)
+  uint32_t* slot = ring + 2 * tid;  // my slot of the ring row written this step
+  int ring_row = 0;
   for (int j = 0; j < steps; ++j) {
     uint32_t* rw = raw + (j & 1) * (kBandSegMax / 4 + 2);
-    if (own_a) rw[tid] = next_a;
-    if (own_b) rw[tid + 256] = next_b;
+    rw[tid] = next_a;  // (words nobody loads are never consumed unpatched)
+    if (tid < 2) rw[tid + 256] = next_b;
     if (j + 1 < steps) {  // the next row's loads stay in flight behind this row's arithmetic
-      const uint8_t* nrow = row_ptr(j + 1);
-      if (own_a) next_a = load_word(nrow, xa);
-      if (own_b) next_b = load_word(nrow, xb);
+      const long long noff = row_off(j + 1);
+      if (own_a) next_a = load_word(noff, xa);
+      if (own_b) next_b = load_word(noff, xb);
     }
     __syncthreads();
     if (tid < G) {
@@ -786,7 +790,6 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
 #pragma unroll
       for (int i = 4 - R; i <= 4 + R; ++i) sa += q[i];
       const uint32_t sb = sa + q[5 + R] - q[4 - R];  // (s1, s3)
-      uint32_t* slot = ring + ((j % K) * (kBandSegMax / 4) + tid) * 2;
       va += sa;
       vb += sb;
       if (j >= K) {  // drop the row that leaves the window
@@ -795,6 +798,12 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
       }
       slot[0] = sa;
       slot[1] = sb;
+      if (++ring_row == K) {
+        ring_row = 0;
+        slot -= (K - 1) * 2 * (kBandSegMax / 4);
+      } else {
+        slot += 2 * (kBandSegMax / 4);
+      }
       if (j >= 2 * R) {
         uint32_t px;
         if (R == 0) {
@@ -845,12 +854,18 @@ __global__ void __launch_bounds__(256)
   const int amode = area_mode(cw, ch, &ix, &iy);
   const uint8_t* src = frames + (long long)blockIdx.z * frame_stride;
   float* rcells = rowcells + (long long)blockIdx.z * h * 32;
+  const bool fast = ((reinterpret_cast<uintptr_t>(src) | uintptr_t(row_stride) | uintptr_t(w)) & 3) == 0;
+#define CB_BAND(RR)                                                                                      \
+  if (fast) band_body<RR, true>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); \
+  else band_body<RR, false>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells);     \
+  break;
   switch (blur_k_for((long long)cw * ch)) {
-    case 0: band_body<0>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
-    case 3: band_body<1>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
-    case 5: band_body<2>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
-    default: band_body<3>(src, row_stride, w, h, rl, rt, cw, ch, amode, ix, g, band_smem, rcells); break;
+    case 0: CB_BAND(0)
+    case 3: CB_BAND(1)
+    case 5: CB_BAND(2)
+    default: CB_BAND(3)
   }
+#undef CB_BAND
 }
 
 size_t band_smem_bytes(int band_rows) {
