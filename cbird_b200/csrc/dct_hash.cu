@@ -484,32 +484,50 @@ __device__ __forceinline__ int blur_round(int s, int k) {  // nearest integer of
   }
 }
 
-// 4 consecutive horizontal box sums (radius R) from the three words around them; b(j) = pixel x0-4+j
+// nearest integer of s / K^2 for s <= 255 K^2 as one multiply: ((s + K^2/2) * ceil(2^24 / K^2)) >> 24 (checked
+// exhaustively for K = 3, 5, 7; the product fits 32 bits). blur_mul/blur_add give the two constants.
+template <int K>
+struct BlurMagic {
+  static constexpr uint32_t mul = K == 7 ? 342393u : (K == 5 ? 671089u : 1864136u);
+  static constexpr uint32_t add = uint32_t(K * K / 2) * mul;
+};
+
+// The four box sums of a 4-pixel group from the three words around it, as packed u16 lane pairs
+// sa = (s0, s2), sb = (s1, s3). q(i) = (pixel i, pixel i+2), pixel i = byte i of (wl, wc, wr); the group is
+// bytes 4..7. Lanes stay below 2^16 (<= 7*255), and "add, then subtract" never borrows across lanes.
 template <int R>
-__device__ __forceinline__ void hsum4(uint32_t wl, uint32_t wc, uint32_t wr, int& s0, int& s1, int& s2, int& s3) {
-  auto b = [&](int j) -> int {  // j in 0..11, compile-time after unrolling
-    const uint32_t word = j < 4 ? wl : (j < 8 ? wc : wr);
-    return int((word >> (8 * (j & 3))) & 0xFFu);
-  };
-  s0 = 0;
+__device__ __forceinline__ void hsum4_packed(uint32_t wl, uint32_t wc, uint32_t wr, uint32_t& sa, uint32_t& sb) {
+  const uint32_t w2 = __funnelshift_r(wl, wc, 16), w6 = __funnelshift_r(wc, wr, 16);
+  constexpr uint32_t kLanes = 0x00FF00FFu;
+  const uint32_t q[10] = {wl & kLanes, (wl >> 8) & kLanes, w2 & kLanes, (w2 >> 8) & kLanes, wc & kLanes,
+                          (wc >> 8) & kLanes, w6 & kLanes, (w6 >> 8) & kLanes, wr & kLanes, (wr >> 8) & kLanes};
+  sa = 0;
 #pragma unroll
-  for (int j = 4 - R; j <= 4 + R; ++j) s0 += b(j);
-  s1 = s0 + b(5 + R) - b(4 - R);
-  s2 = s1 + b(6 + R) - b(5 - R);
-  s3 = s2 + b(7 + R) - b(6 - R);
+  for (int i = 4 - R; i <= 4 + R; ++i) sa += q[i];
+  sb = sa + q[5 + R] - q[4 - R];
 }
 
-// word-wise separable box blur (radius R) of the view [rl, rl+cw) x [rt, rt+ch) of the w x h frame in
-// `img` (w % 4 == 0); `hs` receives u16 row sums for all parent columns (stride w); the blurred view is
-// written back into `img` densely (stride cw). Pixels outside the view come from the parent frame,
-// reflect-101 only at the parent's edges — cv::blur on a non-isolated ROI. All 256 threads call it.
+// vertical sums (packed like hsum4_packed) -> the group's four blurred pixels as one word
+template <int K>
+__device__ __forceinline__ uint32_t blur_round4(uint32_t va, uint32_t vb) {
+  const uint32_t p0 = (va & 0xFFFFu) * BlurMagic<K>::mul + BlurMagic<K>::add, p2 = (va >> 16) * BlurMagic<K>::mul + BlurMagic<K>::add;
+  const uint32_t p1 = (vb & 0xFFFFu) * BlurMagic<K>::mul + BlurMagic<K>::add, p3 = (vb >> 16) * BlurMagic<K>::mul + BlurMagic<K>::add;
+  return __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);  // byte 3 of each product
+}
+
+// word-wise separable box blur (radius R >= 1) of the view [rl, rl+cw) x [rt, rt+ch) of the w x h frame in
+// `img` (w % 4 == 0, h >= 32); `hs` receives the packed row sums of every 4-pixel group of the parent (2 words
+// per group); the blurred view is written back into `img` IN PLACE at the parent's layout (stride w). Pixels
+// outside the view come from the parent frame, reflect-101 only at the parent's edges — cv::blur on a
+// non-isolated ROI. The vertical pass keeps a running sum per group and row segment (2 loads per output row
+// instead of K). All 256 threads call it.
 template <int R>
 __device__ __forceinline__ void blur_view_words(uint8_t* img, uint16_t* hs, int w, int h, int rl, int rt, int cw, int ch) {
   constexpr int K = 2 * R + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wq = w >> 2, hw = w >> 1;
-  const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
-  uint32_t* hs32 = reinterpret_cast<uint32_t*>(hs);
+  const int wq = w >> 2;
+  uint32_t* img32 = reinterpret_cast<uint32_t*>(img);
+  uint2* hs2 = reinterpret_cast<uint2*>(hs);
   for (int y = warp; y < h; y += 8) {
     const uint32_t* row32 = img32 + y * wq;
     for (int g = lane; g < wq; g += 32) {
@@ -518,26 +536,33 @@ __device__ __forceinline__ void blur_view_words(uint8_t* img, uint16_t* hs, int 
       // reflect-101 at the frame edge, expressed on bytes: pixel -j == pixel j, pixel w-1+j == pixel w-1-j
       if (g == 0) wl = __byte_perm(wc, wr, 0x1234);            // (p4, p3, p2, p1) stand in for pixels -4..-1
       if (g == wq - 1) wr = __byte_perm(row32[max(g - 1, 0)], wc, 0x3456);  // pixels w..w+3 = (w-2, w-3, w-4, w-5)
-      int s0, s1, s2, s3;
-      hsum4<R>(wl, wc, wr, s0, s1, s2, s3);
-      hs32[y * hw + 2 * g] = uint32_t(s0) | (uint32_t(s1) << 16);
-      hs32[y * hw + 2 * g + 1] = uint32_t(s2) | (uint32_t(s3) << 16);
+      uint32_t sa, sb;
+      hsum4_packed<R>(wl, wc, wr, sa, sb);
+      hs2[y * wq + g] = make_uint2(sa, sb);
     }
   }
   __syncthreads();
-  const int p0 = rl >> 1, p1 = (rl + cw + 1) >> 1;  // parent column pairs touching the view
-  for (int yy = warp; yy < ch; yy += 8) {
-    const int y = rt + yy;
-    int rows[K];
+  auto refl = [](int p, int n) { p = abs(p); return min(p, 2 * (n - 1) - p); };  // |overshoot| <= R < n
+  const int g0 = rl >> 2, ng = ((rl + cw + 3) >> 2) - g0;  // parent groups touching the view
+  const int ns = max(1, min(256 / ng, ch));                // row segments per group
+  const int seg_rows = (ch + ns - 1) / ns;
+  for (int it = threadIdx.x; it < ng * ns; it += 256) {
+    const int seg = it / ng, g = g0 + it - seg * ng;
+    const int ya = rt + seg * seg_rows, yb = min(rt + ch, ya + seg_rows);  // parent rows [ya, yb)
+    if (ya >= yb) continue;
+    uint32_t va = 0, vb = 0;
 #pragma unroll
-    for (int d = 0; d < K; ++d) rows[d] = reflect101(y + d - R, h) * hw;
-    for (int p = p0 + lane; p < p1; p += 32) {
-      uint32_t acc = 0;
-#pragma unroll
-      for (int d = 0; d < K; ++d) acc += hs32[rows[d] + p];  // two u16 lanes, max 255*49 each: no carry
-      const int x = 2 * p - rl;
-      if (x >= 0 && x < cw) img[yy * cw + x] = uint8_t(blur_round(int(acc & 0xFFFFu), K));
-      if (x + 1 >= 0 && x + 1 < cw) img[yy * cw + x + 1] = uint8_t(blur_round(int(acc >> 16), K));
+    for (int d = -R; d <= R; ++d) {
+      const uint2 e = hs2[refl(ya + d, h) * wq + g];
+      va += e.x;
+      vb += e.y;
+    }
+    for (int y = ya;;) {
+      img32[y * wq + g] = blur_round4<K>(va, vb);
+      if (++y >= yb) break;
+      const uint2 in = hs2[refl(y + R, h) * wq + g], out = hs2[refl(y - 1 - R, h) * wq + g];
+      va = va + in.x - out.x;
+      vb = vb + in.y - out.y;
     }
   }
   __syncthreads();
@@ -654,9 +679,7 @@ __global__ void __launch_bounds__(256)
   if (k && (w & 3) == 0) {
     if (k == 3) blur_view_words<1>(img, hs, w, h, rl, rt, cw, ch);
     else if (k == 5) blur_view_words<2>(img, hs, w, h, rl, rt, cw, ch);
-    else blur_view_words<3>(img, hs, w, h, rl, rt, cw, ch);
-    bl = img;
-    bl_stride = cw;
+    else blur_view_words<3>(img, hs, w, h, rl, rt, cw, ch);  // blurred in place: bl / bl_stride stay the parent's
   } else if (k) {
     const int r = k >> 1;
     for (int y = warp; y < h; y += 8) {  // horizontal sums for every parent row, view columns
@@ -761,9 +784,6 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
   // Running vertical sums of the 4 pixels as packed u16 pairs (s0,s2) and (s1,s3): every lane stays below
   // 49*255 < 2^16 and "add the new row, then drop the old one" never borrows across lanes.
   uint32_t va = 0, vb = 0;
-  constexpr uint32_t kM = K == 7 ? 342393u : (K == 5 ? 671089u : 1864136u);  // ceil(2^24 / K^2)
-  constexpr uint32_t kC = uint32_t(K * K / 2) * kM;  // nearest integer of s / K^2 == ((s + K^2/2) * kM) >> 24, exact for
-                                                    // s <= 255 K^2 (and the product fits 32 bits)
   uint32_t* slot = ring + 2 * tid;  // my slot of the ring row written this step
   int ring_row = 0;
   for (int j = 0; j < steps; ++j) {
@@ -782,14 +802,8 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
       const uint32_t wc = rw[tid + 1];
       if (left_edge) wl = __byte_perm(wc, wr, 0x1234);   // pixels -4..-1 = pixels 4, 3, 2, 1
       if (right_edge) wr = __byte_perm(wl, wc, 0x3456);  // pixels w..w+3 = pixels w-2, w-3, w-4, w-5
-      const uint32_t w2 = __funnelshift_r(wl, wc, 16), w6 = __funnelshift_r(wc, wr, 16);
-      constexpr uint32_t kLanes = 0x00FF00FFu;
-      const uint32_t q[10] = {wl & kLanes, (wl >> 8) & kLanes, w2 & kLanes, (w2 >> 8) & kLanes, wc & kLanes,
-                              (wc >> 8) & kLanes, w6 & kLanes, (w6 >> 8) & kLanes, wr & kLanes, (wr >> 8) & kLanes};
-      uint32_t sa = 0;  // (s0, s2): box sums of pixels 4 and 6
-#pragma unroll
-      for (int i = 4 - R; i <= 4 + R; ++i) sa += q[i];
-      const uint32_t sb = sa + q[5 + R] - q[4 - R];  // (s1, s3)
+      uint32_t sa, sb;  // (s0, s2) and (s1, s3)
+      hsum4_packed<R>(wl, wc, wr, sa, sb);
       va += sa;
       vb += sb;
       if (j >= K) {  // drop the row that leaves the window
@@ -805,14 +819,7 @@ __device__ __forceinline__ void band_body(const uint8_t* __restrict__ src, long 
         slot += 2 * (kBandSegMax / 4);
       }
       if (j >= 2 * R) {
-        uint32_t px;
-        if (R == 0) {
-          px = wc;
-        } else {
-          const uint32_t p0 = (va & 0xFFFFu) * kM + kC, p2 = (va >> 16) * kM + kC;
-          const uint32_t p1 = (vb & 0xFFFFu) * kM + kC, p3 = (vb >> 16) * kM + kC;
-          px = __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);  // byte 3 of each
-        }
+        const uint32_t px = R == 0 ? wc : blur_round4<K>(va, vb);
         reinterpret_cast<uint32_t*>(bl + (j - 2 * R) * bl_stride)[tid] = px;
       }
     }

@@ -1,5 +1,7 @@
 """device-resident timing of the video-frame hash path (128x128 frames, autocrop + blur + area + hash)."""
 import ctypes as C
+import sys
+sys.path.insert(0, ".")
 import numpy as np, torch
 import cbird_b200 as cb
 from cbird_b200 import synth
