@@ -584,8 +584,25 @@ __global__ void __launch_bounds__(256)
 
   const uint8_t* src = frames + (long long)blockIdx.x * frame_stride;
   const int tid = threadIdx.x;
-  // 1. frame -> shared memory
-  if ((w & 3) == 0 && (row_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+  // 1. frame -> shared memory (16-byte loads, four in flight per thread, when the geometry allows)
+  if ((w & 15) == 0 && (row_stride & 15) == 0 && (((reinterpret_cast<uintptr_t>(src) | (img - smem_raw)) & 15) == 0)) {
+    const int wv = w >> 4, total = h * wv;
+    uint4* img128 = reinterpret_cast<uint4*>(img);
+    for (int i0 = tid; i0 < total; i0 += 4 * 256) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < total) {
+          const int y = i / wv, xv = i - y * wv;
+          v[u] = __ldg(reinterpret_cast<const uint4*>(src + (long long)y * row_stride) + xv);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 256 < total) img128[i0 + u * 256] = v[u];
+    }
+  } else if ((w & 3) == 0 && (row_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
     const int wq = w >> 2;
     uint32_t* img32 = reinterpret_cast<uint32_t*>(img);
     for (int y = tid >> 5; y < h; y += 8) {
@@ -711,8 +728,20 @@ __global__ void __launch_bounds__(256)
   if (amode == 3 && tid < 64) s_taps[tid] = tid < 32 ? make_taps(tid, cw, cw / 32.0) : make_taps(tid - 32, ch, ch / 32.0);
   __syncthreads();
   auto px = [&](int y, int x) { return bl[y * bl_stride + x]; };
-  for (int i = tid; i < 1024; i += 256)
-    tile[i] = amode == 3 ? area_pixel_taps(px, s_taps[i & 31], s_taps[32 + (i >> 5)]) : area_pixel_fast(px, amode, ix, iy, i & 31, i >> 5);
+  if (amode == 2 && (ix & 3) == 0 && (((bl - img) | bl_stride) & 3) == 0) {
+    // integer scale with whole words per cell: the exact integer cell sum, four pixels per __dp4a
+    const float inv = __fdiv_rn(1.f, float(ix * iy));
+    for (int i = tid; i < 1024; i += 256) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(bl + (i >> 5) * iy * bl_stride + (i & 31) * ix);
+      unsigned sum = 0;
+      for (int j = 0; j < iy; ++j, p += bl_stride >> 2)
+        for (int k = 0; k < (ix >> 2); ++k) sum = __dp4a(p[k], 0x01010101u, sum);
+      tile[i] = uint8_t(min(255, max(0, __float2int_rn(__fmul_rn(float(int(sum)), inv)))));
+    }
+  } else {
+    for (int i = tid; i < 1024; i += 256)
+      tile[i] = amode == 3 ? area_pixel_taps(px, s_taps[i & 31], s_taps[32 + (i >> 5)]) : area_pixel_fast(px, amode, ix, iy, i & 31, i >> 5);
+  }
   __syncthreads();
 
   // 5. hash
