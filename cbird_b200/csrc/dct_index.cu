@@ -5,6 +5,7 @@
 // are mirrored in HBM and every search is a brute-force scan (scan64.cu), so add() is an append and
 // remove() a row rewrite.  Results are exact radius sets, like the VP tree's.
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <unordered_set>
@@ -38,6 +39,76 @@ __global__ void hits_to_matches(const cb_pair* __restrict__ pairs, unsigned long
   if (keep) atomicAdd(n_valid, 1ull);
 }
 
+// Database::searchIndex's post step (database.cpp:1703-1737) for every needle row of a -similar pass, on the
+// sorted hit list: maxThresh escalation, filterSelf, maxMatches. One thread per needle row.
+struct SimilarPost {
+  int dht, max_thresh, min_matches, max_matches, filter_self, escalate;
+};
+
+__global__ void similar_post_count(const cb_hit* __restrict__ hits, unsigned long long n_hits,
+                                   const uint64_t* __restrict__ row_hash, const uint32_t* __restrict__ row_id, uint32_t n,
+                                   SimilarPost P, unsigned long long* __restrict__ begin, int* __restrict__ thr,
+                                   long long* __restrict__ kept) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row > n) return;
+  if (row == n) {  // the scan's last slot: offsets[n] = total
+    kept[n] = 0;
+    return;
+  }
+  unsigned long long lo = 0, hi = n_hits;  // first hit of this needle (hits are sorted by needle, score, id)
+  while (lo < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    if (hits[mid].needle < row) lo = mid + 1; else hi = mid;
+  }
+  begin[row] = lo;
+  int t = P.dht;
+  long long k = 0;
+  if (row_hash[row] != 0) {  // needles without hash find nothing (dcthashindex.cpp:196-200)
+    unsigned long long j = lo;
+    if (P.escalate) {
+      // the reference re-runs find() with dht+1, dht+2, ... while the needle has <= minMatches matches (self
+      // included) and the threshold stays <= maxThresh (:1703-1725)
+      long long cnt = 0;
+      for (;;) {
+        while (j < n_hits && hits[j].needle == row && hits[j].score < t) ++j, ++cnt;
+        if (cnt > P.min_matches || t + 1 > P.max_thresh) break;
+        ++t;
+      }
+    }
+    const uint32_t self = row_id[row];
+    for (j = lo; j < n_hits && k < P.max_matches; ++j) {
+      const cb_hit h = hits[j];
+      if (h.needle != row || h.score >= t) break;
+      if (P.filter_self && h.mediaId == self) continue;
+      ++k;
+    }
+  }
+  thr[row] = t;
+  kept[row] = k;
+}
+
+__global__ void similar_post_scatter(const cb_hit* __restrict__ hits, unsigned long long n_hits,
+                                     const uint32_t* __restrict__ row_id, uint32_t n, SimilarPost P,
+                                     const unsigned long long* __restrict__ begin, const int* __restrict__ thr,
+                                     const long long* __restrict__ kept, const long long* __restrict__ offsets,
+                                     cb_hit* __restrict__ out) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const long long want = kept[row];
+  if (!want) return;
+  const uint32_t self = row_id[row];
+  const int t = thr[row];
+  cb_hit* dst = out + offsets[row];
+  long long k = 0;
+  for (unsigned long long j = begin[row]; k < want; ++j) {
+    const cb_hit h = hits[j];
+    if (P.filter_self && h.mediaId == self) continue;
+    dst[k++] = h;
+  }
+  (void)n_hits;
+  (void)t;
+}
+
 struct HitLess {
   __device__ __forceinline__ bool operator()(const cb_hit& x, const cb_hit& y) const {
     if (x.needle != y.needle) return x.needle < y.needle;
@@ -65,6 +136,10 @@ struct DctIndex {
   DevBuf<cb_hit> d_hits;
   DevBuf<unsigned char> d_temp;
   DevBuf<unsigned long long> d_counts;  // [0] scan count, [1] valid count
+  DevBuf<unsigned long long> d_post_begin;  // -similar post step scratch
+  DevBuf<int> d_post_thr;
+  DevBuf<long long> d_post_kept, d_post_off;
+  DevBuf<cb_hit> d_post_out;
   unsigned long long* h_counts = nullptr;  // pinned
   // pinned staging for the latency path (few needles, few hits): needles in, first raw hits out
   static constexpr size_t kStageNeedles = 1024, kStagePairs = 4096;
@@ -310,14 +385,9 @@ int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, i
   return (out && k > cap) ? CB_ERR_CAPACITY : CB_OK;
 }
 
-struct RawHits {  // malloc'ed result buffer handed to the caller (cb_free) without another copy
-  cb_hit* p = nullptr;
-  size_t n = 0;
-};
-
 static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int threshold, int64_t row_begin,
                           int64_t row_end, bool self_needles, bool filter_self, std::vector<cb_hit>& out,
-                          bool symmetric_ok = false, RawHits* raw = nullptr) {
+                          bool symmetric_ok = false) {
   out.clear();
   if (!I.loaded) {
     set_error("index not loaded");
@@ -349,21 +419,6 @@ static int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int 
                        (self_needles && filter_self) ? I.d_ids.p : nullptr, 0, &n_valid, latency_path ? &out : nullptr,
                        &on_host, symmetric);
   if (rc != CB_OK) return rc;
-  if (raw) {
-    raw->n = on_host ? out.size() : size_t(n_valid);
-    raw->p = static_cast<cb_hit*>(malloc(std::max<size_t>(1, raw->n) * sizeof(cb_hit)));
-    if (!raw->p) {
-      set_error("out of host memory");
-      return CB_ERR_INVALID;
-    }
-    if (on_host) {
-      if (raw->n) memcpy(raw->p, out.data(), raw->n * sizeof(cb_hit));
-    } else if (raw->n) {
-      CB_CUDA(cudaMemcpyAsync(raw->p, I.d_hits.p, raw->n * sizeof(cb_hit), cudaMemcpyDeviceToHost, I.stream));
-      CB_CUDA(cudaStreamSynchronize(I.stream));
-    }
-    return CB_OK;
-  }
   if (on_host) return CB_OK;
   out.resize(n_valid);
   if (n_valid) {
@@ -462,55 +517,68 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   const int dht = p->dctThresh;
   const bool escalate = p->maxThresh > 0 && p->maxThresh > dht;
   const int scan_thresh = escalate ? p->maxThresh : dht;
-  std::vector<cb_hit> scratch;
-  RawHits raw;
-  int rc = run_find_batch(I, nullptr, 0, scan_thresh, 0, n, true, false, scratch, true, &raw);
-  if (rc != CB_OK) {
-    free(raw.p);
-    return rc;
+  if (!I.loaded) {
+    set_error("index not loaded");
+    return CB_ERR_NOT_LOADED;
   }
-  cb_hit* hits = raw.p;
-  const size_t n_hits = raw.n;
-  // searchIndex post step (database.cpp:1729-1737): hits are already sorted by (needle, score, id);
-  // drop the needle itself when filterSelf, cut every needle's list at maxMatches. Needles without
-  // hash find nothing. Compaction happens in place in the buffer that is handed to the caller.
+  CB_CUDA(cudaSetDevice(I.device));
+  int rc = I.sync_to_device();
+  if (rc != CB_OK) return rc;
+  unsigned long long n_valid = 0;
+  rc = I.search_device(I.d_hashes.p, uint32_t(n), 0, uint32_t(n), scan_thresh, nullptr, 0, &n_valid, nullptr, nullptr, true);
+  if (rc != CB_OK) return rc;
+  // searchIndex post step (database.cpp:1729-1737) on the device: d_hits is sorted by (needle, score, id);
+  // per needle row pick the effective threshold, drop the needle itself when filterSelf, cut at maxMatches,
+  // then an exclusive scan of the kept counts gives the offsets and a scatter packs the lists.
+  SimilarPost P{dht, p->maxThresh, p->minMatches, p->maxMatches < 0 ? 0 : p->maxMatches, p->filterSelf ? 1 : 0,
+                escalate ? 1 : 0};
   int64_t* offsets = static_cast<int64_t*>(malloc(size_t(n + 1) * sizeof(int64_t)));
   if (!offsets) {
-    free(raw.p);
     set_error("out of host memory");
     return CB_ERR_INVALID;
   }
-  const int64_t max_matches = p->maxMatches < 0 ? 0 : p->maxMatches;
-  const bool filter_self = p->filterSelf != 0;
-  const uint64_t* row_hash = I.hashes.data();
-  const uint32_t* row_id = I.ids.data();
-  size_t w = 0, i = 0;
-  for (int64_t row = 0; row < n; ++row) {
-    offsets[row] = int64_t(w);
-    size_t j = i;
-    while (j < n_hits && int64_t(hits[j].needle) == row) ++j;
-    if (row_hash[row] != 0) {
-      int t = dht;  // effective threshold of this needle
-      if (escalate) {
-        for (;;) {
-          size_t cnt = 0;
-          for (size_t k = i; k < j && hits[k].score < t; ++k) ++cnt;
-          if (int64_t(cnt) > p->minMatches || t + 1 > p->maxThresh) break;
-          ++t;
-        }
-      }
-      int64_t kept = 0;
-      for (size_t k = i; k < j && hits[k].score < t; ++k) {
-        if (filter_self && hits[k].mediaId == row_id[row]) continue;
-        if (kept >= max_matches) break;
-        if (w != k) hits[w] = hits[k];
-        ++w;
-        ++kept;
-      }
+  offsets[0] = 0;
+  size_t w = 0;
+  cb_hit* hits = nullptr;
+  auto fail = [&](int code) {
+    free(offsets);
+    free(hits);
+    return code;
+  };
+  if (n > 0) {
+    if ((rc = I.d_post_begin.reserve(size_t(n))) != CB_OK || (rc = I.d_post_thr.reserve(size_t(n))) != CB_OK ||
+        (rc = I.d_post_kept.reserve(size_t(n) + 1)) != CB_OK || (rc = I.d_post_off.reserve(size_t(n) + 1)) != CB_OK ||
+        (rc = I.d_post_out.reserve(std::max<size_t>(1, size_t(n_valid)))) != CB_OK || (rc = I.d_hits.reserve(1)) != CB_OK)
+      return fail(rc);
+    const unsigned blocks = unsigned((n + 1 + 255) / 256);
+    similar_post_count<<<blocks, 256, 0, I.stream>>>(I.d_hits.p, n_valid, I.d_hashes.p, I.d_ids.p, uint32_t(n), P,
+                                                    I.d_post_begin.p, I.d_post_thr.p, I.d_post_kept.p);
+    if (cudaGetLastError() != cudaSuccess) return fail(cuda_fail(cudaPeekAtLastError(), "similar_post_count", __FILE__, __LINE__));
+    size_t tb = 0;
+    cudaError_t ce = cub::DeviceScan::ExclusiveSum(nullptr, tb, I.d_post_kept.p, I.d_post_off.p, int(n + 1), I.stream);
+    if (ce == cudaSuccess && (rc = I.d_temp.reserve(tb + 16)) != CB_OK) return fail(rc);
+    if (ce == cudaSuccess) ce = cub::DeviceScan::ExclusiveSum(I.d_temp.p, tb, I.d_post_kept.p, I.d_post_off.p, int(n + 1), I.stream);
+    if (ce == cudaSuccess) {
+      similar_post_scatter<<<blocks, 256, 0, I.stream>>>(I.d_hits.p, n_valid, I.d_ids.p, uint32_t(n), P, I.d_post_begin.p,
+                                                        I.d_post_thr.p, I.d_post_kept.p, I.d_post_off.p, I.d_post_out.p);
+      ce = cudaGetLastError();
     }
-    i = j;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(offsets, I.d_post_off.p, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, I.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(I.stream);
+    if (ce != cudaSuccess) return fail(cuda_fail(ce, "similar post step", __FILE__, __LINE__));
+    counters().launches += 3;
+    w = size_t(offsets[n]);
   }
-  offsets[n] = int64_t(w);
+  hits = static_cast<cb_hit*>(malloc(std::max<size_t>(1, w) * sizeof(cb_hit)));
+  if (!hits) {
+    set_error("out of host memory");
+    return fail(CB_ERR_INVALID);
+  }
+  if (w) {
+    cudaError_t ce = cudaMemcpyAsync(hits, I.d_post_out.p, w * sizeof(cb_hit), cudaMemcpyDeviceToHost, I.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(I.stream);
+    if (ce != cudaSuccess) return fail(cuda_fail(ce, "similar result copy", __FILE__, __LINE__));
+  }
   *hits_out = hits;
   *n_hits_out = int64_t(w);
   *offsets_out = offsets;
