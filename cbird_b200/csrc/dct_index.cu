@@ -302,11 +302,23 @@ int cb_dct_index_load(cb_dct_index* ix, const uint32_t* ids, const uint64_t* has
   std::lock_guard<std::mutex> lock(I.mu);
   int rc = I.init_device();
   if (rc != CB_OK) return rc;
+  // upload straight from the caller's arrays (full PCIe rate when they are pinned) while the host copies are
+  // made; the stream is drained before returning because the caller may reuse its buffers
+  CB_CUDA(cudaSetDevice(I.device));
+  rc = I.d_hashes.reserve(size_t(n) + 2);
+  if (rc == CB_OK) rc = I.d_ids.reserve(size_t(n) + 2);
+  if (rc != CB_OK) return rc;
+  if (n) {
+    CB_CUDA(cudaMemcpyAsync(I.d_hashes.p, hashes, size_t(n) * 8, cudaMemcpyHostToDevice, I.stream));
+    CB_CUDA(cudaMemcpyAsync(I.d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, I.stream));
+  }
   I.hashes.assign(hashes, hashes + n);
   I.ids.assign(ids, ids + n);
   I.loaded = true;
-  I.dirty = true;
-  return I.sync_to_device();
+  I.d_rows = size_t(n);
+  I.dirty = false;
+  CB_CUDA(cudaStreamSynchronize(I.stream));
+  return CB_OK;
 }
 
 int cb_dct_index_is_loaded(const cb_dct_index* ix) { return ix && ix->impl.loaded ? 1 : 0; }
