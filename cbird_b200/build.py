@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcbird_b200.so")
-SOURCES = ["common.cu", "scan64.cu", "dct_index.cu", "dct_hash.cu", "video_index.cu", "knn256.cu", "vdx.cu", "hamming_tree.cu"]
+SOURCES = ["common.cu", "scan64.cu", "dct_index.cu", "dct_hash.cu", "video_index.cu", "knn256.cu", "vdx.cu", "hamming_tree.cu", "mih.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -82,4 +82,33 @@ int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint
                         cudaStream_t stream);
 int scan64_variant_for(int threshold);
 
+// ---- multi-index (pigeonhole) self-join, mih.cu ------------------------------------------------
+constexpr int kMihMaxThreshold = 10;  // above this the buckets get too coarse to beat the brute-force scan
+struct MihPlan {  // chunk c of a hash = (h >> shift[c]) & mask[c]
+  int chunks;
+  int shift[kMihMaxThreshold];
+  uint32_t mask[kMihMaxThreshold];
+};
+struct MihEmit {  // what the tile-list kernel needs to report MIH hits: sorted position -> row, -> key, the plan
+  const uint32_t* rows;
+  const uint32_t* keys;
+  MihPlan plan;
+};
+struct MihWorkspace {
+  DevBuf<uint32_t> key, key2, val, val2, ofs, n_small, n_big, small_at, big_at;
+  DevBuf<uint64_t> sorted;
+  DevBuf<cb_scan_tile> small_tiles, big_tiles;
+  DevBuf<unsigned char> temp;
+  DevBuf<unsigned long long> info;  // [0] small items, [1] tile-list items, [2] pair tests, [3] kept (row, chunk) items
+  unsigned long long* h_info = nullptr;
+  ~MihWorkspace();
+};
+MihPlan mih_plan(int threshold);
+bool mih_applicable(uint64_t n, int threshold);
+int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, cb_pair* out,
+                    unsigned long long cap, unsigned long long* d_count, MihWorkspace& ws, unsigned long long max_tests,
+                    int* declined, cudaStream_t stream);
+int scan64_tiles_mih_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, const MihEmit& E,
+                            cudaStream_t stream);
+
 }  // namespace cbird

@@ -136,6 +136,7 @@ struct DctIndex {
   DevBuf<cb_hit> d_hits;
   DevBuf<unsigned char> d_temp;
   DevBuf<unsigned long long> d_counts;  // [0] scan count, [1] valid count
+  MihWorkspace mih;                         // multi-index self-join scratch (mih.cu)
   DevBuf<unsigned long long> d_post_begin;  // -similar post step scratch
   DevBuf<int> d_post_thr;
   DevBuf<long long> d_post_kept, d_post_off;
@@ -200,13 +201,28 @@ struct DctIndex {
     unsigned long long guess = symmetric_self ? 3ull * n_rows : 2ull * n_q + (1ull << 16);
     guess = std::min<unsigned long long>(std::max<unsigned long long>(guess, 1ull << 20), 1ull << 28);
     unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, guess);
+    static const bool no_mih = getenv("CB_NO_MIH") != nullptr;  // measurement / parity aid: brute-force scan only
+    bool mih_declined = no_mih;
     for (int attempt = 0; attempt < 3; ++attempt) {
       int rc = d_pairs.reserve(cap);
       if (rc != CB_OK) return rc;
       cap = d_pairs.cap;
       CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 2 * sizeof(unsigned long long), stream));
       Scan64Launch L;
-      if (symmetric_self) {
+      if (symmetric_self && !mih_declined && mih_applicable(n_rows, threshold)) {
+        // small thresholds: multi-index self-join (same hit set from a fraction of the pair tests); declined
+        // when the buckets are so skewed that it would cost more than half of the symmetric brute-force scan
+        int declined = 0;
+        rc = scan64_self_mih(d_hashes.p, n_rows, threshold, 0, 1, d_pairs.p, cap, d_counts.p, mih,
+                             (unsigned long long)n_rows * n_rows / 4, &declined, stream);
+        if (rc != CB_OK) return rc;
+        mih_declined = declined != 0;
+      } else {
+        mih_declined = true;
+      }
+      if (!mih_declined) {
+        // hits are in d_pairs / d_counts already
+      } else if (symmetric_self) {
         // `-similar` over the whole index: d(a,b) == d(b,a), so only tiles on/above the diagonal are
         // tested and every off-diagonal hit is emitted in both orders (half the pair tests)
         L = Scan64Launch{d_hashes.p, n_rows, d_hashes.p, n_rows, threshold, 0, d_pairs.p, cap, d_counts.p, 0, true};
@@ -215,8 +231,10 @@ struct DctIndex {
       } else {
         L = Scan64Launch{d_q, n_q, d_hashes.p + row_begin, n_rows, threshold, 0, d_pairs.p, cap, d_counts.p};
       }
-      rc = scan64_launch(L, stream);
-      if (rc != CB_OK) return rc;
+      if (mih_declined) {
+        rc = scan64_launch(L, stream);
+        if (rc != CB_OK) return rc;
+      }
       CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
       if (host_small && attempt == 0)
         CB_CUDA(cudaMemcpyAsync(h_stage_pairs, d_pairs.p, std::min<size_t>(kStagePairs, cap) * sizeof(cb_pair),

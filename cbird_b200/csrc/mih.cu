@@ -1,0 +1,301 @@
+// Exact all-pairs Hamming radius self-join by multi-index hashing (pigeonhole), for small thresholds.
+//
+// `-similar` over a DctHashIndex asks for every ordered pair (a, b) with hamm64 < T
+// (src/database.cpp:1400-1432 -> DctHashIndex::find per needle, src/dcthashindex.cpp:193-220). The
+// reference prunes with a VP tree per needle; the brute-force kernel (scan64.cu) tests every pair. For
+// small T there is an exact shortcut: bit 0 of a dct hash is always clear (src/cvutil.cpp:537-538), so the
+// 63 usable bits are cut into T chunks, and two hashes that differ in fewer than T bits agree EXACTLY on at
+// least one chunk. Rows are bucketed by the (first <=16 bits of the) chunk value, once per chunk, and only
+// rows sharing a bucket are compared: T * sum(bucket^2) pair tests instead of n^2 (2^20 uniformly random
+// rows, T = 5: 6.7e8 instead of 1.1e12). A pair that shares a bucket in several chunks is reported by the
+// first of them only, so the hit set is exactly the brute-force one (self pairs included, each once).
+//
+//   keys    (chunk << 16 | bucket, row) for every chunk of every row        mih_keys_kernel
+//   sort    one stable LSD radix sort over all chunks                         cub::DeviceRadixSort
+//   gather  hashes in bucket order (bucket-contiguous, like the video index)   mih_gather_kernel
+//   bounds  bucket boundaries by binary search, tile list by exclusive scan    mih_bounds/tiles kernels
+//   scan    small buckets: one CTA per bucket, B side in shared memory, OR-fold pre-filter + exact recheck
+//           large buckets: the tuned tile-list kernel of scan64.cu (<= 2048 A rows x bucket)
+//
+// Multi-GPU: buckets are dealt to ranks ((bucket + chunk) % n_parts); every rank sorts and scans only its
+// own buckets, and the per-rank hit lists are disjoint by construction.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace cbird {
+
+namespace {
+
+constexpr int kSmallThreads = 128;
+constexpr uint32_t kSmallMax = 512;   // buckets up to this many rows take the small-bucket kernel
+constexpr uint32_t kBigABlock = 2048;  // A rows per work item of the tile-list kernel
+
+__global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, MihPlan plan, uint32_t part,
+                                uint32_t n_parts, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
+                                unsigned long long* __restrict__ counter) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint64_t h = live ? hash[i] : 0;
+  const unsigned lane = threadIdx.x & 31;
+  for (int c = 0; c < plan.chunks; ++c) {
+    const uint32_t k = uint32_t(h >> plan.shift[c]) & plan.mask[c];
+    if (n_parts == 1) {
+      if (live) {
+        key[size_t(c) * n + i] = (uint32_t(c) << 16) | k;
+        val[size_t(c) * n + i] = i;
+      }
+      continue;
+    }
+    const bool mine = live && (k + uint32_t(c)) % n_parts == part;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);  // one atomic per warp and chunk
+    if (!m) continue;
+    unsigned long long base = 0;
+    if (lane == unsigned(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (mine) {
+      const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+      key[at] = (uint32_t(c) << 16) | k;
+      val[at] = i;
+    }
+  }
+}
+
+__global__ void mih_gather_kernel(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ rows, uint32_t m,
+                                  uint64_t* __restrict__ sorted) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) sorted[j] = hash[rows[j]];
+}
+
+// ofs[k] = first sorted position whose key is >= k, k in [0, n_buckets]
+__global__ void mih_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t m, uint32_t n_buckets,
+                                  uint32_t* __restrict__ ofs) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_buckets) return;
+  uint32_t lo = 0, hi = m;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (sorted_key[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  ofs[k] = lo;
+}
+
+// work items per bucket: small buckets -> 1 item of the small kernel; large ones -> ceil(s / 2048) tile-list items
+__global__ void mih_tile_counts_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, uint32_t* __restrict__ n_small,
+                                       uint32_t* __restrict__ n_big, unsigned long long* __restrict__ info) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long tests = 0;
+  if (k <= n_buckets) {
+    uint32_t s = 0;
+    if (k < n_buckets) s = ofs[k + 1] - ofs[k];
+    n_small[k] = (s > 0 && s <= kSmallMax) ? 1u : 0u;
+    n_big[k] = s > kSmallMax ? (s + kBigABlock - 1) / kBigABlock : 0u;
+    tests = (unsigned long long)s * s;
+  }
+  // pair tests of the whole pass (block reduction, one atomic per CTA)
+  __shared__ unsigned long long red[8];
+  for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tests;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) t += red[w];
+    if (t) atomicAdd(info + 2, t);
+  }
+}
+
+__global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets,
+                                      const uint32_t* __restrict__ small_at, const uint32_t* __restrict__ big_at,
+                                      cb_scan_tile* __restrict__ small_tiles, cb_scan_tile* __restrict__ big_tiles,
+                                      unsigned long long* __restrict__ info) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_buckets) return;
+  if (k == n_buckets) {  // the exclusive scans end here: totals
+    info[0] = small_at[k];
+    info[1] = big_at[k];
+    return;
+  }
+  const uint32_t b0 = ofs[k], s = ofs[k + 1] - b0;
+  if (s == 0) return;
+  if (s <= kSmallMax) {
+    small_tiles[small_at[k]] = cb_scan_tile{b0, s, b0, s};
+  } else {
+    const uint32_t at = big_at[k];
+    for (uint32_t t = 0, a = 0; a < s; ++t, a += kBigABlock)
+      big_tiles[at + t] = cb_scan_tile{b0 + a, min(kBigABlock, s - a), b0, s};
+  }
+}
+
+// One CTA per small bucket (<= 512 rows): the bucket goes to shared memory once, thread t owns rows
+// t, t+128, ... as the A side, and every (A, B) pair is pre-filtered with popc((alo^blo)|(ahi^bhi)) <= distance
+// (1 POPC per pair) before the exact test. Hits leave as original row numbers, and only from the first chunk
+// in which the pair shares a bucket.
+__global__ void __launch_bounds__(kSmallThreads)
+    mih_small_kernel(const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ rows,
+                     const uint32_t* __restrict__ keys, const cb_scan_tile* __restrict__ tiles, MihPlan plan,
+                     int threshold, cb_pair* __restrict__ out, unsigned long long cap,
+                     unsigned long long* __restrict__ count) {
+  __shared__ uint2 sb[kSmallMax];
+  const cb_scan_tile t = tiles[blockIdx.x];
+  const uint32_t s = t.b_count;
+  for (uint32_t i = threadIdx.x; i < s; i += kSmallThreads) {
+    const uint64_t v = sorted[t.b_begin + i];
+    sb[i] = make_uint2(uint32_t(v), uint32_t(v >> 32));
+  }
+  __syncthreads();
+  const int chunk = int(keys[t.b_begin] >> 16);
+  for (uint32_t a = threadIdx.x; a < s; a += kSmallThreads) {
+    const uint2 av = sb[a];
+    for (uint32_t b = 0; b < s; ++b) {
+      const uint2 bv = sb[b];  // broadcast read
+      const uint32_t xlo = av.x ^ bv.x, xhi = av.y ^ bv.y;
+      if (int(__popc(xlo | xhi)) >= threshold) continue;
+      const int d = __popc(xlo) + __popc(xhi);
+      if (d >= threshold) continue;
+      const uint64_t x = (uint64_t(xhi) << 32) | xlo;
+      bool first = true;
+      for (int c = 0; c < chunk; ++c)
+        if (((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) first = false;
+      if (!first) continue;
+      const unsigned long long pos = atomicAdd(count, 1ull);
+      if (pos < cap)
+        *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[t.b_begin + a], rows[t.b_begin + b], uint32_t(d), 0u);
+    }
+  }
+}
+
+}  // namespace
+
+MihPlan mih_plan(int threshold) {
+  MihPlan p;
+  const int chunks = std::max(1, std::min(threshold, kMihMaxThreshold));
+  p.chunks = chunks;
+  const int base = 63 / chunks, rem = 63 % chunks;
+  int start = 1;  // bit 0 of a dct hash carries no information (src/cvutil.cpp:537-538)
+  for (int c = 0; c < kMihMaxThreshold; ++c) {
+    const int len = c < chunks ? base + (c < rem ? 1 : 0) : 0;
+    p.shift[c] = c < chunks ? start : 0;
+    p.mask[c] = c < chunks ? ((1u << std::min(len, 16)) - 1u) : 0u;
+    start += len;
+  }
+  return p;
+}
+
+bool mih_applicable(uint64_t n, int threshold) {
+  return threshold >= 1 && threshold <= kMihMaxThreshold && n >= (1u << 15) &&
+         n * uint64_t(threshold) < 0xFFFF0000ull;
+}
+
+MihWorkspace::~MihWorkspace() {
+  if (h_info) cudaFreeHost(h_info);
+}
+
+// every ordered pair (a, b), a == b included, with hamm64 < threshold whose first shared bucket belongs to
+// `part`; appended to out (count is always the total). *declined = 1 (nothing emitted) when the buckets are so
+// skewed that the pass would cost more than `max_tests` pair tests (0 = never decline).
+int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, cb_pair* out,
+                    unsigned long long cap, unsigned long long* d_count, MihWorkspace& ws, unsigned long long max_tests,
+                    int* declined, cudaStream_t stream) {
+  if (declined) *declined = 0;
+  if (n == 0 || threshold <= 0) return CB_OK;
+  if (threshold > kMihMaxThreshold || uint64_t(n) * uint64_t(threshold) >= 0xFFFF0000ull || n_parts == 0 || part >= n_parts) {
+    set_error("scan64_self_mih: threshold %d / %u rows / part %u of %u outside the supported range", threshold, n, part,
+              n_parts);
+    return CB_ERR_UNSUPPORTED;
+  }
+  const MihPlan plan = mih_plan(threshold);
+  const size_t total = size_t(n) * plan.chunks;
+  const uint32_t n_buckets = uint32_t(plan.chunks) << 16;
+  int rc;
+  if ((rc = ws.key.reserve(total)) != CB_OK || (rc = ws.key2.reserve(total)) != CB_OK || (rc = ws.val.reserve(total)) != CB_OK ||
+      (rc = ws.val2.reserve(total)) != CB_OK || (rc = ws.sorted.reserve(total + 2)) != CB_OK ||
+      (rc = ws.ofs.reserve(n_buckets + 2)) != CB_OK || (rc = ws.n_small.reserve(n_buckets + 2)) != CB_OK ||
+      (rc = ws.n_big.reserve(n_buckets + 2)) != CB_OK || (rc = ws.small_at.reserve(n_buckets + 2)) != CB_OK ||
+      (rc = ws.big_at.reserve(n_buckets + 2)) != CB_OK || (rc = ws.info.reserve(4)) != CB_OK)
+    return rc;
+  if (!ws.h_info) CB_CUDA(cudaMallocHost(&ws.h_info, 4 * sizeof(unsigned long long)));
+  CB_CUDA(cudaMemsetAsync(ws.info.p, 0, 4 * sizeof(unsigned long long), stream));
+  mih_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan, part, n_parts, ws.key.p, ws.val.p, ws.info.p + 3);
+  CB_CUDA(cudaGetLastError());
+  uint32_t m = uint32_t(total);
+  if (n_parts > 1) {  // only this rank's share of the (row, chunk) items was written
+    CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    m = uint32_t(ws.h_info[0]);
+  }
+  counters().launches += 1;
+  if (m == 0) return CB_OK;
+  int key_bits = 16;
+  while ((1 << (key_bits - 16)) < plan.chunks) ++key_bits;
+  size_t tb = 0, tb2 = 0;
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                          key_bits, stream));
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, ws.n_small.p, ws.small_at.p, int(n_buckets + 1), stream));
+  if ((rc = ws.temp.reserve(std::max(tb, tb2) + 16)) != CB_OK) return rc;
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(ws.temp.p, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                          key_bits, stream));
+  mih_gather_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_hashes, ws.val2.p, m, ws.sorted.p);
+  CB_CUDA(cudaGetLastError());
+  const unsigned bblocks = (n_buckets + 1 + 255) / 256;
+  mih_bounds_kernel<<<bblocks, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
+  CB_CUDA(cudaGetLastError());
+  mih_tile_counts_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.n_small.p, ws.n_big.p, ws.info.p);
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_small.p, ws.small_at.p, int(n_buckets + 1), stream));
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
+  // upper bounds of the two work lists: one item per non-empty small bucket, ceil(s/2048) per large one
+  const size_t max_small = std::min<size_t>(n_buckets, m), max_big = size_t(m) / kSmallMax + 1;
+  if ((rc = ws.small_tiles.reserve(max_small + 1)) != CB_OK || (rc = ws.big_tiles.reserve(max_big + 1)) != CB_OK) return rc;
+  mih_tile_write_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.small_at.p, ws.big_at.p, ws.small_tiles.p,
+                                                    ws.big_tiles.p, ws.info.p);
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  CB_CUDA(cudaStreamSynchronize(stream));
+  counters().launches += 5;
+  const uint32_t n_small = uint32_t(ws.h_info[0]), n_big = uint32_t(ws.h_info[1]);
+  const unsigned long long tests = ws.h_info[2];
+  if (max_tests && tests > max_tests) {
+    if (declined) *declined = 1;
+    return CB_OK;
+  }
+  if (n_small) {
+    mih_small_kernel<<<n_small, kSmallThreads, 0, stream>>>(ws.sorted.p, ws.val2.p, ws.key2.p, ws.small_tiles.p, plan, threshold,
+                                                           out, cap, d_count);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+  }
+  if (n_big) {
+    Scan64Launch L{ws.sorted.p, m, ws.sorted.p, m, threshold, 0, out, cap, d_count};
+    MihEmit E{ws.val2.p, ws.key2.p, plan};
+    rc = scan64_tiles_mih_launch(L, ws.big_tiles.p, n_big, E, stream);
+    if (rc != CB_OK) return rc;
+  }
+  counters().comparisons += tests;
+  return CB_OK;
+}
+
+}  // namespace cbird
+
+using namespace cbird;
+
+extern "C" {
+
+int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts,
+                           cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  if (!d_hashes || !d_count || (!d_out && cap)) {
+    set_error("cb_scan64_self_mih_dev: null pointer argument");
+    return CB_ERR_INVALID;
+  }
+  static thread_local MihWorkspace ws[16];  // per calling thread and device
+  return scan64_self_mih(d_hashes, n, threshold, part, n_parts, d_out, cap, d_count, ws[current_device() & 15], 0, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int cb_scan64_mih_max_threshold(void) { return kMihMaxThreshold; }
+
+}  // extern "C"

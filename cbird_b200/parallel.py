@@ -71,9 +71,14 @@ class ShardedSimilar:
     symmetric=True (default) uses d(a,b) == d(b,a): each rank tests only the 2048-row tiles on/above
     the diagonal of its shard and emits every off-diagonal hit in both orders — half the pair tests,
     the same merged hit set.
+    mih=True (default) switches to the multi-index self-join (cb_scan64_self_mih_dev) whenever the threshold
+    and row count allow it: the chunk buckets, not the rows, are dealt to the ranks, and the per-rank lists
+    are still disjoint with the same union. mih=False keeps the brute-force scan (measurement / parity).
     """
 
-    def __init__(self, n_rows: int, device: torch.device, cap: int = 1 << 22, symmetric: bool = True):
+    MIH_MIN_ROWS = 1 << 15
+
+    def __init__(self, n_rows: int, device: torch.device, cap: int = 1 << 22, symmetric: bool = True, mih: bool = True):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.n_rows = n_rows
@@ -87,8 +92,17 @@ class ShardedSimilar:
         self.pairs = torch.empty((cap, 4), dtype=torch.int32, device=device)
         self.count = torch.zeros(1, dtype=torch.int64, device=device)
         self._L = lib()
+        self.mih = mih
+        self.last_path = None  # "mih" or "scan": what the last scan_local used
+
+    def uses_mih(self, threshold: int) -> bool:
+        t = int(threshold)
+        return (self.mih and 1 <= t <= self._L.cb_scan64_mih_max_threshold() and self.n_rows >= self.MIH_MIN_ROWS
+                and self.n_rows * t < 0xFFFF0000)
 
     def issued_pair_tests(self) -> int:
+        """pair tests of the brute-force scan of this rank's shard (the multi-index path issues far fewer; the
+        library counts them, cb_stats.comparisons)."""
         return issued_pair_tests(self.n_rows, self.begin, self.end, self.symmetric)
 
     def scan_local(self, d_hashes: torch.Tensor, threshold: int) -> torch.Tensor:
@@ -98,7 +112,13 @@ class ShardedSimilar:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         while True:
             self.count.zero_()
-            if self.end > self.begin:
+            if self.uses_mih(threshold):
+                self.last_path = "mih"
+                check(self._L.cb_scan64_self_mih_dev(d_hashes.data_ptr(), self.n_rows, int(threshold), self.rank, self.world,
+                                                     self.pairs.data_ptr(), self.cap, self.count.data_ptr(),
+                                                     C.c_void_p(stream)))
+            elif self.end > self.begin:
+                self.last_path = "scan"
                 check(self._L.cb_scan64_self_dev(d_hashes.data_ptr(), self.n_rows, self.begin, self.end, int(threshold),
                                                  1 if self.symmetric else 0, self.pairs.data_ptr(), self.cap,
                                                  self.count.data_ptr(), C.c_void_p(stream)))

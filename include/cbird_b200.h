@@ -170,6 +170,17 @@ int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin,
 int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b,
                         const cb_scan_tile* d_tiles, uint32_t n_tiles, int threshold, cb_pair* d_out, uint64_t cap,
                         unsigned long long* d_count, void* stream);
+/* The same hit set as cb_scan64_self_dev(row_begin = 0, row_end = n) -- every ORDERED pair (a, b), a == b included,
+ * with hamm64 < threshold -- found by multi-index hashing instead of testing all n^2 pairs: the 63 usable bits
+ * (bit 0 of a dct hash is always clear, src/cvutil.cpp:537-538) are cut into `threshold` chunks; two hashes
+ * closer than the threshold agree exactly on at least one chunk, so only rows sharing a chunk bucket are
+ * compared. threshold in [1, cb_scan64_mih_max_threshold()], n * threshold < 2^32 - 65536. Multi-GPU: buckets are
+ * dealt to `n_parts` ranks; rank `part` reports the pairs whose first shared bucket is its own, so the per-rank
+ * lists are disjoint and their union is the full set. *d_count (not reset here) receives the total, also
+ * beyond `cap`. Exact on any input; fastest when the hashes spread over the buckets. */
+int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts,
+                           cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
+int cb_scan64_mih_max_threshold(void);
 /* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
  * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
 int cb_scan64_variant(int threshold);
