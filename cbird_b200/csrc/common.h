@@ -95,11 +95,11 @@ struct MihEmit {  // what the tile-list kernel needs to report MIH hits: sorted 
   MihPlan plan;
 };
 struct MihWorkspace {
-  DevBuf<uint32_t> key, key2, val, val2, ofs, n_small, n_big, small_at, big_at;
+  DevBuf<uint32_t> key, key2, val, val2, ofs, n_big, big_at;
   DevBuf<uint64_t> sorted;
-  DevBuf<cb_scan_tile> small_tiles, big_tiles;
+  DevBuf<cb_scan_tile> big_tiles;
   DevBuf<unsigned char> temp;
-  DevBuf<unsigned long long> info;  // [0] small items, [1] tile-list items, [2] pair tests, [3] kept (row, chunk) items
+  DevBuf<unsigned long long> info;  // [1] tile-list items, [2] pair tests, [3] kept (row, chunk) items
   unsigned long long* h_info = nullptr;
   ~MihWorkspace();
 };

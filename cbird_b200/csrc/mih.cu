@@ -14,7 +14,9 @@
 //   sort    one stable LSD radix sort over all chunks                         cub::DeviceRadixSort
 //   gather  hashes in bucket order (bucket-contiguous, like the video index)   mih_gather_kernel
 //   bounds  bucket boundaries by binary search, tile list by exclusive scan    mih_bounds/tiles kernels
-//   scan    small buckets: one CTA per bucket, B side in shared memory, OR-fold pre-filter + exact recheck
+//   scan    small buckets (<= 512 rows): one CTA per 512 sorted positions, the surrounding window in shared
+//           memory, every row against its own bucket, OR-fold pre-filter + exact recheck, hits collected in
+//           shared memory and appended with one global atomic per CTA
 //           large buckets: the tuned tile-list kernel of scan64.cu (<= 2048 A rows x bucket)
 //
 // Multi-GPU: buckets are dealt to ranks ((bucket + chunk) % n_parts); every rank sorts and scans only its
@@ -83,20 +85,18 @@ __global__ void mih_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint3
   ofs[k] = lo;
 }
 
-// work items per bucket: small buckets -> 1 item of the small kernel; large ones -> ceil(s / 2048) tile-list items
-__global__ void mih_tile_counts_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, uint32_t* __restrict__ n_small,
-                                       uint32_t* __restrict__ n_big, unsigned long long* __restrict__ info) {
+// tile-list items per bucket (large buckets only: ceil(s / 2048)) and the pair tests of the whole pass
+__global__ void mih_tile_counts_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, uint32_t* __restrict__ n_big,
+                                       unsigned long long* __restrict__ info) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long tests = 0;
   if (k <= n_buckets) {
     uint32_t s = 0;
     if (k < n_buckets) s = ofs[k + 1] - ofs[k];
-    n_small[k] = (s > 0 && s <= kSmallMax) ? 1u : 0u;
     n_big[k] = s > kSmallMax ? (s + kBigABlock - 1) / kBigABlock : 0u;
     tests = (unsigned long long)s * s;
   }
-  // pair tests of the whole pass (block reduction, one atomic per CTA)
-  __shared__ unsigned long long red[8];
+  __shared__ unsigned long long red[8];  // block reduction, one atomic per CTA
   for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tests;
   __syncthreads();
@@ -107,64 +107,94 @@ __global__ void mih_tile_counts_kernel(const uint32_t* __restrict__ ofs, uint32_
   }
 }
 
-__global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets,
-                                      const uint32_t* __restrict__ small_at, const uint32_t* __restrict__ big_at,
-                                      cb_scan_tile* __restrict__ small_tiles, cb_scan_tile* __restrict__ big_tiles,
-                                      unsigned long long* __restrict__ info) {
+__global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, const uint32_t* __restrict__ big_at,
+                                      cb_scan_tile* __restrict__ big_tiles, unsigned long long* __restrict__ info) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n_buckets) return;
-  if (k == n_buckets) {  // the exclusive scans end here: totals
-    info[0] = small_at[k];
+  if (k == n_buckets) {  // the exclusive scan ends here: total
     info[1] = big_at[k];
     return;
   }
   const uint32_t b0 = ofs[k], s = ofs[k + 1] - b0;
-  if (s == 0) return;
-  if (s <= kSmallMax) {
-    small_tiles[small_at[k]] = cb_scan_tile{b0, s, b0, s};
-  } else {
-    const uint32_t at = big_at[k];
-    for (uint32_t t = 0, a = 0; a < s; ++t, a += kBigABlock)
-      big_tiles[at + t] = cb_scan_tile{b0 + a, min(kBigABlock, s - a), b0, s};
-  }
+  if (s <= kSmallMax) return;
+  const uint32_t at = big_at[k];
+  for (uint32_t t = 0, a = 0; a < s; ++t, a += kBigABlock)
+    big_tiles[at + t] = cb_scan_tile{b0 + a, min(kBigABlock, s - a), b0, s};
 }
 
-// One CTA per small bucket (<= 512 rows): the bucket goes to shared memory once, thread t owns rows
-// t, t+128, ... as the A side, and every (A, B) pair is pre-filtered with popc((alo^blo)|(ahi^bhi)) <= distance
-// (1 POPC per pair) before the exact test. Hits leave as original row numbers, and only from the first chunk
-// in which the pair shares a bucket.
+// Small buckets (<= 512 rows). One CTA owns 512 consecutive sorted positions as A rows and keeps the window
+// [base - 512, base + 1024) in shared memory, which contains every small bucket that overlaps its rows. Thread
+// t tests rows base + t, + 128, ... against their own bucket: popc((alo^blo)|(ahi^bhi)) <= distance is the
+// pre-filter (1 POPC per pair), then the exact distance. A hit is kept only in the first chunk in which the two
+// hashes share a bucket, leaves as original row numbers, and is staged in shared memory so that the global
+// counter sees one atomic per CTA (every row at least finds itself: per-hit global atomics would serialise).
+constexpr int kSmallRows = 512, kHitBuf = 1024;
+
 __global__ void __launch_bounds__(kSmallThreads)
     mih_small_kernel(const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ rows,
-                     const uint32_t* __restrict__ keys, const cb_scan_tile* __restrict__ tiles, MihPlan plan,
+                     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ofs, uint32_t m, MihPlan plan,
                      int threshold, cb_pair* __restrict__ out, unsigned long long cap,
                      unsigned long long* __restrict__ count) {
-  __shared__ uint2 sb[kSmallMax];
-  const cb_scan_tile t = tiles[blockIdx.x];
-  const uint32_t s = t.b_count;
-  for (uint32_t i = threadIdx.x; i < s; i += kSmallThreads) {
-    const uint64_t v = sorted[t.b_begin + i];
-    sb[i] = make_uint2(uint32_t(v), uint32_t(v >> 32));
+  __shared__ uint2 win[3 * kSmallRows + 4];  // +4: the 4-row steps may read past the last bucket
+  __shared__ uint4 hitbuf[kHitBuf];
+  __shared__ unsigned n_hit;
+  __shared__ unsigned long long g_base;
+  const uint32_t base = blockIdx.x * kSmallRows;
+  const long long w0 = (long long)base - kSmallRows;
+  for (int i = threadIdx.x; i < 3 * kSmallRows; i += kSmallThreads) {
+    const long long pos = w0 + i;
+    uint64_t v = 0;
+    if (pos >= 0 && pos < (long long)m) v = sorted[pos];
+    win[i] = make_uint2(uint32_t(v), uint32_t(v >> 32));
   }
+  if (threadIdx.x < 4) win[3 * kSmallRows + threadIdx.x] = make_uint2(0u, 0u);
+  if (threadIdx.x == 0) n_hit = 0;
   __syncthreads();
-  const int chunk = int(keys[t.b_begin] >> 16);
-  for (uint32_t a = threadIdx.x; a < s; a += kSmallThreads) {
-    const uint2 av = sb[a];
-    for (uint32_t b = 0; b < s; ++b) {
-      const uint2 bv = sb[b];  // broadcast read
-      const uint32_t xlo = av.x ^ bv.x, xhi = av.y ^ bv.y;
-      if (int(__popc(xlo | xhi)) >= threshold) continue;
+  for (int r = 0; r < kSmallRows / kSmallThreads; ++r) {
+    const uint32_t a = base + threadIdx.x + r * kSmallThreads;
+    if (a >= m) continue;
+    const uint32_t key = keys[a];
+    const uint32_t bs = ofs[key], be = ofs[key + 1];
+    if (be - bs > kSmallMax) continue;  // a large bucket: the tile-list kernel has it
+    const int chunk = int(key >> 16);
+    const uint2 av = win[a - base + kSmallRows];
+    auto emit = [&](uint32_t b, uint32_t xlo, uint32_t xhi) {
       const int d = __popc(xlo) + __popc(xhi);
-      if (d >= threshold) continue;
+      if (d >= threshold) return;
       const uint64_t x = (uint64_t(xhi) << 32) | xlo;
-      bool first = true;
       for (int c = 0; c < chunk; ++c)
-        if (((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) first = false;
-      if (!first) continue;
-      const unsigned long long pos = atomicAdd(count, 1ull);
-      if (pos < cap)
-        *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[t.b_begin + a], rows[t.b_begin + b], uint32_t(d), 0u);
+        if (((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) return;  // an earlier chunk reports this pair
+      const uint4 hit = make_uint4(rows[a], rows[b], uint32_t(d), 0u);
+      const unsigned at = atomicAdd(&n_hit, 1u);
+      if (at < kHitBuf) {
+        hitbuf[at] = hit;
+      } else {  // staging full (a cluster of near-duplicates): straight to the list
+        const unsigned long long pos = atomicAdd(count, 1ull);
+        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = hit;
+      }
+    };
+    // four B rows per step: independent loads and pre-filters, one branch; rows past the bucket's end are
+    // read from the (padded) window but never reported
+    const uint2* wb = win + (bs - base + kSmallRows);
+    const uint32_t s = be - bs;
+    for (uint32_t j = 0; j < s; j += 4) {
+      const uint2 b0 = wb[j], b1 = wb[j + 1], b2 = wb[j + 2], b3 = wb[j + 3];
+      const uint32_t x0l = av.x ^ b0.x, x0h = av.y ^ b0.y, x1l = av.x ^ b1.x, x1h = av.y ^ b1.y;
+      const uint32_t x2l = av.x ^ b2.x, x2h = av.y ^ b2.y, x3l = av.x ^ b3.x, x3h = av.y ^ b3.y;
+      const int p0 = __popc(x0l | x0h), p1 = __popc(x1l | x1h), p2 = __popc(x2l | x2h), p3 = __popc(x3l | x3h);
+      if (min(min(p0, p1), min(p2, p3)) >= threshold) continue;
+      if (p0 < threshold) emit(bs + j, x0l, x0h);
+      if (p1 < threshold && j + 1 < s) emit(bs + j + 1, x1l, x1h);
+      if (p2 < threshold && j + 2 < s) emit(bs + j + 2, x2l, x2h);
+      if (p3 < threshold && j + 3 < s) emit(bs + j + 3, x3l, x3h);
     }
   }
+  __syncthreads();
+  const unsigned staged = min(n_hit, unsigned(kHitBuf));
+  if (threadIdx.x == 0 && staged) g_base = atomicAdd(count, (unsigned long long)staged);
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < staged; i += kSmallThreads)
+    if (g_base + i < cap) *reinterpret_cast<uint4*>(out + g_base + i) = hitbuf[i];
 }
 
 }  // namespace
@@ -212,8 +242,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   int rc;
   if ((rc = ws.key.reserve(total)) != CB_OK || (rc = ws.key2.reserve(total)) != CB_OK || (rc = ws.val.reserve(total)) != CB_OK ||
       (rc = ws.val2.reserve(total)) != CB_OK || (rc = ws.sorted.reserve(total + 2)) != CB_OK ||
-      (rc = ws.ofs.reserve(n_buckets + 2)) != CB_OK || (rc = ws.n_small.reserve(n_buckets + 2)) != CB_OK ||
-      (rc = ws.n_big.reserve(n_buckets + 2)) != CB_OK || (rc = ws.small_at.reserve(n_buckets + 2)) != CB_OK ||
+      (rc = ws.ofs.reserve(n_buckets + 2)) != CB_OK || (rc = ws.n_big.reserve(n_buckets + 2)) != CB_OK ||
       (rc = ws.big_at.reserve(n_buckets + 2)) != CB_OK || (rc = ws.info.reserve(4)) != CB_OK)
     return rc;
   if (!ws.h_info) CB_CUDA(cudaMallocHost(&ws.h_info, 4 * sizeof(unsigned long long)));
@@ -233,7 +262,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   size_t tb = 0, tb2 = 0;
   CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
                                           key_bits, stream));
-  CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, ws.n_small.p, ws.small_at.p, int(n_buckets + 1), stream));
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
   if ((rc = ws.temp.reserve(std::max(tb, tb2) + 16)) != CB_OK) return rc;
   CB_CUDA(cub::DeviceRadixSort::SortPairs(ws.temp.p, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
                                           key_bits, stream));
@@ -242,31 +271,26 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   const unsigned bblocks = (n_buckets + 1 + 255) / 256;
   mih_bounds_kernel<<<bblocks, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
   CB_CUDA(cudaGetLastError());
-  mih_tile_counts_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.n_small.p, ws.n_big.p, ws.info.p);
+  mih_tile_counts_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.n_big.p, ws.info.p);
   CB_CUDA(cudaGetLastError());
-  CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_small.p, ws.small_at.p, int(n_buckets + 1), stream));
   CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
-  // upper bounds of the two work lists: one item per non-empty small bucket, ceil(s/2048) per large one
-  const size_t max_small = std::min<size_t>(n_buckets, m), max_big = size_t(m) / kSmallMax + 1;
-  if ((rc = ws.small_tiles.reserve(max_small + 1)) != CB_OK || (rc = ws.big_tiles.reserve(max_big + 1)) != CB_OK) return rc;
-  mih_tile_write_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.small_at.p, ws.big_at.p, ws.small_tiles.p,
-                                                    ws.big_tiles.p, ws.info.p);
+  // upper bound of the tile list: ceil(s / 2048) items per bucket of more than 512 rows
+  if ((rc = ws.big_tiles.reserve(size_t(m) / kSmallMax + 2)) != CB_OK) return rc;
+  mih_tile_write_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.big_at.p, ws.big_tiles.p, ws.info.p);
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
   CB_CUDA(cudaStreamSynchronize(stream));
-  counters().launches += 5;
-  const uint32_t n_small = uint32_t(ws.h_info[0]), n_big = uint32_t(ws.h_info[1]);
+  counters().launches += 4;
+  const uint32_t n_big = uint32_t(ws.h_info[1]);
   const unsigned long long tests = ws.h_info[2];
   if (max_tests && tests > max_tests) {
     if (declined) *declined = 1;
     return CB_OK;
   }
-  if (n_small) {
-    mih_small_kernel<<<n_small, kSmallThreads, 0, stream>>>(ws.sorted.p, ws.val2.p, ws.key2.p, ws.small_tiles.p, plan, threshold,
-                                                           out, cap, d_count);
-    CB_CUDA(cudaGetLastError());
-    counters().launches += 1;
-  }
+  mih_small_kernel<<<(m + kSmallRows - 1) / kSmallRows, kSmallThreads, 0, stream>>>(ws.sorted.p, ws.val2.p, ws.key2.p, ws.ofs.p, m,
+                                                                                   plan, threshold, out, cap, d_count);
+  CB_CUDA(cudaGetLastError());
+  counters().launches += 1;
   if (n_big) {
     Scan64Launch L{ws.sorted.p, m, ws.sorted.p, m, threshold, 0, out, cap, d_count};
     MihEmit E{ws.val2.p, ws.key2.p, plan};
