@@ -19,6 +19,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int current_device();          // device selected by cb_set_device on this thread (default 0)
 int ensure_device();           // CB_OK or CB_ERR_NO_DEVICE; also cudaSetDevice(current_device())
 
+// result buffers returned through the C ABI and released with cb_free: pinned (pooled) when large
+void* result_alloc(size_t bytes);
+void result_free(void* p);
+
 struct Counters {
   std::atomic<uint64_t> comparisons{0}, hits{0}, launches{0}, frames{0};
 };

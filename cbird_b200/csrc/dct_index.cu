@@ -485,7 +485,7 @@ int cb_dct_index_find(cb_dct_index* ix, uint64_t needle_hash, const cb_params* p
 
 static int export_hits(const std::vector<cb_hit>& hits, cb_hit** out, int64_t* n_out) {
   *n_out = int64_t(hits.size());
-  *out = static_cast<cb_hit*>(malloc(std::max<size_t>(1, hits.size()) * sizeof(cb_hit)));
+  *out = static_cast<cb_hit*>(result_alloc(hits.size() * sizeof(cb_hit)));
   if (!*out) {
     set_error("out of host memory");
     return CB_ERR_INVALID;
@@ -562,7 +562,7 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   // then an exclusive scan of the kept counts gives the offsets and a scatter packs the lists.
   SimilarPost P{dht, p->maxThresh, p->minMatches, p->maxMatches < 0 ? 0 : p->maxMatches, p->filterSelf ? 1 : 0,
                 escalate ? 1 : 0};
-  int64_t* offsets = static_cast<int64_t*>(malloc(size_t(n + 1) * sizeof(int64_t)));
+  int64_t* offsets = static_cast<int64_t*>(result_alloc(size_t(n + 1) * sizeof(int64_t)));
   if (!offsets) {
     set_error("out of host memory");
     return CB_ERR_INVALID;
@@ -571,8 +571,8 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
   size_t w = 0;
   cb_hit* hits = nullptr;
   auto fail = [&](int code) {
-    free(offsets);
-    free(hits);
+    result_free(offsets);
+    result_free(hits);
     return code;
   };
   if (n > 0) {
@@ -599,7 +599,7 @@ int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** o
     counters().launches += 3;
     w = size_t(offsets[n]);
   }
-  hits = static_cast<cb_hit*>(malloc(std::max<size_t>(1, w) * sizeof(cb_hit)));
+  hits = static_cast<cb_hit*>(result_alloc(w * sizeof(cb_hit)));
   if (!hits) {
     set_error("out of host memory");
     return fail(CB_ERR_INVALID);
