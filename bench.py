@@ -552,6 +552,7 @@ def main():
                 "traffic": None, "peak_source": peak_note, "kernel_ms": kern_ms,
                 "nominal_pairs_per_launch": nominal_local, "issued_pair_tests": issued_local,
                 "issued_share_of_nominal": issued_local / nominal_local, "algorithmic_popc_per_pair": 2,
+                "issued_popc_frac": issued_local / (kern_ms * 1e-3) / popc_peak,  # 1 pre-filter POPC per issued test, whole pass
                 "note": "achieved = ALGORITHMIC work (2 POPC per nominal pair, SURVEY 8d) / pass time. frac is far above 1 because "
                         "the pass is an exact index, not a faster pair test: it issues issued_pair_tests, a small share of the "
                         "nominal square, and its time goes to the sort and the bucket scans (profiles/launches_bench_r01.csv). "

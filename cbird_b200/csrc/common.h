@@ -88,8 +88,9 @@ int scan64_variant_for(int threshold);
 
 // ---- multi-index (pigeonhole) self-join, mih.cu ------------------------------------------------
 constexpr int kMihMaxThreshold = 10;  // above this the buckets get too coarse to beat the brute-force scan
-struct MihPlan {  // chunk c of a hash = (h >> shift[c]) & mask[c]
+struct MihPlan {  // chunk c of a hash = (h >> shift[c]) & mask[c]; sort key = (c << key_shift) | bucket
   int chunks;
+  int key_shift;  // bits of the widest bucket index (<= 16)
   int shift[kMihMaxThreshold];
   uint32_t mask[kMihMaxThreshold];
 };

@@ -10,7 +10,7 @@
 // rows, T = 5: 6.7e8 instead of 1.1e12). A pair that shares a bucket in several chunks is reported by the
 // first of them only, so the hit set is exactly the brute-force one (self pairs included, each once).
 //
-//   keys    (chunk << 16 | bucket, row) for every chunk of every row        mih_keys_kernel
+//   keys    (chunk << bucket bits | bucket, row) for every chunk of every row mih_keys_kernel
 //   sort    one stable LSD radix sort over all chunks                         cub::DeviceRadixSort
 //   gather  hashes in bucket order (bucket-contiguous, like the video index)   mih_gather_kernel
 //   bounds  bucket boundaries by binary search, tile list by exclusive scan    mih_bounds/tiles kernels
@@ -47,7 +47,7 @@ __global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, M
     const uint32_t k = uint32_t(h >> plan.shift[c]) & plan.mask[c];
     if (n_parts == 1) {
       if (live) {
-        key[size_t(c) * n + i] = (uint32_t(c) << 16) | k;
+        key[size_t(c) * n + i] = (uint32_t(c) << plan.key_shift) | k;
         val[size_t(c) * n + i] = i;
       }
       continue;
@@ -60,7 +60,7 @@ __global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, M
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (mine) {
       const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-      key[at] = (uint32_t(c) << 16) | k;
+      key[at] = (uint32_t(c) << plan.key_shift) | k;
       val[at] = i;
     }
   }
@@ -126,8 +126,10 @@ __global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t
 // [base - 512, base + 1024) in shared memory, which contains every small bucket that overlaps its rows. Thread
 // t tests rows base + t, + 128, ... against their own bucket: popc((alo^blo)|(ahi^bhi)) <= distance is the
 // pre-filter (1 POPC per pair), then the exact distance. A hit is kept only in the first chunk in which the two
-// hashes share a bucket, leaves as original row numbers, and is staged in shared memory so that the global
-// counter sees one atomic per CTA (every row at least finds itself: per-hit global atomics would serialise).
+// hashes share a bucket, and is staged in shared memory as packed window positions: the global counter sees
+// one atomic per CTA (every row at least finds itself: per-hit global atomics would serialise) and the
+// translation to original row numbers happens at the flush, all threads in parallel, instead of two dependent
+// global loads in the middle of the scan loop.
 constexpr int kSmallRows = 512, kHitBuf = 1024;
 
 __global__ void __launch_bounds__(kSmallThreads)
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kSmallThreads)
                      int threshold, cb_pair* __restrict__ out, unsigned long long cap,
                      unsigned long long* __restrict__ count) {
   __shared__ uint2 win[3 * kSmallRows + 4];  // +4: the 4-row steps may read past the last bucket
-  __shared__ uint4 hitbuf[kHitBuf];
+  __shared__ uint32_t hitbuf[kHitBuf];  // (a - base) | (b - base + 512) << 9 | distance << 20
   __shared__ unsigned n_hit;
   __shared__ unsigned long long g_base;
   const uint32_t base = blockIdx.x * kSmallRows;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kSmallThreads)
     const uint32_t key = keys[a];
     const uint32_t bs = ofs[key], be = ofs[key + 1];
     if (be - bs > kSmallMax) continue;  // a large bucket: the tile-list kernel has it
-    const int chunk = int(key >> 16);
+    const int chunk = int(key >> plan.key_shift);
     const uint2 av = win[a - base + kSmallRows];
     auto emit = [&](uint32_t b, uint32_t xlo, uint32_t xhi) {
       const int d = __popc(xlo) + __popc(xhi);
@@ -164,13 +166,13 @@ __global__ void __launch_bounds__(kSmallThreads)
       const uint64_t x = (uint64_t(xhi) << 32) | xlo;
       for (int c = 0; c < chunk; ++c)
         if (((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) return;  // an earlier chunk reports this pair
-      const uint4 hit = make_uint4(rows[a], rows[b], uint32_t(d), 0u);
+      // positions are translated to row numbers when the CTA flushes: no global load on this path
       const unsigned at = atomicAdd(&n_hit, 1u);
       if (at < kHitBuf) {
-        hitbuf[at] = hit;
+        hitbuf[at] = (a - base) | ((b - base + kSmallRows) << 9) | (uint32_t(d) << 20);
       } else {  // staging full (a cluster of near-duplicates): straight to the list
         const unsigned long long pos = atomicAdd(count, 1ull);
-        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = hit;
+        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[a], rows[b], uint32_t(d), 0u);
       }
     };
     // four B rows per step: independent loads and pre-filters, one branch; rows past the bucket's end are
@@ -194,7 +196,11 @@ __global__ void __launch_bounds__(kSmallThreads)
   if (threadIdx.x == 0 && staged) g_base = atomicAdd(count, (unsigned long long)staged);
   __syncthreads();
   for (unsigned i = threadIdx.x; i < staged; i += kSmallThreads)
-    if (g_base + i < cap) *reinterpret_cast<uint4*>(out + g_base + i) = hitbuf[i];
+    if (g_base + i < cap) {
+      const uint32_t e = hitbuf[i];
+      const uint32_t a = base + (e & 511u), b = base + ((e >> 9) & 2047u) - kSmallRows;
+      *reinterpret_cast<uint4*>(out + g_base + i) = make_uint4(rows[a], rows[b], e >> 20, 0u);
+    }
 }
 
 }  // namespace
@@ -203,12 +209,14 @@ MihPlan mih_plan(int threshold) {
   MihPlan p;
   const int chunks = std::max(1, std::min(threshold, kMihMaxThreshold));
   p.chunks = chunks;
+  p.key_shift = 0;
   const int base = 63 / chunks, rem = 63 % chunks;
   int start = 1;  // bit 0 of a dct hash carries no information (src/cvutil.cpp:537-538)
   for (int c = 0; c < kMihMaxThreshold; ++c) {
     const int len = c < chunks ? base + (c < rem ? 1 : 0) : 0;
     p.shift[c] = c < chunks ? start : 0;
     p.mask[c] = c < chunks ? ((1u << std::min(len, 16)) - 1u) : 0u;
+    p.key_shift = std::max(p.key_shift, std::min(len, 16));
     start += len;
   }
   return p;
@@ -238,7 +246,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   }
   const MihPlan plan = mih_plan(threshold);
   const size_t total = size_t(n) * plan.chunks;
-  const uint32_t n_buckets = uint32_t(plan.chunks) << 16;
+  const uint32_t n_buckets = uint32_t(plan.chunks) << plan.key_shift;
   int rc;
   if ((rc = ws.key.reserve(total)) != CB_OK || (rc = ws.key2.reserve(total)) != CB_OK || (rc = ws.val.reserve(total)) != CB_OK ||
       (rc = ws.val2.reserve(total)) != CB_OK || (rc = ws.sorted.reserve(total + 2)) != CB_OK ||
@@ -257,8 +265,8 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   }
   counters().launches += 1;
   if (m == 0) return CB_OK;
-  int key_bits = 16;
-  while ((1 << (key_bits - 16)) < plan.chunks) ++key_bits;
+  int key_bits = plan.key_shift;  // (chunk << key_shift) | bucket: as few radix passes as the threshold allows
+  while ((1 << (key_bits - plan.key_shift)) < plan.chunks) ++key_bits;
   size_t tb = 0, tb2 = 0;
   CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
                                           key_bits, stream));

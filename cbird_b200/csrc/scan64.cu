@@ -74,7 +74,7 @@ __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds
   if (ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
     if constexpr (MIH) {
       const uint64_t x = (uint64_t(ahi ^ bhi) << 32) | xlo;
-      const int chunk = int(M->keys[ai] >> 16);
+      const int chunk = int(M->keys[ai] >> M->plan.key_shift);
       for (int c = 0; c < chunk; ++c)
         if ((uint32_t(x >> M->plan.shift[c]) & M->plan.mask[c]) == 0) return;
       ai = M->rows[ai];
