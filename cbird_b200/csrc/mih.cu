@@ -160,20 +160,28 @@ __global__ void __launch_bounds__(kSmallThreads)
     if (be - bs > kSmallMax) continue;  // a large bucket: the tile-list kernel has it
     const int chunk = int(key >> plan.key_shift);
     const uint2 av = win[a - base + kSmallRows];
-    auto emit = [&](uint32_t b, uint32_t xlo, uint32_t xhi) {
-      const int d = __popc(xlo) + __popc(xhi);
-      if (d >= threshold) return;
-      const uint64_t x = (uint64_t(xhi) << 32) | xlo;
-      for (int c = 0; c < chunk; ++c)
-        if (((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) return;  // an earlier chunk reports this pair
+    auto stage = [&](uint32_t b, uint32_t d) {
       // positions are translated to row numbers when the CTA flushes: no global load on this path
       const unsigned at = atomicAdd(&n_hit, 1u);
       if (at < kHitBuf) {
-        hitbuf[at] = (a - base) | ((b - base + kSmallRows) << 9) | (uint32_t(d) << 20);
+        hitbuf[at] = (a - base) | ((b - base + kSmallRows) << 9) | (d << 20);
       } else {  // staging full (a cluster of near-duplicates): straight to the list
         const unsigned long long pos = atomicAdd(count, 1ull);
-        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[a], rows[b], uint32_t(d), 0u);
+        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[a], rows[b], d, 0u);
       }
+    };
+    auto emit = [&](uint32_t b, uint32_t xlo, uint32_t xhi) {
+      if (b == a) {  // every row meets itself in every chunk: settle that before anything else
+        if (chunk == 0) stage(b, 0u);
+        return;
+      }
+      const int d = __popc(xlo) + __popc(xhi);
+      if (d >= threshold) return;
+      const uint64_t x = (uint64_t(xhi) << 32) | xlo;
+#pragma unroll
+      for (int c = 0; c < kMihMaxThreshold - 1; ++c)  // unrolled: the plan stays in the constant bank
+        if (c < chunk && ((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) return;  // an earlier chunk reports it
+      stage(b, uint32_t(d));
     };
     // four B rows per step: independent loads and pre-filters, one branch; rows past the bucket's end are
     // read from the (padded) window but never reported
