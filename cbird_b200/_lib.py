@@ -68,6 +68,7 @@ SIGNATURES = {
     "cb_scan64_self_dev": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_self_mih_dev": (C.c_int, [_vp, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_mih_max_threshold": (C.c_int, []),
+    "cb_scan64_mih_plan": (C.c_int, [C.c_int, _vp, _vp]),
     "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),

@@ -338,4 +338,17 @@ int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, 
 
 int cb_scan64_mih_max_threshold(void) { return kMihMaxThreshold; }
 
+int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks) {
+  if (threshold < 1 || threshold > kMihMaxThreshold) {
+    set_error("cb_scan64_mih_plan: threshold %d outside [1, %d]", threshold, kMihMaxThreshold);
+    return CB_ERR_UNSUPPORTED;
+  }
+  const MihPlan p = mih_plan(threshold);
+  for (int c = 0; c < p.chunks; ++c) {
+    if (shifts) shifts[c] = p.shift[c];
+    if (masks) masks[c] = p.mask[c];
+  }
+  return p.chunks;
+}
+
 }  // extern "C"

@@ -181,6 +181,9 @@ int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, 
 int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts,
                            cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
 int cb_scan64_mih_max_threshold(void);
+/* the bucket layout the self-join uses for a threshold (host only, no device needed): chunk c of a hash is
+ * (h >> shifts[c]) & masks[c]; returns the number of chunks (== threshold) or a negative status */
+int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks);
 /* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
  * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
 int cb_scan64_variant(int threshold);
