@@ -14,7 +14,7 @@
 //   sort    one stable LSD radix sort over all chunks                         cub::DeviceRadixSort
 //   gather  hashes in bucket order (bucket-contiguous, like the video index)   mih_gather_kernel
 //   bounds  bucket boundaries by binary search, tile list by exclusive scan    mih_bounds/tiles kernels
-//   scan    small buckets (<= 512 rows): one CTA per 512 sorted positions, the surrounding window in shared
+//   scan    small buckets (<= 1024 rows): one CTA per 512 sorted positions, the surrounding window in shared
 //           memory, every row against its own bucket, OR-fold pre-filter + exact recheck, hits collected in
 //           shared memory and appended with one global atomic per CTA
 //           large buckets: the tuned tile-list kernel of scan64.cu (<= 2048 A rows x bucket)
@@ -33,7 +33,7 @@ namespace cbird {
 namespace {
 
 constexpr int kSmallThreads = 128;
-constexpr uint32_t kSmallMax = 512;   // buckets up to this many rows take the small-bucket kernel
+constexpr uint32_t kSmallMax = 1024;  // buckets up to this many rows take the small-bucket kernel
 constexpr uint32_t kBigABlock = 2048;  // A rows per work item of the tile-list kernel
 
 __global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, MihPlan plan, uint32_t part,
@@ -122,8 +122,8 @@ __global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t
     big_tiles[at + t] = cb_scan_tile{b0 + a, min(kBigABlock, s - a), b0, s};
 }
 
-// Small buckets (<= 512 rows). One CTA owns 512 consecutive sorted positions as A rows and keeps the window
-// [base - 512, base + 1024) in shared memory, which contains every small bucket that overlaps its rows. Thread
+// Small buckets (<= 1024 rows). One CTA owns 512 consecutive sorted positions as A rows and keeps the window
+// [base - 1024, base + 1536) in shared memory, which contains every small bucket that overlaps its rows. Thread
 // t tests rows base + t, + 128, ... against their own bucket: popc((alo^blo)|(ahi^bhi)) <= distance is the
 // pre-filter (1 POPC per pair), then the exact distance. A hit is kept only in the first chunk in which the two
 // hashes share a bucket, and is staged in shared memory as packed window positions: the global counter sees
@@ -131,25 +131,26 @@ __global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t
 // translation to original row numbers happens at the flush, all threads in parallel, instead of two dependent
 // global loads in the middle of the scan loop.
 constexpr int kSmallRows = 512, kHitBuf = 1024;
+constexpr int kWin = kSmallRows + 2 * int(kSmallMax);  // window: positions [base - kSmallMax, base + kSmallRows + kSmallMax)
 
 __global__ void __launch_bounds__(kSmallThreads)
     mih_small_kernel(const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ rows,
                      const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ofs, uint32_t m, MihPlan plan,
                      int threshold, cb_pair* __restrict__ out, unsigned long long cap,
                      unsigned long long* __restrict__ count) {
-  __shared__ uint2 win[3 * kSmallRows + 4];  // +4: the 4-row steps may read past the last bucket
-  __shared__ uint32_t hitbuf[kHitBuf];  // (a - base) | (b - base + 512) << 9 | distance << 20
+  __shared__ uint2 win[kWin + 4];  // +4: the 4-row steps may read past the last bucket
+  __shared__ uint32_t hitbuf[kHitBuf];  // (a - base) | (b - base + kSmallMax) << 9 | distance << 21
   __shared__ unsigned n_hit;
   __shared__ unsigned long long g_base;
   const uint32_t base = blockIdx.x * kSmallRows;
-  const long long w0 = (long long)base - kSmallRows;
-  for (int i = threadIdx.x; i < 3 * kSmallRows; i += kSmallThreads) {
+  const long long w0 = (long long)base - (long long)kSmallMax;
+  for (int i = threadIdx.x; i < kWin; i += kSmallThreads) {
     const long long pos = w0 + i;
     uint64_t v = 0;
     if (pos >= 0 && pos < (long long)m) v = sorted[pos];
     win[i] = make_uint2(uint32_t(v), uint32_t(v >> 32));
   }
-  if (threadIdx.x < 4) win[3 * kSmallRows + threadIdx.x] = make_uint2(0u, 0u);
+  if (threadIdx.x < 4) win[kWin + threadIdx.x] = make_uint2(0u, 0u);
   if (threadIdx.x == 0) n_hit = 0;
   __syncthreads();
   for (int r = 0; r < kSmallRows / kSmallThreads; ++r) {
@@ -159,12 +160,12 @@ __global__ void __launch_bounds__(kSmallThreads)
     const uint32_t bs = ofs[key], be = ofs[key + 1];
     if (be - bs > kSmallMax) continue;  // a large bucket: the tile-list kernel has it
     const int chunk = int(key >> plan.key_shift);
-    const uint2 av = win[a - base + kSmallRows];
+    const uint2 av = win[a - base + kSmallMax];
     auto stage = [&](uint32_t b, uint32_t d) {
       // positions are translated to row numbers when the CTA flushes: no global load on this path
       const unsigned at = atomicAdd(&n_hit, 1u);
       if (at < kHitBuf) {
-        hitbuf[at] = (a - base) | ((b - base + kSmallRows) << 9) | (d << 20);
+        hitbuf[at] = (a - base) | ((b - base + kSmallMax) << 9) | (d << 21);
       } else {  // staging full (a cluster of near-duplicates): straight to the list
         const unsigned long long pos = atomicAdd(count, 1ull);
         if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[a], rows[b], d, 0u);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kSmallThreads)
     };
     // four B rows per step: independent loads and pre-filters, one branch; rows past the bucket's end are
     // read from the (padded) window but never reported
-    const uint2* wb = win + (bs - base + kSmallRows);
+    const uint2* wb = win + (bs - base + kSmallMax);
     const uint32_t s = be - bs;
     for (uint32_t j = 0; j < s; j += 4) {
       const uint2 b0 = wb[j], b1 = wb[j + 1], b2 = wb[j + 2], b3 = wb[j + 3];
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kSmallThreads)
   for (unsigned i = threadIdx.x; i < staged; i += kSmallThreads)
     if (g_base + i < cap) {
       const uint32_t e = hitbuf[i];
-      const uint32_t a = base + (e & 511u), b = base + ((e >> 9) & 2047u) - kSmallRows;
-      *reinterpret_cast<uint4*>(out + g_base + i) = make_uint4(rows[a], rows[b], e >> 20, 0u);
+      const uint32_t a = base + (e & 511u), b = base + ((e >> 9) & 4095u) - kSmallMax;
+      *reinterpret_cast<uint4*>(out + g_base + i) = make_uint4(rows[a], rows[b], e >> 21, 0u);
     }
 }
 
@@ -290,7 +291,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   mih_tile_counts_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.n_big.p, ws.info.p);
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
-  // upper bound of the tile list: ceil(s / 2048) items per bucket of more than 512 rows
+  // upper bound of the tile list: ceil(s / 2048) items per bucket of more than 1024 rows
   if ((rc = ws.big_tiles.reserve(size_t(m) / kSmallMax + 2)) != CB_OK) return rc;
   mih_tile_write_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.big_at.p, ws.big_tiles.p, ws.info.p);
   CB_CUDA(cudaGetLastError());
