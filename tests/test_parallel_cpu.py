@@ -94,3 +94,60 @@ def test_symmetric_shards_are_tile_aligned_and_balanced():
             if n >= 1048576:
                 assert max(cost) / (sum(cost) / world) < 1.05  # equal-cost ranges
             assert sum(parallel.issued_pair_tests(n, b, e, False) for b, e in spans) == n * n
+
+
+def _mih_lists(h, t, part, parts, shifts, masks):
+    """numpy restatement of what rank `part` reports in the bucket-dealt multi-index self-join: pairs whose FIRST
+    shared chunk bucket (chunk c, bucket k) satisfies (k + c) % parts == part (cbird_b200/csrc/mih.cu)."""
+    x = h[:, None] ^ h[None, :]
+    d = np.zeros(x.shape, np.int64)
+    for s in range(0, 64, 8):
+        d += np.unpackbits(((x >> np.uint64(s)) & np.uint64(0xFF)).astype(np.uint8)[..., None], axis=-1).sum(axis=-1, dtype=np.int64)
+    keys = [(h >> shifts[c]) & masks[c] for c in range(t)]
+    earlier = np.zeros(x.shape, bool)
+    out = []
+    for c in range(t):
+        same = keys[c][:, None] == keys[c][None, :]
+        mine = ((keys[c] + np.uint64(c)) % np.uint64(parts) == np.uint64(part))[:, None]
+        ia, ib = np.nonzero(same & ~earlier & (d < t) & mine)
+        out.append(np.stack([ia, ib, d[ia, ib], np.zeros(len(ia), np.int64)], 1))
+        earlier |= same
+    return np.concatenate(out).astype(np.int32)
+
+
+def _worker_mih(rank, world, port, n, t, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cbird_b200 as cb
+    from cbird_b200 import parallel, synth
+
+    shifts, masks = np.zeros(16, np.int32), np.zeros(16, np.uint32)
+    assert cb.lib().cb_scan64_mih_plan(t, shifts.ctypes.data, masks.ctypes.data) == t  # host only: no device needed
+    h, _ = synth.dct_hashes(n, seed=2, planted_frac=0.4)
+    local = torch.from_numpy(_mih_lists(h, t, rank, world, shifts[:t].astype(np.uint64), masks[:t].astype(np.uint64)))
+    merged = parallel.allgather_hits(local)
+    np.save(os.path.join(out_dir, "mih_%d.npy" % rank), merged.numpy())
+    np.save(os.path.join(out_dir, "mih_local_%d.npy" % rank), local.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_bucket_dealt_multi_index_merge(tmp_path, po):
+    # the N>1 path of the multi-index self-join: buckets dealt to ranks, disjoint lists, all-gather == brute force
+    n, world, t = 1500, 2, 5
+    mp.spawn(_worker_mih, args=(world, _free_port(), n, t, str(tmp_path)), nprocs=world, join=True)
+    from cbird_b200 import synth
+
+    h, ids = synth.dct_hashes(n, seed=2, planted_frac=0.4)
+    want, total, _ = po.dct_find_batch(h, ids, h, t)
+    want = want.copy()
+    want[:, 1] -= 1
+    locals_ = [np.load(tmp_path / ("mih_local_%d.npy" % r)) for r in range(world)]
+    assert sum(len(x) for x in locals_) == total and min(len(x) for x in locals_) > total // 8
+    for r in range(world):
+        m = np.load(tmp_path / ("mih_%d.npy" % r)).astype(np.int64)
+        m = m[np.lexsort((m[:, 2], m[:, 1], m[:, 0]))][:, :3]
+        assert np.array_equal(m, want)
