@@ -57,6 +57,14 @@ def ncu_traffic(kernel_substr):
     return None
 
 
+def mih_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_mih_small_r01.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -545,11 +553,13 @@ def main():
             roofline = {
                 "bound": "int_pipe",
                 "kernel": "multi-index self-join pass: mih_keys_kernel, cub radix sort, mih_gather/bounds/tile kernels, "
-                          "mih_small_kernel (+ scan64_tiles_mih_kernel for buckets over 512 rows)",
+                          "mih_small_kernel (+ scan64_tiles_mih_kernel for buckets over 1024 rows)",
                 "achieved": nominal_local * 2.0 / (kern_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12,
                 "unit": "TPOPC/s (nominal 2 POPC.b32 per 64-bit pair)",
                 "frac": nominal_local / (kern_ms * 1e-3) / pair_peak,
-                "traffic": None, "peak_source": peak_note, "kernel_ms": kern_ms,
+                "traffic": mih_traffic(), "peak_source": peak_note, "kernel_ms": kern_ms,
+                "traffic_note": "dram bytes of one mih_small_kernel launch (69 % of the pass) from the committed ncu capture at "
+                                "2^20 rows, dht 5 (profiles/ncu_mih_small_r01.json); algorithmic: 8 B per row in + 16 B per hit out",
                 "nominal_pairs_per_launch": nominal_local, "issued_pair_tests": issued_local,
                 "issued_share_of_nominal": issued_local / nominal_local, "algorithmic_popc_per_pair": 2,
                 "issued_popc_frac": issued_local / (kern_ms * 1e-3) / popc_peak,  # 1 pre-filter POPC per issued test, whole pass
