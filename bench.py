@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — cbird hot path on B200: `-similar` all-pairs Hamming comparisons/sec (+ DCT hashes/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R] [--legs a,b,...]
 
-A step = one `-similar` all-pairs pass over the synthetic index: every row is a needle against every
-row (N independent Index::find calls in the reference, src/database.cpp:1400-1432), threshold dht=5.
-comparisons = rows^2 per step (the reference's semantics) — the NOMINAL count: like the
-reference's VP tree (which prunes most pairs) the scan does not issue all of them: d(a,b)==d(b,a), so
-only the 2048-row tiles on/above the diagonal are tested and hits are mirrored. The issued count and
-the rate on issued pairs are reported beside it (roofline.pairs_issued_per_launch, roofline.frac).
-  value : comparisons/s with the hashes resident in HBM (scan kernel + hit list + multi-GPU all-gather)
-  e2e   : the same through the public Index API / C ABI from HOST buffers (H2D of ids+hashes, D2H of hits)
-Multi-GPU: rows sharded across ranks, needles replicated, hit lists all-gathered over NCCL; weak
-scaling (rows grow with sqrt(N) so every GPU keeps 2^40 pair tests per step).
-Extra keys: dct_hash (kernel (a) frames/s + HBM roofline), single_needle, roofline, cpu_baseline.
-`--impl reference` times the reference's own VP-tree search (oracle/_ref, its headers compiled
-unmodified) on all host cores for the same metric.
+A step = one `-similar` all-pairs pass over the synthetic index: every row is a needle against every row
+(N independent Index::find calls in the reference, src/database.cpp:1400-1432), threshold dht=5, followed by
+the searchIndex post step per needle (src/database.cpp:1703-1737). comparisons = rows^2 per step — the
+reference's NOMINAL count: like its VP tree, the exact multi-index self-join prunes almost all of
+them; the pair tests really issued are reported beside it (roofline.issued_pair_tests).
+
+Workload: BASELINE configs[2], 10^7 hashes, at every N (strong scaling). With N > 1 (torchrun, one process per
+GPU) the library's own communicator (cb_comm_init_rank, NCCL) shards the pass: hashes replicated, chunk buckets
+dealt to the ranks, every hit sent to the rank owning its needle row (all-to-all), sort + post step per rank.
+  value : rows^2 / device time of DctHashIndex.similar_count (hashes resident in HBM: bucket pass, exchange,
+          hit sort, post step; results stay on the device), max over ranks
+  e2e   : rows^2 / wall time of DctHashIndex.load + .similar from pinned HOST buffers (H2D of ids+hashes, the
+          same pass, D2H of the CSR result); the same API at every N (every rank returns its needle rows)
+Parity is checked in the run: the e2e result lists of a needle sample are compared, pair for pair, with the
+reference VP tree (oracle/_ref, its own headers compiled unmodified), and the total with a CPU count over the
+planted clusters. Extra legs: target_100M (the north_star's 10^8-row index), dct_hash, find (single needle +
+concurrent callers), video (configs[3]), orb (configs[4] at 10^7 rows on one GPU).
+`--impl reference` times the reference's VP-tree search (all host cores, bounded needle sample) for the same
+metric and config.
 """
 import argparse
 import ctypes as C
@@ -32,37 +38,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 DHT = 5
-BASE_ROWS = 1 << 20
+DEFAULT_ROWS = 10_000_000
+TARGET_ROWS = 100_000_000
 HASH_FRAMES = 1 << 20
 SM_COUNT = 148
 POPC_PER_CLK_SM = 16.0  # measured: tools/probe/pipe_probe.cu -> profiles/pipe_probe_r01.json
-
-
-def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full summary
-    (profiles/ncu_full_r01.json; capture sizes are stated there), or None."""
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_full_r01.json")) as f:
-            prof = json.load(f)
-        units = prof.get("units", {})
-        for k in prof["kernels"]:
-            if kernel_substr in k["Kernel Name"]:
-                total = 0.0
-                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    total += float(k[key]) * scale[units.get(key, "byte")]
-                return total
-    except Exception:
-        pass
-    return None
-
-
-def mih_traffic():
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_mih_small_r01.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except Exception:
-        return None
+ALU_PER_CLK_SM = 64.0   # LOP3 lanes / clk / SM, same probe
+SEED = 3
 
 
 def load_peaks():
@@ -72,6 +54,19 @@ def load_peaks():
         return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summaries (profiles/ncu_*_r02.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_full_r02.json")) as f:
+            prof = json.load(f)
+        for k in prof["kernels"]:
+            if kernel in k["kernel"]:
+                return float(k["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -125,47 +120,115 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(hashes, ids, budget_s, threads):
-    """reference VpTree (oracle/_ref, src/tree/vptree.h compiled unmodified) or, if the prebuilt library
-    is absent, the oracle's brute restatement; bounded sample of needles; returns dict."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import pyoracle as po
+# ---------------------------------------------------------------------------------------------------------
+# CPU side (the checker and the baseline): the reference's own VP tree from oracle/_ref
+# ---------------------------------------------------------------------------------------------------------
+class RefTree:
+    """DctTree (VpTree) of the reference over (hashes, ids); falls back to the oracle's brute-force port when
+    the prebuilt reference library is absent."""
 
-    n = len(hashes)
-    ref = po.ref()
-    kind = "reference" if ref is not None else "port"
-    hashes = np.ascontiguousarray(hashes)
-    ids = np.ascontiguousarray(ids)
+    def __init__(self, hashes, ids):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle as po
 
-    if ref is not None:
+        self.po = po
+        self.ref = po.ref()
+        self.hashes = np.ascontiguousarray(hashes)
+        self.ids = np.ascontiguousarray(ids)
+        self.kind = "reference" if self.ref is not None else "port"
         t0 = time.time()
-        tree = ref.ref_dcttree_create(hashes, ids, n)
-        build_s = time.time() - t0
+        self.tree = self.ref.ref_dcttree_create(self.hashes, self.ids, len(self.hashes)) if self.ref is not None else None
+        self.build_s = time.time() - t0
 
-        def run(m):
+    def close(self):
+        if self.tree is not None:
+            self.ref.ref_dcttree_destroy(self.tree)
+            self.tree = None
+
+    def count(self, needles, threads):
+        """-> (seconds, total matches)"""
+        needles = np.ascontiguousarray(needles)
+        if self.tree is not None:
             ms = C.c_double(0)
-            total = ref.ref_dcttree_search_batch(tree, hashes[:m], m, DHT, threads, None, None, None, 0, C.byref(ms))
-            return ms.value / 1e3, total
-    else:
-        build_s = 0.0
+            total = self.ref.ref_dcttree_search_batch(self.tree, needles, len(needles), DHT, threads, None, None, None, 0,
+                                                      C.byref(ms))
+            return ms.value / 1e3, int(total)
+        _, total, ms = self.po.dct_find_batch(self.hashes, self.ids, needles, DHT, threads=threads, keep=False)
+        return ms / 1e3, int(total)
 
-        def run(m):
-            _, total, ms = po.dct_find_batch(hashes, ids, hashes[:m], DHT, threads=threads, keep=False)
-            return ms / 1e3, total
+    def lists(self, needles, threads):
+        """canonical (needle, id, dist) triples of every needle's radius set"""
+        needles = np.ascontiguousarray(needles)
+        if self.tree is None:
+            trip, _, _ = self.po.dct_find_batch(self.hashes, self.ids, needles, DHT, threads=threads, keep=True)
+            return trip
+        ms = C.c_double(0)
+        total = self.ref.ref_dcttree_search_batch(self.tree, needles, len(needles), DHT, threads, None, None, None, 0, C.byref(ms))
+        q = np.zeros(total, np.int32)
+        i = np.zeros(total, np.uint32)
+        d = np.zeros(total, np.int32)
+        self.ref.ref_dcttree_search_batch(self.tree, needles, len(needles), DHT, threads, q.ctypes.data, i.ctypes.data,
+                                          d.ctypes.data, total, C.byref(ms))
+        return self.po.canonical(q, i, d)
 
-    m = min(n, 2048 * threads)
-    t, _ = run(m)  # calibration
-    per = max(t / m, 1e-9)
-    m2 = int(min(n, max(m, budget_s / per)))
-    t2, total = run(m2)
-    if ref is not None:
-        ref.ref_dcttree_destroy(tree)
-    return {"value": m2 * n / t2, "unit": "comparisons/s", "cores": threads, "kind": kind,
-            "sample": "%d of %d needles through %s over a %d-row index, dht=%d, %d threads, %.2f s "
-                      "(nominal needles x rows / time; tree build %.2f s not counted)" %
-                      (m2, n, "the reference VpTree (DctTree::search)" if ref is not None else "the brute-force port",
-                       n, DHT, threads, t2, build_s),
-            "seconds": t2, "needles": m2, "hits": int(total)}
+    def rate(self, budget_s, threads):
+        n = len(self.hashes)
+        m = min(n, 64 * threads)
+        t, _ = self.count(self.hashes[:m], threads)  # calibration
+        per = max(t / m, 1e-9)
+        m2 = int(min(n, max(m, budget_s / per)))
+        t2, total = self.count(self.hashes[:m2], threads)
+        what = "the reference VpTree (DctTree::search)" if self.tree is not None else "the brute-force port"
+        return {"value": m2 * float(n) / t2, "unit": "comparisons/s", "cores": threads, "kind": self.kind,
+                "sample": "%d of %d needles through %s over a %d-row index, dht=%d, %d threads, %.2f s (nominal needles x "
+                          "rows / time; tree build %.2f s not counted)" % (m2, n, what, n, DHT, threads, t2, self.build_s),
+                "seconds": t2, "needles": m2, "hits": total}
+
+
+def expected_hits(n, seed, planted_frac=0.1, max_flips=6, threshold=DHT):
+    """exact -similar hit count of synth.dct_hashes_fast from its own planting plan: n self pairs + 2 x the pairs
+    closer than the threshold inside every cluster {source row, rows planted from it}. Pairs of unrelated random
+    64-bit hashes under the threshold are not counted (expected number n^2 * 3.7e-14)."""
+    from cbird_b200 import synth
+
+    h, _, dst, src = synth.dct_hashes_fast(n, seed, planted_frac, max_flips, return_plan=True)
+    if len(dst) == 0:
+        return n
+    planted = np.zeros(n, bool)
+    planted[dst] = True
+    # cluster key = source row; the source row itself belongs to the cluster when it still holds its own value
+    keys = np.concatenate([src, np.unique(src[~planted[src]])])
+    rows = np.concatenate([dst, np.unique(src[~planted[src]])])
+    order = np.lexsort((rows, keys))
+    keys, vals = keys[order], h[rows[order]]
+    pairs = 0
+    for off in range(1, 64):
+        same = keys[off:] == keys[:-off]
+        if not same.any():
+            break
+        x = vals[off:][same] ^ vals[:-off][same]
+        d = np.zeros(len(x), np.int64)
+        for s in range(0, 64, 16):
+            d += POP16[((x >> np.uint64(s)) & np.uint64(0xFFFF)).astype(np.int64)]
+        pairs += int((d < threshold).sum())
+    return n + 2 * pairs
+
+
+POP16 = np.array([bin(i).count("1") for i in range(1 << 16)], np.int64)
+
+
+def workload_config(world, n_rows):
+    return {"workload": "DctHashIndex -similar all-pairs, %d synthetic 64-bit dct hashes (10%% planted near-duplicates), dht=%d "
+                        "+ searchIndex post step (maxMatches unlimited, filterSelf off): BASELINE configs[2]" % (n_rows, DHT),
+            "rows": n_rows, "dht": DHT, "seed": SEED,
+            "parallelism": "%d rank(s): hashes replicated, chunk buckets of the multi-index self-join dealt to the ranks, NCCL "
+                           "all-to-all of the hit keys to the ranks owning the needle rows, sort + post step per rank" % world,
+            "algorithm": "exact multi-index (pigeonhole) self-join: 63 usable bits in dht chunks, rows bucketed per chunk by one "
+                         "radix sort, unordered pairs inside a bucket tested once; identical hit set to the brute-force scan and "
+                         "to the reference VP tree (checked in this run: `parity`)",
+            "comparisons": "nominal rows^2 per step (reference semantics: every row is a needle against the whole index); the pair "
+                           "tests actually issued are in roofline.issued_pair_tests",
+            "l2": "256 MiB buffer written between timed steps (80 MB of hashes would otherwise stay in the 126 MB L2)"}
 
 
 def run_reference_arm(args):
@@ -175,23 +238,24 @@ def run_reference_arm(args):
     from cbird_b200 import synth
 
     world = args.gpus
-    n_rows = rows_for(world)
-    hashes, ids = synth.dct_hashes_fast(n_rows, seed=3)
+    n_rows = args.rows
+    hashes, ids = synth.dct_hashes_fast(n_rows, seed=SEED)
     threads = os.cpu_count() or 1
+    tree = RefTree(hashes, ids)
     # K+W bounded samples; keep the whole run within a few minutes
     budget = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
-    res = None
-    times = []
+    res, times = None, []
     for i in range(args.warmup + args.steps):
-        res = cpu_reference_rate(hashes, ids, budget, threads)
+        res = tree.rate(budget, threads)
         if i >= args.warmup:
             times.append(res)
+    tree.close()
     value = float(np.mean([r["value"] for r in times]))
     ms = float(np.mean([r["seconds"] for r in times])) * 1e3
     line = {
         "impl": "reference", "metric": "hamming_comparisons_per_sec", "value": value, "unit": "comparisons/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(world, n_rows),
         "cpu_baseline": {"value": value, "unit": "comparisons/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
@@ -201,52 +265,31 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-ROWS_OVERRIDE = 0
-
-
-def rows_for(world):
-    # weak scaling: every GPU keeps BASE_ROWS^2 pair tests per step -> rows = BASE_ROWS * sqrt(world)
-    n = ROWS_OVERRIDE or int(round(BASE_ROWS * (world ** 0.5)))
-    return (n + 4095) // 4096 * 4096
-
-
-def workload_config(world, n_rows):
-    return {"workload": "DctHashIndex -similar all-pairs, %d synthetic 64-bit dct hashes (10%% planted near-duplicates), "
-                        "dht=%d; N=1 is BASELINE configs[1]'s 1M-hash index, N>1 grows rows by sqrt(N) (configs[2] shape)"
-                        % (n_rows, DHT),
-            "rows": n_rows, "dht": DHT, "seed": 3,
-            "parallelism": "hashes replicated, chunk buckets of the multi-index self-join dealt to %d rank(s), NCCL all-gather "
-                           "of the (disjoint) hit lists" % world,
-            "algorithm": "exact multi-index (pigeonhole) self-join for dht <= 10: 63 usable bits in dht chunks, rows bucketed per "
-                         "chunk by one radix sort, only rows sharing a bucket are compared; identical hit set to the brute-force "
-                         "scan (tests/test_mih_gpu.py). The brute-force symmetric scan is timed beside it (roofline.brute_force_scan)",
-            "comparisons": "nominal rows^2 per step (reference semantics: every row is a needle against the whole index); the pair "
-                           "tests actually issued are reported in roofline.issued_pair_tests",
-            "l2": "256 MiB buffer written between timed steps (inputs are 8 B/row and fit L2)"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip dct_hash / single-needle / cpu_baseline legs")
-    ap.add_argument("--rows", type=int, default=0, help="override the index size (e.g. 10000000 = BASELINE configs[2]); "
-                                                        "default 2^20 * sqrt(gpus) (weak scaling)")
+    ap.add_argument("--rows", type=int, default=DEFAULT_ROWS, help="index size (default 10^7 = BASELINE configs[2])")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline leg")
+    ap.add_argument("--legs", default="target_100M,dct_hash,find,video,orb,nonuniform",
+                    help="extra legs to run (comma list)")
+    ap.add_argument("--parity-needles", type=int, default=20000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    global ROWS_OVERRIDE
-    ROWS_OVERRIDE = max(0, args.rows)
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    legs = set() if args.no_extras else set(x for x in args.legs.split(",") if x)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        legs &= {"target_100M"}  # the other legs are single-GPU measurements (rank 0 would keep the others waiting)
 
     import torch
     import torch.distributed as dist
 
     import cbird_b200 as cb
-    from cbird_b200 import build, parallel, synth
+    from cbird_b200 import build, synth
 
     build.build()
     L = cb.lib()
@@ -261,343 +304,446 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     cb._lib.check(L.cb_set_device(local_rank))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
-
-    hbm_peak, sm_max_mhz, peak_src = load_peaks()
-    n_rows = rows_for(world)
-    hashes, ids = synth.dct_hashes_fast(n_rows, seed=3)
-    h_hashes = torch.from_numpy(hashes.view(np.int64)).pin_memory()
-    h_ids = torch.from_numpy(ids.view(np.int32)).pin_memory()
-    d_hashes = h_hashes.to(dev, non_blocking=True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sharded = parallel.ShardedSimilar(n_rows, dev)
-    torch.cuda.synchronize()
+    if world > 1:
+        # torch.distributed carries the NCCL id of the library's own communicator and reduces the timings;
+        # the data path (all-gather of the rows, all-to-all of the hits) is inside the library
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            assert L.cb_comm_unique_id(buf, 128) == 128, L.cb_last_error()
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        cb._lib.check(L.cb_comm_init_rank(raw, 128, rank, world, local_rank))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        return sharded.similar(d_hashes, DHT)
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    hbm_peak, sm_max_mhz, peak_src = load_peaks()
+    n_rows = args.rows
+    hashes, ids = synth.dct_hashes_fast(n_rows, seed=SEED)
+    h_hashes = torch.from_numpy(hashes.view(np.int64)).pin_memory()
+    h_ids = torch.from_numpy(ids.view(np.int32)).pin_memory()
+    np_ids, np_hashes = h_ids.numpy().view(np.uint32), h_hashes.numpy().view(np.uint64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    params = cb.SearchParams(dctThresh=DHT, filterSelf=False, maxMatches=1 << 30)
+    ix = cb.DctHashIndex()
+    ix.load(np_ids, np_hashes)
 
     # ---------------- device-resident value ----------------
     for _ in range(max(args.warmup, 3)):
-        merged = step_device()
-    n_hits = int(merged.shape[0])
+        n_kept, issued = ix.similar_count(params)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    cb_stats0 = cb._lib.cb_stats()
-    L.cb_stats_get(C.byref(cb_stats0))
+    stats0 = cb._lib.cb_stats()
+    L.cb_stats_get(C.byref(stats0))
+    prof = cb._lib.cb_profile()
+    L.cb_profile_get(C.byref(prof), 1)
+    L.cb_profile_enable(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    walls = []
     barrier()
     wall0 = time.time()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed steps (not inside the timed span)
+        barrier()
         ev[i][0].record()
-        kev[i][0].record()
-        local = sharded.scan_local(d_hashes, DHT)
-        kev[i][1].record()
-        merged = parallel.allgather_hits(local)
+        t0 = time.time()
+        n_kept, issued = ix.similar_count(params)  # blocking: returns when this rank's streams have drained
+        walls.append(time.time() - t0)
         ev[i][1].record()
     barrier()
     wall = time.time() - wall0
-    cb_stats1 = cb._lib.cb_stats()
-    L.cb_stats_get(C.byref(cb_stats1))
-    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms = float(t[0]), float(t[1])
-    launches = int(cb_stats1.kernel_launches - cb_stats0.kernel_launches)
+    L.cb_profile_enable(0)
+    L.cb_profile_get(C.byref(prof), 1)
+    stats1 = cb._lib.cb_stats()
+    L.cb_stats_get(C.byref(stats1))
+    step_ms = reduce_max(sum(a.elapsed_time(b) for a, b in ev) / args.steps)
+    launches = int(stats1.kernel_launches - stats0.kernel_launches)
     comparisons = float(n_rows) * float(n_rows)
     value = comparisons / (step_ms * 1e-3)
-    path = sharded.last_path
-    issued_local = (float(cb_stats1.comparisons - cb_stats0.comparisons) / args.steps if path == "mih"
-                    else float(sharded.issued_pair_tests()))
+    hits_total = int(reduce_sum(n_kept))
+    issued_total = reduce_sum(issued)
+    S = cb._lib.PROFILE_SLOTS
+    bucket_ms = prof.ms[S["mih_bucket_kernel"]] / max(1, prof.launches[S["mih_bucket_kernel"]])
+    bucket_ms_step = reduce_max(prof.ms[S["mih_bucket_kernel"]] / args.steps)
+    sort_ms_step = reduce_max((prof.ms[S["mih_sort"]] + prof.ms[S["hit_sort"]]) / args.steps)
+    scan_ms_step = reduce_max(prof.ms[S["scan64_kernel"]] / args.steps)
 
-    # ---------------- the brute-force symmetric scan of the same job, timed beside it ----------------
-    brute = None
-    if path == "mih":
-        bsh = parallel.ShardedSimilar(n_rows, dev, mih=False)
-        bsh.scan_local(d_hashes, DHT)
-        bt = []
-        for i in range(3):
-            flush.fill_(i)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            bl = bsh.scan_local(d_hashes, DHT)
-            b.record()
-            torch.cuda.synchronize()
-            bt.append(a.elapsed_time(b))
-        bt = torch.tensor([sum(bt) / len(bt)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
-        brute = {"kernel_ms": float(bt[0]), "issued": float(bsh.issued_pair_tests()), "hits_local": int(bl.shape[0])}
-        del bsh
-
-    # ---------------- e2e through the public API, host buffers ----------------
-    host_out = {"buf": None}
-
-    trace = os.environ.get("CB_BENCH_TRACE") and rank == 0
-
+    # ---------------- e2e through the public API, host buffers, the same call at every N ----------------
     def step_e2e():
-        t_a = time.time()
-        hh = h_hashes.to(dev, non_blocking=True)  # H2D of this step's input from pinned memory
-        local = sharded.scan_local(hh, DHT)
-        t_b = time.time()
-        m = parallel.allgather_hits(local)        # every rank ends up with the merged list on its device
-        t_c = time.time()
-        if rank != 0:
-            torch.cuda.synchronize()
-            return m
-        if host_out["buf"] is None or host_out["buf"].shape[0] < m.shape[0]:
-            host_out["buf"] = torch.empty((int(m.shape[0] * 1.25) + 1024, 4), dtype=torch.int32).pin_memory()
-        out = host_out["buf"][: m.shape[0]]
-        out.copy_(m, non_blocking=True)           # D2H of the step's result to the caller (rank 0)
-        torch.cuda.synchronize()
-        if trace:
-            print("e2e trace: h2d+scan %.2f ms, all-gather %.2f ms, d2h %.2f ms" % ((t_b - t_a) * 1e3, (t_c - t_b) * 1e3,
-                                                                                    (time.time() - t_c) * 1e3), file=sys.stderr)
-        return out
+        ix.load(np_ids, np_hashes)      # H2D inside the C ABI (this rank's rows + all-gather when N > 1)
+        return ix.similar(params)       # CSR of this process's needle rows on the host
 
     e2e_steps = max(3, min(args.steps, 5))
-    if world == 1:
-        ix = cb.DctHashIndex()
-        params = cb.SearchParams(dctThresh=DHT, filterSelf=False, maxMatches=1 << 30)
-        np_ids, np_hashes = h_ids.numpy().view(np.uint32), h_hashes.numpy().view(np.uint64)
-
-        def step_e2e():  # noqa: F811 — N=1 goes through the Index plugin surface itself
-            ix.load(np_ids, np_hashes)          # H2D inside the C ABI
-            return ix.similar(params)[1]        # hits on the host (sorted by needle, score, id)
-    for _ in range(3):  # warm-up: pinned result buffers, allocator and NCCL buffers reach their steady state
-        out = step_e2e()
+    for _ in range(3):  # warm-up: pinned result buffers and NCCL buffers reach their steady state
+        off, out = step_e2e()
     barrier()
     t0 = time.time()
     for _ in range(e2e_steps):
-        out = step_e2e()
+        off, out = step_e2e()
     barrier()
-    e2e_s = (time.time() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
-    e2e_hits = int(len(out))
-    hit_bytes = 12 if world == 1 else 16
+    e2e_s = reduce_max((time.time() - t0) / e2e_steps)
+    r0, r1 = ix.shard_rows()
+    h2d = 12 * (r1 - r0) if world > 1 else 12 * n_rows
     e2e = {"value": comparisons / e2e_s, "unit": "comparisons/s",
-           "h2d_bytes_per_step": int((12 if world == 1 else 8) * n_rows),
-           "d2h_bytes_per_step": int(e2e_hits * hit_bytes + 16),
+           "h2d_bytes_per_step": int(reduce_sum(h2d)), "d2h_bytes_per_step": int(reduce_sum(len(out) * 12 + (r1 - r0 + 1) * 8)),
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "DctHashIndex.load + .similar (cb_dct_index_load / cb_dct_index_similar_alloc)" if world == 1
-                  else "ShardedSimilar.similar on host-pinned hashes (cb_scan64_dev + NCCL all-gather) + D2H"}
-
+           "api": "DctHashIndex.load + .similar (cb_dct_index_load / cb_dct_index_similar_alloc) on every rank; pinned host "
+                  "buffers in, CSR (offsets, hits sorted by score, id) of the rank's needle rows out"}
     clocks = sampler.finish() if rank == 0 else None
+
+    # ---------------- parity, every run ----------------
+    parity = None
+    threads = os.cpu_count() or 1
+    tree = None
+    if rank == 0:
+        parity = {"hits_total": hits_total, "e2e_hits_rank0": int(len(out))}
+        want_total = expected_hits(n_rows, SEED)
+        parity["expected_hits_from_planted_clusters"] = int(want_total)
+        parity["total_matches_expectation"] = bool(abs(hits_total - want_total) <= 2)
+        tree = RefTree(hashes, ids)
+        m = min(args.parity_needles, r1 - r0)
+        pick = np.sort(np.random.default_rng(11).choice(r1 - r0, size=m, replace=False)) + r0
+        want = tree.lists(hashes[pick], threads)  # (needle index in pick, id, dist), removed ids never occur here
+        rows = np.concatenate([np.full(int(off[p - r0 + 1] - off[p - r0]), k, np.int64) for k, p in enumerate(pick)]) if m else np.zeros(0, np.int64)
+        sel = np.concatenate([np.arange(off[p - r0], off[p - r0 + 1]) for p in pick]) if m else np.zeros(0, np.int64)
+        got = np.stack([rows, out["mediaId"][sel].astype(np.int64), out["score"][sel].astype(np.int64)], 1)
+        got = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))]
+        parity.update({"needles_compared_with_reference_vptree": int(m), "reference_matches": int(len(want)),
+                       "identical": bool(len(got) == len(want) and np.array_equal(got, want)),
+                       "checker": tree.kind + (" VpTree (oracle/_ref)" if tree.kind == "reference" else " brute force")})
+        if not parity["identical"] or not parity["total_matches_expectation"]:
+            print("PARITY FAILURE: " + json.dumps(parity), file=sys.stderr, flush=True)
 
     extras = {}
     if rank == 0 and not args.no_extras:
-        # ---- exact variant (2 POPC / pair): the nominal-roofline kernel ----
-        L.cb_scan64_force_variant(0)
-        sub = min(n_rows, 1 << 19)
-        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        buf = torch.empty((1 << 22, 4), dtype=torch.int32, device=dev)
-        ms_best = 1e30
-        for r in range(4):
-            cnt.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cb._lib.check(L.cb_scan64_dev(d_hashes.data_ptr(), sub, d_hashes.data_ptr(), sub, DHT, 0, buf.data_ptr(),
-                                          buf.shape[0], cnt.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            b.record()
-            torch.cuda.synchronize()
-            if r:
-                ms_best = min(ms_best, a.elapsed_time(b))
-        L.cb_scan64_force_variant(-1)
-        exact_rate = float(sub) * sub / (ms_best * 1e-3)
-        extras["exact_rate"] = exact_rate
+        extras["cpu_baseline"] = tree.rate(10.0, threads)
+    if tree is not None:
+        tree.close()
+    del tree
 
-        # ---- kernel (a): DCT hashing of 2^20 32x32 frames ----
-        frames = synth.luma_frames(HASH_FRAMES, seed=2)
-        h_frames = torch.from_numpy(frames).pin_memory()
-        d_frames = h_frames.to(dev)
-        d_out = torch.empty(HASH_FRAMES, dtype=torch.int64, device=dev)
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for _ in range(3):
-            cb._lib.check(L.cb_hash_batch_dev(d_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, d_out.data_ptr(), stream))
-        torch.cuda.synchronize()
-        hk = []
-        for i in range(10):
-            flush.fill_(i)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cb._lib.check(L.cb_hash_batch_dev(d_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, d_out.data_ptr(), stream))
-            b.record()
-            torch.cuda.synchronize()
-            hk.append(a.elapsed_time(b))
-        hash_ms = float(np.mean(hk))
-        out_np = np.zeros(HASH_FRAMES, np.uint64)
-        cb._lib.check(L.cb_hash_batch(h_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, out_np.ctypes.data))
-        t0 = time.time()
-        for _ in range(3):
-            cb._lib.check(L.cb_hash_batch(h_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, out_np.ctypes.data))
-        hash_e2e_s = (time.time() - t0) / 3
-        assert np.array_equal(out_np, d_out.cpu().numpy().view(np.uint64))
-        hash_bytes = HASH_FRAMES * 1032.0
-        extras["dct_hash"] = {
-            "metric": "dct_hashes_per_sec", "value": HASH_FRAMES / (hash_ms * 1e-3), "unit": "frames/s",
-            "ms": hash_ms, "frames": HASH_FRAMES, "shape": "32x32 u8 luma",
-            "e2e": {"value": HASH_FRAMES / hash_e2e_s, "unit": "frames/s", "h2d_bytes_per_step": HASH_FRAMES * 1024,
-                    "d2h_bytes_per_step": HASH_FRAMES * 8},
-            "roofline": {"bound": "hbm", "achieved": hash_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": hash_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": ncu_traffic("dct_hash32_kernel"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_frame": 1032}}
-        # video-sized frames (the decoder hands 128x128 luma, src/scanner.cpp:1043-1048): fused
-        # stage->blur->INTER_AREA->hash kernel, one CTA per frame
-        vbase = synth.video_frames(256, seed=3, letterbox=(12, 0))
-        nv = 1 << 15
-        d_v = torch.from_numpy(np.tile(vbase, (nv // 256, 1, 1))).to(dev)
-        d_vo = torch.empty(nv, dtype=torch.int64, device=dev)
-        vt = []
-        for i in range(8):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cb._lib.check(L.cb_hash_batch_dev(d_v.data_ptr(), nv, 128, 128, 128, 128 * 128, d_vo.data_ptr(), stream))
-            b.record()
-            torch.cuda.synchronize()
-            vt.append(a.elapsed_time(b))
-        v_ms = float(np.mean(vt[2:]))
-        extras["dct_hash_video"] = {"metric": "dct_hashes_per_sec", "value": nv / (v_ms * 1e-3), "unit": "frames/s",
-                                    "shape": "128x128 u8 luma (k=5 blur + INTER_AREA 4x4 + DCT hash)", "frames": nv, "ms": v_ms,
-                                    "roofline": {"bound": "hbm", "achieved": nv * 16392.0 / (v_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                                 "unit": "GB/s", "frac": nv * 16392.0 / (v_ms * 1e-3) / 1e9 / hbm_peak,
-                                                 "algorithmic_bytes_per_frame": 16392, "traffic": None}}
-        del d_v
-        # CPU baseline for the hash: the oracle's plain-C++ restatement on all host cores, bounded sample
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import pyoracle as po
-        threads = os.cpu_count() or 1
-        sample = frames[: 1 << 18]
-        _, ms = po.dct_hash64_batch(sample, threads=threads)
-        extras["dct_hash"]["cpu_baseline"] = {"value": len(sample) / (ms * 1e-3), "unit": "frames/s", "cores": threads,
-                                              "kind": "port", "sample": "%d of %d frames, oracle C++ restatement of dctHash64" % (len(sample), HASH_FRAMES)}
-
-        # ---- single-needle find over the 1M index (cfg2, latency-bound) ----
-        ix1 = cb.DctHashIndex()
-        ix1.load(ids[:BASE_ROWS], hashes[:BASE_ROWS])
-        p5 = cb.SearchParams(dctThresh=DHT)
-        for r in range(3):
-            ix1.find(cb.Media(dctHash=int(hashes[r])), p5)
-        t0 = time.time()
-        for r in range(200):
-            ix1.find(cb.Media(dctHash=int(hashes[r])), p5)
-        single_us = (time.time() - t0) / 200 * 1e6
-        t0 = time.time()
-        ix1.find_batch(hashes[:1000], p5)
-        batch_s = time.time() - t0
-        extras["single_needle"] = {"index_rows": BASE_ROWS, "find_latency_us": single_us,
-                                   "batched_1000_needles_per_s": 1000 / batch_s,
-                                   "note": "8 MB streamed per needle = 1.2 us at HBM peak: launch/sync latency bound"}
-        extras["cpu_baseline"] = cpu_reference_rate(hashes, ids, 12.0, threads)
-        # equal-work CPU leg: the reference's RadixMap_t with radix 0 = one bucket = brute force (radix.h:187-210)
-        ref = po.ref()
-        if ref is not None:
-            hh = np.ascontiguousarray(hashes[:BASE_ROWS])
-            radix = ref.ref_radix_create(0)
-            ref.ref_radix_insert(radix, np.zeros(len(hh), np.uint32), np.arange(len(hh), dtype=np.int32), hh, len(hh))
-            m = 256 * threads
-            ms = C.c_double(0)
-            ref.ref_radix_search_batch_count(radix, hh[:m], m, DHT, threads, C.byref(ms))
-            m2 = int(min(len(hh), max(m, m * 4000.0 / max(ms.value, 1e-3))))
-            ref.ref_radix_search_batch_count(radix, hh[:m2], m2, DHT, threads, C.byref(ms))
-            ref.ref_radix_destroy(radix)
-            extras["cpu_brute_force"] = {"value": m2 * float(len(hh)) / (ms.value * 1e-3), "unit": "comparisons/s",
-                                         "cores": threads, "kind": "reference",
-                                         "sample": "%d needles x %d rows through the reference RadixMap_t(radix 0), %.2f s" % (m2, len(hh), ms.value / 1e3)}
-        # OpenCV itself (the reference's own arithmetic) on one core, small sample
-        try:
-            import dcthash_cv2 as dc
-            t0 = time.time()
-            for f in frames[:20000]:
-                dc.hash_from_tile32_cv2(f)
-            extras["dct_hash"]["cpu_cv2_single_core"] = {"value": 20000 / (time.time() - t0), "unit": "frames/s",
-                                                         "sample": "20000 frames through python cv2 (cv2.dct etc., call overhead included)"}
-        except Exception as e:  # cv2 missing on the box: not fatal for the bench line
-            extras["dct_hash"]["cpu_cv2_single_core"] = {"unavailable": str(e)}
+    # ---------------- extra legs ----------------
+    if "target_100M" in legs:
+        extras["target_100M"] = leg_target(cb, L, torch, dist, dev, rank, world, barrier, reduce_max, reduce_sum, flush)
+    if rank == 0:
+        if "dct_hash" in legs:
+            extras.update(leg_dct_hash(cb, L, torch, dev, flush, hbm_peak, peak_src))
+        if "find" in legs:
+            extras["find"] = leg_find(cb, hashes, ids)
+        if "nonuniform" in legs:
+            extras["nonuniform"] = leg_nonuniform(cb, L, torch, dev)
+        if "video" in legs:
+            extras["video"] = leg_video(cb)
+        if "orb" in legs:
+            extras["orb"] = leg_orb(cb, sm_max_mhz)
 
     if rank == 0:
-        popc_peak = SM_COUNT * POPC_PER_CLK_SM * sm_max_mhz * 1e6          # POPC.b32 lanes / s
-        pair_peak = popc_peak / 2.0                                          # nominal algorithm: 2 POPC per pair
-        variant = int(L.cb_scan64_variant(DHT))
-        peak_note = "148 SM x 16 POPC lanes/clk/SM (measured, profiles/pipe_probe_r01.json) x %.0f MHz max SM clock" % sm_max_mhz
-
-        def scan_roofline(ms, issued):
-            rate = issued / (ms * 1e-3)  # rank 0, scan kernel only, ISSUED pair tests
-            return {"kernel": "scan64_kernel<%d>" % variant, "achieved": rate * 2.0 / 1e12, "frac": rate / pair_peak,
-                    "kernel_ms": ms, "pairs_issued_per_launch": issued, "issued_popc_per_pair": {2: 0.5, 1: 1.0, 0: 2.0}[variant],
-                    "traffic": ncu_traffic("scan64_kernel<%d>" % variant),
-                    "traffic_note": "bytes per launch from the committed ncu capture at 2^19 x 2^19 rows (algorithmic: 8 B per row "
-                                    "= 4.2 MB)",
-                    "note": "symmetric half of the pair grid; variant 2 pre-filters with a lower bound that costs 0.5 POPC/pair "
-                            "and re-tests survivors exactly, so frac (on 2 POPC per ISSUED pair) exceeds 1; exact_variant is the "
-                            "2-POPC kernel on the full square"}
-
-        if path == "mih":
-            nominal_local = comparisons / world
-            roofline = {
-                "bound": "int_pipe",
-                "kernel": "multi-index self-join pass: mih_keys_kernel, cub radix sort, mih_gather/bounds/tile kernels, "
-                          "mih_small_kernel (+ scan64_tiles_mih_kernel for buckets over 1024 rows)",
-                "achieved": nominal_local * 2.0 / (kern_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12,
-                "unit": "TPOPC/s (nominal 2 POPC.b32 per 64-bit pair)",
-                "frac": nominal_local / (kern_ms * 1e-3) / pair_peak,
-                "traffic": mih_traffic(), "peak_source": peak_note, "kernel_ms": kern_ms,
-                "traffic_note": "dram bytes of one mih_small_kernel launch (69 % of the pass) from the committed ncu capture at "
-                                "2^20 rows, dht 5 (profiles/ncu_mih_small_r01.json); algorithmic: 8 B per row in + 16 B per hit out",
-                "nominal_pairs_per_launch": nominal_local, "issued_pair_tests": issued_local,
-                "issued_share_of_nominal": issued_local / nominal_local, "algorithmic_popc_per_pair": 2,
-                "issued_popc_frac": issued_local / (kern_ms * 1e-3) / popc_peak,  # 1 pre-filter POPC per issued test, whole pass
-                "note": "achieved = ALGORITHMIC work (2 POPC per nominal pair, SURVEY 8d) / pass time. frac is far above 1 because "
-                        "the pass is an exact index, not a faster pair test: it issues issued_pair_tests, a small share of the "
-                        "nominal square, and its time goes to the sort and the bucket scans (profiles/launches_bench_r01.csv). "
-                        "Kernel quality against the POPC roofline is what brute_force_scan reports",
-            }
-            if brute:
-                roofline["brute_force_scan"] = scan_roofline(brute["kernel_ms"], brute["issued"])
-                roofline["brute_force_scan"]["speedup_of_multi_index_pass"] = brute["kernel_ms"] / kern_ms
-        else:
-            roofline = scan_roofline(kern_ms, issued_local)
-            roofline.update({"bound": "int_pipe", "peak": popc_peak / 1e12, "unit": "TPOPC/s (nominal 2 POPC.b32 per 64-bit pair)",
-                             "peak_source": peak_note, "nominal_pairs_per_launch": comparisons / world,
-                             "algorithmic_popc_per_pair": 2})
-        if "exact_rate" in extras:
-            (roofline.get("brute_force_scan") or roofline)["exact_variant"] = {
-                "kernel": "scan64_kernel<0>", "achieved": extras["exact_rate"] * 2 / 1e12,
-                "frac": extras["exact_rate"] / pair_peak, "comparisons_per_s": extras["exact_rate"]}
+        popc_peak = SM_COUNT * POPC_PER_CLK_SM * sm_max_mhz * 1e6  # POPC.b32 lanes / s
+        alu_peak = SM_COUNT * ALU_PER_CLK_SM * sm_max_mhz * 1e6    # LOP3 lanes / s
+        pair_peak = popc_peak / 2.0                                 # nominal algorithm: 2 POPC per pair
+        cv, cn = C.c_int(1), C.c_int(1)
+        L.cb_scan64_mih_config(n_rows, DHT, C.byref(cv), C.byref(cn))
+        variant, need = int(cv.value), int(cn.value)
+        popc_per_test = {1: 1.0, 2: 0.5, 3: 0.5}[variant]
+        lop_per_test = {1: 2.0, 2: 1.5, 3: 2.5}[variant]
+        issued_rank0 = float(issued)
+        k_s = max(bucket_ms_step, 1e-9) * 1e-3
+        popc_frac = issued_rank0 * popc_per_test / k_s / popc_peak
+        alu_frac = issued_rank0 * lop_per_test / k_s / alu_peak
+        roofline = {
+            "bound": "int_pipe", "kernel": ("mih_bucket_kernel<%d>" % variant) if need == 1 else "mih_walk_kernel",
+            "chunks_per_bucket_key": need,
+            "achieved": issued_rank0 * popc_per_test / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
+            "frac": popc_frac,
+            "frac_definition": "POPC.b32 lane-instructions EXECUTED by the dominant kernel (issued pair tests x %.1f: one POPC "
+                               "per two pairs in the pre-filter) / its CUDA-event duration on the library's stream / POPC peak"
+                               % popc_per_test,
+            "alu_pipe_frac": alu_frac,
+            "alu_pipe_note": "the pre-filter costs %.1f LOP3 per pair test; LOP3 peak = 148 SM x 64 lanes/clk (measured). The "
+                             "kernel is bound by whichever of the two integer pipes is fuller" % lop_per_test,
+            "kernel_ms_per_step": bucket_ms_step, "kernel_ms_per_launch": bucket_ms,
+            "kernel_share_of_step": bucket_ms_step / step_ms, "sort_ms_per_step": sort_ms_step,
+            "brute_scan_ms_per_step": scan_ms_step,
+            "issued_pair_tests": issued_total, "issued_pair_tests_rank0": issued_rank0,
+            "issued_share_of_nominal": issued_total / comparisons,
+            "nominal_frac": comparisons / world / (step_ms * 1e-3) / pair_peak,
+            "nominal_frac_note": "rows^2 x 2 POPC / step time / peak: NOT a hardware fraction (the index issues a small share of "
+                                 "the square); kept because SURVEY 8d defines the metric on nominal comparisons",
+            "traffic": committed_traffic("mih_bucket_kernel"),
+            "peak_source": "148 SM x 16 POPC lanes/clk/SM (measured, profiles/pipe_probe_r01.json) x %.0f MHz max SM clock" % sm_max_mhz,
+        }
         line = {
             "metric": "hamming_comparisons_per_sec", "value": value, "unit": "comparisons/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "strong" if ROWS_OVERRIDE else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(world, n_rows),
-            "hits_per_step": n_hits, "kernel_ms_per_step": kern_ms, "wall_s_timed_region": wall, "path": path,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "hits_per_step": hits_total, "wall_ms_per_step": float(np.mean(walls)) * 1e3, "wall_s_timed_region": wall,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity": parity,
         }
         if "cpu_baseline" in extras:
-            cbl = extras["cpu_baseline"]
+            cbl = extras.pop("cpu_baseline")
             line["cpu_baseline"] = {k: cbl[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        for k in ("dct_hash", "dct_hash_video", "single_needle", "cpu_brute_force"):
-            if k in extras:
-                line[k] = extras[k]
+        line.update(extras)
         print(json.dumps(line), flush=True)
+    del ix
     if world > 1:
         dist.barrier()
+        L.cb_shutdown()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# extra legs
+# ---------------------------------------------------------------------------------------------------------
+def leg_target(cb, L, torch, dist, dev, rank, world, barrier, reduce_max, reduce_sum, flush):
+    """the north_star's target: -similar over a 10^8-hash index (every rank: replicated hashes, its share of buckets)."""
+    from cbird_b200 import synth
+
+    n = TARGET_ROWS
+    t0 = time.time()
+    h, ids = synth.dct_hashes_fast(n, seed=SEED + 1)
+    gen_s = time.time() - t0
+    ix = cb.DctHashIndex()
+    t0 = time.time()
+    ix.load(ids, h)
+    load_s = time.time() - t0
+    params = cb.SearchParams(dctThresh=DHT, filterSelf=False, maxMatches=1 << 30)
+    kept, issued = ix.similar_count(params)  # warm-up (allocations)
+    times = []
+    for i in range(2):
+        flush.fill_(i)
+        barrier()
+        t0 = time.time()
+        kept, issued = ix.similar_count(params)
+        times.append(time.time() - t0)
+    barrier()
+    ms = reduce_max(float(np.mean(times)) * 1e3)
+    total = int(reduce_sum(kept))
+    out = {"rows": n, "dht": DHT, "ms_per_pass": ms, "value": float(n) * n / (ms * 1e-3), "unit": "comparisons/s (nominal rows^2)",
+           "hits": total, "issued_pair_tests": reduce_sum(issued), "load_s": load_s, "synth_s": gen_s,
+           "what": "DctHashIndex.similar_count (bucket pass, exchange, hit sort, post step; lists stay on the device)"}
+    if rank == 0:
+        want = expected_hits(n, SEED + 1)
+        out["expected_hits_from_planted_clusters"] = int(want)
+        out["hit_count_matches"] = bool(abs(total - want) <= 4)
+    del ix
+    return out
+
+
+def leg_dct_hash(cb, L, torch, dev, flush, hbm_peak, peak_src):
+    from cbird_b200 import synth
+
+    out = {}
+    frames = synth.luma_frames(HASH_FRAMES, seed=2)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = h_frames.to(dev)
+    d_out = torch.empty(HASH_FRAMES, dtype=torch.int64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        cb._lib.check(L.cb_hash_batch_dev(d_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, d_out.data_ptr(), stream))
+    torch.cuda.synchronize()
+    hk = []
+    for i in range(10):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cb._lib.check(L.cb_hash_batch_dev(d_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, d_out.data_ptr(), stream))
+        b.record()
+        torch.cuda.synchronize()
+        hk.append(a.elapsed_time(b))
+    hash_ms = float(np.mean(hk))
+    out_np = np.zeros(HASH_FRAMES, np.uint64)
+    cb._lib.check(L.cb_hash_batch(h_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, out_np.ctypes.data))
+    t0 = time.time()
+    for _ in range(3):
+        cb._lib.check(L.cb_hash_batch(h_frames.data_ptr(), HASH_FRAMES, 32, 32, 32, 1024, out_np.ctypes.data))
+    hash_e2e_s = (time.time() - t0) / 3
+    assert np.array_equal(out_np, d_out.cpu().numpy().view(np.uint64))
+    hash_bytes = HASH_FRAMES * 1032.0
+    out["dct_hash"] = {
+        "metric": "dct_hashes_per_sec", "unit": "frames/s", "frames": HASH_FRAMES, "shape": "32x32 u8 luma (BASELINE configs[1])",
+        "e2e": {"value": HASH_FRAMES / hash_e2e_s, "unit": "frames/s", "h2d_bytes_per_step": HASH_FRAMES * 1024,
+                "d2h_bytes_per_step": HASH_FRAMES * 8,
+                "note": "cb_hash_batch from pinned host frames: PCIe-bound (1 KB per frame in), this is the rate a caller with "
+                        "host-resident frames sees"},
+        "device_resident": {"value": HASH_FRAMES / (hash_ms * 1e-3), "unit": "frames/s", "ms": hash_ms,
+                            "note": "frames already in HBM (e.g. produced by a GPU decoder)"},
+        "roofline": {"bound": "hbm", "kernel": "dct_hash32_kernel", "achieved": hash_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": hash_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
+                     "traffic": committed_traffic("dct_hash32_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_frame": 1032}}
+    # video-sized frames (the decoder hands 128x128 luma, src/scanner.cpp:1043-1048): one CTA per frame
+    vbase = synth.video_frames(256, seed=3, letterbox=(12, 0))
+    nv = 1 << 15
+    d_v = torch.from_numpy(np.tile(vbase, (nv // 256, 1, 1))).to(dev)
+    d_vo = torch.empty(nv, dtype=torch.int64, device=dev)
+    vt = []
+    for i in range(8):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cb._lib.check(L.cb_hash_batch_dev(d_v.data_ptr(), nv, 128, 128, 128, 128 * 128, d_vo.data_ptr(), stream))
+        b.record()
+        torch.cuda.synchronize()
+        vt.append(a.elapsed_time(b))
+    v_ms = float(np.mean(vt[2:]))
+    out["dct_hash_video"] = {"metric": "dct_hashes_per_sec", "value": nv / (v_ms * 1e-3), "unit": "frames/s",
+                             "shape": "128x128 u8 luma (k=5 blur + INTER_AREA 4x4 + DCT hash)", "frames": nv, "ms": v_ms,
+                             "roofline": {"bound": "hbm", "kernel": "frame_hash_fused_kernel",
+                                          "achieved": nv * 16392.0 / (v_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": nv * 16392.0 / (v_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_frame": 16392,
+                                          "traffic": committed_traffic("frame_hash_fused_kernel")}}
+    del d_v
+    # CPU side: the oracle's C++ restatement on all cores, and OpenCV itself (the reference's arithmetic) on a sample —
+    # whose hashes also give this run's bit-flip rate against cv2
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    threads = os.cpu_count() or 1
+    sample = frames[: 1 << 18]
+    _, ms = po.dct_hash64_batch(sample, threads=threads)
+    out["dct_hash"]["cpu_baseline"] = {"value": len(sample) / (ms * 1e-3), "unit": "frames/s", "cores": threads, "kind": "port",
+                                       "sample": "%d of %d frames, oracle C++ restatement of dctHash64" % (len(sample), HASH_FRAMES)}
+    try:
+        import dcthash_cv2 as dc
+        ncv = 20000
+        t0 = time.time()
+        cvh = np.array([dc.hash_from_tile32_cv2(f) for f in frames[:ncv]], dtype=np.uint64)
+        cv_s = time.time() - t0
+        x = cvh ^ out_np[:ncv]
+        flipped = int(sum(POP16[((x >> np.uint64(s)) & np.uint64(0xFFFF)).astype(np.int64)].sum() for s in range(0, 64, 16)))
+        out["dct_hash"]["cpu_cv2_single_core"] = {"value": ncv / cv_s, "unit": "frames/s",
+                                                  "sample": "%d frames through python cv2 (cv2.dct etc., call overhead included)" % ncv}
+        out["dct_hash"]["flip_vs_cv2"] = {"hashes_compared": ncv, "hashes_differ": int((x != 0).sum()), "bits_flipped": flipped,
+                                          "bits_total": 63 * ncv, "cv2_version": dc.cv2.__version__,
+                                          "note": "GPU hashes of this run vs OpenCV's own f32 DCT on the same frames; flips are "
+                                                  "coefficients tied with the mean (north_star: stated, measured rate)"}
+    except Exception as e:  # cv2 missing on the box: not fatal for the bench line
+        out["dct_hash"]["flip_vs_cv2"] = {"unavailable": str(e)}
+    return out
+
+
+def leg_find(cb, hashes, ids):
+    """configs[1]'s second half: single-needle find over a 2^20-row index — one caller, and the reference's real call
+    pattern: many host threads calling find() at once (tools/find_bench.cpp drives the C ABI from std::threads)."""
+    n = 1 << 20
+    ix1 = cb.DctHashIndex()
+    ix1.load(ids[:n], hashes[:n])
+    p5 = cb.SearchParams(dctThresh=DHT)
+    for r in range(5):
+        ix1.find(cb.Media(dctHash=int(hashes[r])), p5)
+    t0 = time.time()
+    for r in range(300):
+        ix1.find(cb.Media(dctHash=int(hashes[r])), p5)
+    single_us = (time.time() - t0) / 300 * 1e6
+    t0 = time.time()
+    ix1.find_batch(hashes[:1000], p5)
+    batch_s = time.time() - t0
+    out = {"index_rows": n, "find_latency_us_python_caller": single_us, "batched_1000_needles_per_s": 1000 / batch_s}
+    del ix1
+    exe = os.path.join(ROOT, "cbird_b200", "find_bench")
+    threads = min(32, os.cpu_count() or 1)
+    try:
+        r = subprocess.run([exe, str(n), str(threads), "2.0", str(DHT)], capture_output=True, text=True, timeout=180)
+        out["concurrent_find"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        out["concurrent_find"] = {"unavailable": repr(e)}
+    # the reference's VP tree under the same call pattern
+    try:
+        tree = RefTree(hashes[:n], ids[:n])
+        res = tree.rate(4.0, threads)
+        out["cpu_reference_finds_per_s"] = {"value": res["needles"] / res["seconds"], "cores": threads, "kind": tree.kind,
+                                            "sample": res["sample"]}
+        tree.close()
+    except Exception as e:
+        out["cpu_reference_finds_per_s"] = {"unavailable": repr(e)}
+    return out
+
+
+def leg_nonuniform(cb, L, torch, dev):
+    """-similar on hashes that are NOT uniformly random: the dct hashes of configs[1]'s 2^20 synthetic frames (as the
+    config says) and a clustered set (1000 centres x 1000 members within 8 flips)."""
+    from cbird_b200 import synth
+
+    out = {}
+    frames = synth.luma_frames(1 << 20, seed=2)
+    fh = cb.dct_hash64_batch(frames)
+    rng = np.random.default_rng(5)
+    centres = rng.integers(0, 2 ** 63, size=1000, dtype=np.uint64) << np.uint64(1)
+    cl = np.repeat(centres, 1000)
+    for k in range(8):
+        bits = rng.integers(1, 64, size=len(cl)).astype(np.uint64)
+        cl ^= np.where(rng.random(len(cl)) < 0.5, np.uint64(1) << bits, np.uint64(0)).astype(np.uint64)
+    params = cb.SearchParams(dctThresh=DHT, filterSelf=False, maxMatches=1 << 30)
+    for name, h in (("frame_hashes_2^20", fh), ("clustered_1000x1000", cl)):
+        ids = np.arange(1, len(h) + 1, dtype=np.uint32)
+        ix = cb.DctHashIndex()
+        ix.load(ids, h)
+        res = {}
+        for mode, need in (("multi_index", 0), ("brute_force", -1)):
+            L.cb_scan64_mih_force(0, need)
+            ix.similar_count(params)
+            t0 = time.time()
+            kept, issued = ix.similar_count(params)
+            res[mode] = {"ms": (time.time() - t0) * 1e3, "hits": kept, "issued_pair_tests": issued}
+        L.cb_scan64_mih_force(0, 0)
+        sizes = bucket_histogram(L, h)
+        res.update({"rows": int(len(h)), "distinct_hashes": int(len(np.unique(h))), "bucket_sizes": sizes,
+                    "same_hits": res["multi_index"]["hits"] == res["brute_force"]["hits"],
+                    "multi_index_declined": res["multi_index"]["issued_pair_tests"] == res["brute_force"]["issued_pair_tests"]})
+        out[name] = res
+        del ix
+    return out
+
+
+def bucket_histogram(L, h):
+    shifts = (C.c_int32 * 16)()
+    masks = (C.c_uint32 * 16)()
+    k = L.cb_scan64_mih_plan(DHT, shifts, masks)
+    big, mx, tests = 0, 0, 0.0
+    for c in range(k):
+        b = np.bincount(((h >> np.uint64(shifts[c])) & np.uint64(masks[c])).astype(np.int64), minlength=masks[c] + 1)
+        mx = max(mx, int(b.max()))
+        big += int((b > 4 * len(h) / (masks[c] + 1)).sum())
+        tests += float((b.astype(np.float64) ** 2).sum()) / 2
+    return {"largest_bucket": mx, "buckets_over_4x_mean": big, "pair_tests_upper_triangle": tests,
+            "uniform_expectation": float(sum(len(h) ** 2 / (masks[c] + 1) for c in range(k))) / 2}
+
+
+def leg_video(cb):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+
+    out = {}
+    bc.bench_video(10000, 2000, 100, out)
+    return out
+
+
+def leg_orb(cb, sm_max_mhz):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+
+    out = {}
+    bc.bench_orb(25000, 400, 50, out)
+    return out
 
 
 if __name__ == "__main__":

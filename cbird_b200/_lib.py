@@ -33,6 +33,12 @@ class cb_stats(C.Structure):
                 ("frames_hashed", C.c_uint64)]
 
 
+class cb_profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
+PROFILE_SLOTS = {"mih_bucket_kernel": 0, "mih_sort": 1, "hit_sort": 2, "scan64_kernel": 3, "dct_hash32_kernel": 4}
+
 HIT_DTYPE = np.dtype([("needle", np.uint32), ("mediaId", np.uint32), ("score", np.int32)])
 PAIR_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("dist", np.uint32), ("pad", np.uint32)])
 TREE_MATCH_DTYPE = np.dtype([("needle", np.uint32), ("index", np.uint32), ("distance", np.int32), ("pad", np.uint32),
@@ -55,6 +61,13 @@ SIGNATURES = {
     "cb_stats_get": (C.c_int, [C.POINTER(cb_stats)]),
     "cb_stats_reset": (None, []),
     "cb_free": (None, [_vp]),
+    "cb_init": (C.c_int, [_vp, C.c_int]),
+    "cb_comm_unique_id": (C.c_int, [_vp, C.c_int]),
+    "cb_comm_init_rank": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cb_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cb_shutdown": (None, []),
+    "cb_profile_enable": (None, [C.c_int]),
+    "cb_profile_get": (C.c_int, [C.POINTER(cb_profile), C.c_int]),
     "cb_hash_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     "cb_gray_batch": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp]),
     "cb_hash_batch_color": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp]),
@@ -68,6 +81,9 @@ SIGNATURES = {
     "cb_scan64_self_dev": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_self_mih_dev": (C.c_int, [_vp, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_mih_max_threshold": (C.c_int, []),
+    "cb_scan64_mih_last_tests": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "cb_scan64_mih_force": (None, [C.c_int, C.c_int]),
+    "cb_scan64_mih_config": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cb_scan64_mih_plan": (C.c_int, [C.c_int, _vp, _vp]),
     "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
@@ -83,6 +99,9 @@ SIGNATURES = {
     "cb_dct_index_slice": (_vp, [_vp, _vp, _i64]),
     "cb_dct_index_media_ids": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "cb_dct_index_find": (C.c_int, [_vp, C.c_uint64, C.POINTER(cb_params), _vp, _i64, C.POINTER(_i64)]),
+    "cb_dct_index_find_queue_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cb_dct_index_shard_rows": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "cb_dct_index_similar_count": (C.c_int, [_vp, C.POINTER(cb_params), C.POINTER(_i64), C.POINTER(C.c_uint64)]),
     "cb_dct_index_find_batch_alloc": (C.c_int, [_vp, _vp, _i64, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_dct_index_similar_alloc": (C.c_int, [_vp, C.POINTER(cb_params), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cb_dct_index_similar_shard_alloc": (C.c_int, [_vp, C.POINTER(cb_params), _i64, _i64, C.POINTER(_vp), C.POINTER(_i64)]),

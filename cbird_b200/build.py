@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcbird_b200.so")
-SOURCES = ["common.cu", "scan64.cu", "dct_index.cu", "dct_hash.cu", "video_index.cu", "knn256.cu", "vdx.cu", "hamming_tree.cu", "mih.cu"]
+SOURCES = ["common.cu", "scan64.cu", "dct_index.cu", "dct_hash.cu", "video_index.cu", "knn256.cu", "vdx.cu", "hamming_tree.cu", "mih.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,7 +31,8 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cbird_b200.h"), __file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cbird_b200.h"), __file__,
+                                                                os.path.join(HERE, "..", "tools", "find_bench.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -52,8 +53,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.run(cmd, check=True)
+    # host-side driver of the concurrent find() measurement (bench.py's `find` leg); plain g++ over the C ABI
+    tool = os.path.join(HERE, "..", "tools", "find_bench.cpp")
+    if os.path.exists(tool):
+        subprocess.run(["g++", "-O2", "-std=c++17", tool, "-o", os.path.join(HERE, "find_bench"), "-L" + HERE, "-lcbird_b200",
+                        "-Wl,-rpath,$ORIGIN", "-lpthread"], check=True)
     return LIB
 
 

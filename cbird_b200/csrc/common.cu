@@ -52,6 +52,53 @@ Counters& counters() {
   return c;
 }
 
+// ---- optional kernel timing --------------------------------------------------------------------
+// prof_begin / prof_end bracket one launch with CUDA events on the launching stream. Nothing is synchronised
+// here: the event pairs are queued and cb_profile_get() reads them after the caller's own synchronisation.
+namespace {
+struct ProfRange {
+  int id, device;
+  cudaEvent_t a, b;
+};
+struct ProfState {
+  std::mutex mu;
+  std::vector<ProfRange> done;
+  double ms[kProfCount] = {0};
+  uint64_t n[kProfCount] = {0};
+};
+ProfState& prof_state() {
+  static ProfState* s = new ProfState;
+  return *s;
+}
+std::atomic<int> g_prof_on{0};
+thread_local ProfRange tl_open[kProfCount];
+thread_local bool tl_open_valid[kProfCount] = {false};
+}  // namespace
+
+void prof_begin(int id, cudaStream_t s) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || id < 0 || id >= kProfCount) return;
+  ProfRange r;
+  r.id = id;
+  r.device = 0;
+  cudaGetDevice(&r.device);
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  cudaEventRecord(r.a, s);
+  tl_open[id] = r;
+  tl_open_valid[id] = true;
+}
+
+void prof_end(int id, cudaStream_t s) {
+  if (id < 0 || id >= kProfCount || !tl_open_valid[id]) return;
+  tl_open_valid[id] = false;
+  cudaEventRecord(tl_open[id].b, s);
+  ProfState& P = prof_state();
+  std::lock_guard<std::mutex> lock(P.mu);
+  P.done.push_back(tl_open[id]);
+}
+
 }  // namespace cbird
 
 using namespace cbird;
@@ -194,5 +241,39 @@ void cb_stats_reset(void) {
 }
 
 void cb_free(void* p) { ::cbird::result_free(p); }
+
+void cb_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int cb_profile_get(cb_profile* out, int reset) {
+  if (!out) return CB_ERR_INVALID;
+  ProfState& P = prof_state();
+  std::lock_guard<std::mutex> lock(P.mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (ProfRange& r : P.done) {
+    cudaSetDevice(r.device);
+    float ms = 0;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      P.ms[r.id] += ms;
+      P.n[r.id] += 1;
+    } else {
+      cudaGetLastError();
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  P.done.clear();
+  cudaSetDevice(prev);
+  for (int i = 0; i < CB_PROFILE_SLOTS; ++i) {
+    out->ms[i] = i < kProfCount ? P.ms[i] : 0.0;
+    out->launches[i] = i < kProfCount ? P.n[i] : 0;
+  }
+  if (reset)
+    for (int i = 0; i < kProfCount; ++i) {
+      P.ms[i] = 0;
+      P.n[i] = 0;
+    }
+  return CB_OK;
+}
 
 }  // extern "C"

@@ -7,6 +7,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -33,6 +35,23 @@ Counters& counters();
     cudaError_t e__ = (call);                                                \
     if (e__ != cudaSuccess) return ::cbird::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
+
+// extern "C" bodies: no exception may cross the ABI (the host process would terminate)
+#define CB_API_BEGIN try {
+#define CB_API_END                                                    \
+  }                                                                   \
+  catch (const std::bad_alloc&) {                                     \
+    ::cbird::set_error("out of host memory");                         \
+    return CB_ERR_INVALID;                                            \
+  }                                                                   \
+  catch (const std::exception& e__) {                                 \
+    ::cbird::set_error("internal error: %s", e__.what());             \
+    return CB_ERR_INVALID;                                            \
+  }                                                                   \
+  catch (...) {                                                       \
+    ::cbird::set_error("internal error");                             \
+    return CB_ERR_INVALID;                                            \
+  }
 
 // growable device buffer (never shrinks); not thread-safe, owners lock.
 template <typename T>
@@ -86,34 +105,69 @@ int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint
                         cudaStream_t stream);
 int scan64_variant_for(int threshold);
 
+// ---- multi-GPU ranks driven by this process (comm.cu) ----------------------------------------------
+constexpr int kMaxRanks = 16;
+struct NcclUniqueId {  // layout of ncclUniqueId
+  char internal[128];
+};
+struct CommRank {
+  int rank = 0, world = 1, device = 0;
+  void* nccl = nullptr;  // ncclComm_t, null when world == 1
+};
+struct CommWorld {
+  int world = 1;
+  int n_local = 0;  // 0 = no communicator set up: handles run on the calling thread's device alone
+  CommRank local[kMaxRanks];
+};
+const CommWorld& comm_world();
+// byte-wise collectives on the rank's NCCL communicator (device copies when world == 1)
+int comm_all_gather(const CommRank& R, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+int comm_all_to_all(const CommRank& R, const void* const* send, const size_t* send_bytes, void* const* recv,
+                    const size_t* recv_bytes, cudaStream_t s);
+
+// ---- optional per-kernel timing (CUDA events on the launching stream, collected by cb_profile_get) ----
+enum ProfId { kProfMihBucket = 0, kProfMihSort = 1, kProfHitSort = 2, kProfScan = 3, kProfHash32 = 4, kProfCount = 8 };
+void prof_begin(int id, cudaStream_t s);  // no-ops unless cb_profile_enable(1)
+void prof_end(int id, cudaStream_t s);
+
 // ---- multi-index (pigeonhole) self-join, mih.cu ------------------------------------------------
 constexpr int kMihMaxThreshold = 10;  // above this the buckets get too coarse to beat the brute-force scan
-struct MihPlan {  // chunk c of a hash = (h >> shift[c]) & mask[c]; sort key = (c << key_shift) | bucket
-  int chunks;
-  int key_shift;  // bits of the widest bucket index (<= 16)
-  int shift[kMihMaxThreshold];
-  uint32_t mask[kMihMaxThreshold];
+constexpr int kMihMaxChunks = kMihMaxThreshold + 1;
+constexpr int kMihMaxUnits = 64;      // C(11, 2) = 55
+struct MihPlan {  // chunk c of a hash = (h >> shift[c]) & mask[c]; a unit is one chunk (need 1) or a pair of chunks
+  int chunks;     // (need 2); sort key = (unit << key_shift) | bucket
+  int need;       // chunks of a unit: rows closer than the threshold agree on at least `need` of the chunks
+  int units;
+  int key_shift;  // bits of the widest bucket index
+  int shift[kMihMaxChunks + 1];
+  uint32_t mask[kMihMaxChunks + 1];
+  int bits[kMihMaxChunks + 1];
+  int8_t u_c1[kMihMaxUnits], u_c2[kMihMaxUnits];  // chunks of unit u, lexicographic order (u_c2 == u_c1 for need 1)
 };
-struct MihEmit {  // what the tile-list kernel needs to report MIH hits: sorted position -> row, -> key, the plan
-  const uint32_t* rows;
-  const uint32_t* keys;
-  MihPlan plan;
+struct MihOut {  // where the self-join reports
+  int mode;      // 0: cb_pair{a, b, dist} records, both orders; 1: 64-bit keys needle << needle_shift | dist << 32 | mediaId
+  void* out;
+  unsigned long long cap;
+  unsigned long long* count;  // total, also beyond cap
+  const uint32_t* ids;        // mode 1: row -> mediaId (0 = removed row: dropped)
+  int needle_shift;           // mode 1
 };
 struct MihWorkspace {
-  DevBuf<uint32_t> key, key2, val, val2, ofs, n_big, big_at;
+  DevBuf<uint32_t> key, key2, val, val2, ofs, nblk, blk_at, nitems, item_at;
   DevBuf<uint64_t> sorted;
-  DevBuf<cb_scan_tile> big_tiles;
+  DevBuf<cb_scan_tile> items;
   DevBuf<unsigned char> temp;
-  DevBuf<unsigned long long> info;  // [1] tile-list items, [2] pair tests, [3] kept (row, chunk) items
+  DevBuf<unsigned long long> info;  // 8 slots per unit batch, see mih.cu
   unsigned long long* h_info = nullptr;
+  int n_batches = 0;
   ~MihWorkspace();
 };
-MihPlan mih_plan(int threshold);
+MihPlan mih_plan(int threshold, int need);
+int mih_need_for(uint64_t n, int threshold);
 bool mih_applicable(uint64_t n, int threshold);
-int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, cb_pair* out,
-                    unsigned long long cap, unsigned long long* d_count, MihWorkspace& ws, unsigned long long max_tests,
-                    int* declined, cudaStream_t stream);
-int scan64_tiles_mih_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, const MihEmit& E,
-                            cudaStream_t stream);
+int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, const MihOut& out,
+                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream);
+// after the stream has been synchronised: pair tests of the last pass and whether it declined (copies ws.info)
+int mih_read_info(MihWorkspace& ws, cudaStream_t stream, unsigned long long* tests, int* declined);
 
 }  // namespace cbird

@@ -1093,6 +1093,7 @@ int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long 
   // CTA shape: measured on B200 (tools/hash_bench.py, packed f32x2 build) 16 frames x 128 threads 0.417 ms,
   // 8x64 0.423, 32x256 0.444 per 2^20 frames — the kernel is issue-bound, the shape hardly matters.
   static const int variant = getenv("CB_HASH_VARIANT") ? atoi(getenv("CB_HASH_VARIANT")) : 1;
+  prof_begin(kProfHash32, stream);
   switch (variant) {
     case 1:
       dct_hash32_kernel<16, 128, 8><<<unsigned((n + 15) / 16), 128, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
@@ -1110,6 +1111,7 @@ int launch_hash32(const uint8_t* tiles, long long n, long long t_row, long long 
       dct_hash32_kernel<32, 256, 4><<<unsigned((n + 31) / 32), 256, 0, stream>>>(tiles, n, t_row, t_frame, aligned16, d_out);
       break;
   }
+  prof_end(kProfHash32, stream);
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
   counters().frames += uint64_t(n);

@@ -4,22 +4,27 @@
 // (src/database.cpp:1400-1432 -> DctHashIndex::find per needle, src/dcthashindex.cpp:193-220). The
 // reference prunes with a VP tree per needle; the brute-force kernel (scan64.cu) tests every pair. For
 // small T there is an exact shortcut: bit 0 of a dct hash is always clear (src/cvutil.cpp:537-538), so the
-// 63 usable bits are cut into T chunks, and two hashes that differ in fewer than T bits agree EXACTLY on at
-// least one chunk. Rows are bucketed by the (first <=16 bits of the) chunk value, once per chunk, and only
-// rows sharing a bucket are compared: T * sum(bucket^2) pair tests instead of n^2 (2^20 uniformly random
-// rows, T = 5: 6.7e8 instead of 1.1e12). A pair that shares a bucket in several chunks is reported by the
-// first of them only, so the hit set is exactly the brute-force one (self pairs included, each once).
+// 63 usable bits are cut into k chunks, and two hashes that differ in fewer than T bits agree EXACTLY on at
+// least k - (T - 1) chunks. A "unit" is a set of j = k - (T - 1) chunks (j = 1: k = T chunks, T units;
+// j = 2: k = T + 1 chunks, k(k-1)/2 units with much smaller buckets); rows are bucketed once per unit by the
+// concatenated chunk values and only rows sharing a bucket are compared. A pair that shares a bucket in
+// several units is reported by the first of them only, and every unordered pair is tested once and
+// reported in both orders, so the hit set is exactly the brute-force one.
 //
-//   keys    (chunk << bucket bits | bucket, row) for every chunk of every row mih_keys_kernel
-//   sort    one stable LSD radix sort over all chunks                         cub::DeviceRadixSort
-//   gather  hashes in bucket order (bucket-contiguous, like the video index)   mih_gather_kernel
-//   bounds  bucket boundaries by binary search, tile list by exclusive scan    mih_bounds/tiles kernels
-//   scan    small buckets (<= 1024 rows): one CTA per 512 sorted positions, the surrounding window in shared
-//           memory, every row against its own bucket, OR-fold pre-filter + exact recheck, hits collected in
-//           shared memory and appended with one global atomic per CTA
-//           large buckets: the tuned tile-list kernel of scan64.cu (<= 2048 A rows x bucket)
+//   keys    (unit << bucket bits | bucket, row) for every unit of every row            mih_keys_kernel
+//   sort    one stable LSD radix sort over all units of a batch                         cub::DeviceRadixSort
+//   gather  hashes in bucket order (bucket-contiguous, like the video index)             mih_gather_kernel
+//   bounds  bucket boundaries by binary search                                           mih_bounds_kernel
+//   items   every bucket is cut into blocks of 256 rows; a work item is one block against a segment of
+//           the rows at or after it in the same bucket (upper triangle); two exclusive scans, no host
+//           round trip: the item count stays on the device                               mih_blocks/items kernels
+//   scan    persistent kernel, one WARP per work item: block rows in registers (8 per lane), the
+//           segment streamed through the warp's own 2 KB of shared memory and read with broadcast
+//           LDS.128; a cheap lower bound of the distance first (1 POPC per two pairs), exact re-test of
+//           the survivors; hits staged in shared memory, one global atomic per flush       mih_bucket_kernel
+//   self    every row matches itself                                                      mih_self_kernel
 //
-// Multi-GPU: buckets are dealt to ranks ((bucket + chunk) % n_parts); every rank sorts and scans only its
+// Multi-GPU: buckets are dealt to ranks ((bucket + unit) % n_parts); every rank sorts and scans only its
 // own buckets, and the per-rank hit lists are disjoint by construction.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -32,43 +37,65 @@ namespace cbird {
 
 namespace {
 
-constexpr int kSmallThreads = 128;
-constexpr uint32_t kSmallMax = 1024;  // buckets up to this many rows take the small-bucket kernel
-constexpr uint32_t kBigABlock = 2048;  // A rows per work item of the tile-list kernel
+constexpr int kBkThreads = 256;                // 8 independent warps per CTA
+constexpr int kBkWarps = kBkThreads / 32;
+constexpr int kR = 8;                          // block rows per lane
+constexpr uint32_t kBlk = 32 * kR;             // rows per block (A side of a work item)
+constexpr uint32_t kSegMin = 8192;             // rows per segment (B side of a work item), at least
+constexpr uint32_t kSegsPerBlock = 8;          // a block's range is cut into at most this many (+1) segments
+constexpr int kStage = 64;                     // staged hits per warp
+constexpr uint64_t kPadA = 0x5555555555555555ull, kPadB = 0xAAAAAAAAAAAAAAAAull;
 
-__global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, MihPlan plan, uint32_t part,
+// info[] slots (device, zeroed at the start of every batch)
+enum { kNext = 0, kItems = 1, kTests = 2, kKept = 3, kDeclined = 4, kBlocks = 5, kInfoSlots = 8 };
+
+__device__ __forceinline__ uint32_t unit_bucket(const MihPlan& plan, int u, uint64_t h) {
+  const int c1 = plan.u_c1[u];
+  uint32_t k = uint32_t(h >> plan.shift[c1]) & plan.mask[c1];
+  if (plan.need == 2) {
+    const int c2 = plan.u_c2[u];
+    k |= (uint32_t(h >> plan.shift[c2]) & plan.mask[c2]) << plan.bits[c1];
+  }
+  return k;
+}
+
+// (unit, bucket, row) items of units [u0, u1) — for n_parts > 1 only the buckets dealt to `part`, compacted with
+// one atomic per warp and unit
+__global__ void mih_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, MihPlan plan, int u0, int u1, uint32_t part,
                                 uint32_t n_parts, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
                                 unsigned long long* __restrict__ counter) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
   const uint64_t h = live ? hash[i] : 0;
   const unsigned lane = threadIdx.x & 31;
-  for (int c = 0; c < plan.chunks; ++c) {
-    const uint32_t k = uint32_t(h >> plan.shift[c]) & plan.mask[c];
+  for (int u = u0; u < u1; ++u) {
+    const uint32_t k = unit_bucket(plan, u, h);
     if (n_parts == 1) {
       if (live) {
-        key[size_t(c) * n + i] = (uint32_t(c) << plan.key_shift) | k;
-        val[size_t(c) * n + i] = i;
+        key[size_t(u - u0) * n + i] = (uint32_t(u - u0) << plan.key_shift) | k;
+        val[size_t(u - u0) * n + i] = i;
       }
       continue;
     }
-    const bool mine = live && (k + uint32_t(c)) % n_parts == part;
-    const unsigned m = __ballot_sync(0xffffffffu, mine);  // one atomic per warp and chunk
+    const bool mine = live && (k + uint32_t(u)) % n_parts == part;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
     if (!m) continue;
     unsigned long long base = 0;
     if (lane == unsigned(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (mine) {
       const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-      key[at] = (uint32_t(c) << plan.key_shift) | k;
+      key[at] = (uint32_t(u - u0) << plan.key_shift) | k;
       val[at] = i;
     }
   }
 }
 
-__global__ void mih_gather_kernel(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ rows, uint32_t m,
+__global__ void mih_gather_kernel(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ rows,
+                                  const unsigned long long* __restrict__ m_dev, uint32_t m_bound,
                                   uint64_t* __restrict__ sorted) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t m = m_dev ? uint32_t(*m_dev) : m_bound;
   if (j < m) sorted[j] = hash[rows[j]];
 }
 
@@ -85,155 +112,611 @@ __global__ void mih_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint3
   ofs[k] = lo;
 }
 
-// tile-list items per bucket (large buckets only: ceil(s / 2048)) and the pair tests of the whole pass
-__global__ void mih_tile_counts_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, uint32_t* __restrict__ n_big,
-                                       unsigned long long* __restrict__ info) {
+// blocks of 256 rows per bucket (buckets of one row have no pair to test) and the pair tests of the batch
+__global__ void mih_blocks_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, uint32_t* __restrict__ nblk,
+                                  unsigned long long* __restrict__ info) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long tests = 0;
   if (k <= n_buckets) {
     uint32_t s = 0;
     if (k < n_buckets) s = ofs[k + 1] - ofs[k];
-    n_big[k] = s > kSmallMax ? (s + kBigABlock - 1) / kBigABlock : 0u;
-    tests = (unsigned long long)s * s;
+    nblk[k] = s >= 2 ? (s + kBlk - 1) / kBlk : 0u;
+    tests = (unsigned long long)s * (s + kBlk) / 2;  // upper triangle + the diagonal blocks
   }
-  __shared__ unsigned long long red[8];  // block reduction, one atomic per CTA
+  __shared__ unsigned long long red[8];
   for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tests;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long t = 0;
     for (int w = 0; w < int(blockDim.x >> 5); ++w) t += red[w];
-    if (t) atomicAdd(info + 2, t);
+    if (t) atomicAdd(info + kTests, t);
   }
 }
 
-__global__ void mih_tile_write_kernel(const uint32_t* __restrict__ ofs, uint32_t n_buckets, const uint32_t* __restrict__ big_at,
-                                      cb_scan_tile* __restrict__ big_tiles, unsigned long long* __restrict__ info) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > n_buckets) return;
-  if (k == n_buckets) {  // the exclusive scan ends here: total
-    info[1] = big_at[k];
+__device__ __forceinline__ uint32_t seg_rows(uint32_t range) {  // rows per segment for a block whose range is `range`
+  const uint32_t per = (range + kSegsPerBlock - 1) / kSegsPerBlock;
+  return max(kSegMin, (per + kBlk - 1) / kBlk * kBlk);
+}
+
+struct BlockDesc {
+  uint32_t a_begin, range, unit;  // block rows [a_begin, a_begin + min(256, range)), range = rows from a_begin to the bucket's end
+};
+
+__device__ __forceinline__ bool block_desc(const uint32_t* __restrict__ ofs, const uint32_t* __restrict__ blk_at,
+                                           uint32_t n_buckets, int key_shift, uint32_t g, BlockDesc* d) {
+  if (g >= blk_at[n_buckets]) return false;
+  uint32_t lo = 0, hi = n_buckets;  // last bucket k with blk_at[k] <= g (empty buckets share their successor's start)
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (blk_at[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t b0 = ofs[lo], s = ofs[lo + 1] - b0, i = g - blk_at[lo];
+  d->a_begin = b0 + i * kBlk;
+  d->range = s - i * kBlk;
+  d->unit = lo >> key_shift;
+  return true;
+}
+
+// work items per block: its range [a_begin, bucket end) in segments
+__global__ void mih_item_counts_kernel(const uint32_t* __restrict__ ofs, const uint32_t* __restrict__ blk_at, uint32_t n_buckets,
+                                       int key_shift, uint32_t n_blocks_bound, uint32_t* __restrict__ nitems,
+                                       unsigned long long* __restrict__ info) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_blocks_bound) return;
+  if (g == 0) info[kBlocks] = blk_at[n_buckets];
+  BlockDesc d;
+  uint32_t c = 0;
+  if (g < n_blocks_bound && block_desc(ofs, blk_at, n_buckets, key_shift, g, &d) && d.range >= 2)
+    c = (d.range + seg_rows(d.range) - 1) / seg_rows(d.range);
+  nitems[g] = c;
+}
+
+__global__ void mih_item_write_kernel(const uint32_t* __restrict__ ofs, const uint32_t* __restrict__ blk_at, uint32_t n_buckets,
+                                      int key_shift, uint32_t n_blocks_bound, const uint32_t* __restrict__ item_at,
+                                      cb_scan_tile* __restrict__ items, unsigned long long* __restrict__ info) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_blocks_bound) return;
+  if (g == n_blocks_bound) {  // the exclusive scan ends here: total
+    info[kItems] = item_at[g];
     return;
   }
-  const uint32_t b0 = ofs[k], s = ofs[k + 1] - b0;
-  if (s <= kSmallMax) return;
-  const uint32_t at = big_at[k];
-  for (uint32_t t = 0, a = 0; a < s; ++t, a += kBigABlock)
-    big_tiles[at + t] = cb_scan_tile{b0 + a, min(kBigABlock, s - a), b0, s};
+  BlockDesc d;
+  if (!block_desc(ofs, blk_at, n_buckets, key_shift, g, &d) || d.range < 2) return;
+  const uint32_t seg = seg_rows(d.range), at = item_at[g];
+  const uint32_t a_count = min(kBlk, d.range);
+  for (uint32_t t = 0, b = 0; b < d.range; ++t, b += seg)
+    items[at + t] = cb_scan_tile{d.a_begin, a_count | (d.unit << 16), d.a_begin + b, min(seg, d.range - b)};
 }
 
-// Small buckets (<= 1024 rows). One CTA owns 512 consecutive sorted positions as A rows and keeps the window
-// [base - 1024, base + 1536) in shared memory, which contains every small bucket that overlaps its rows. Thread
-// t tests rows base + t, + 128, ... against their own bucket: popc((alo^blo)|(ahi^bhi)) <= distance is the
-// pre-filter (1 POPC per pair), then the exact distance. A hit is kept only in the first chunk in which the two
-// hashes share a bucket, and is staged in shared memory as packed window positions: the global counter sees
-// one atomic per CTA (every row at least finds itself: per-hit global atomics would serialise) and the
-// translation to original row numbers happens at the flush, all threads in parallel, instead of two dependent
-// global loads in the middle of the scan loop.
-constexpr int kSmallRows = 512, kHitBuf = 1024;
-constexpr int kWin = kSmallRows + 2 * int(kSmallMax);  // window: positions [base - kSmallMax, base + kSmallRows + kSmallMax)
+// ---- hit output ------------------------------------------------------------------------------------
+// mode 0: cb_pair{a, b, dist, 0} records (row numbers), both orders of every pair
+// mode 1: 64-bit sort keys (needle row << needle_shift | dist << 32 | mediaId of the matched row); matched rows
+//         without id (removed, src/dcthashindex.cpp:183-186) are dropped like hits_to_matches does
+struct BucketArgs {
+  const uint64_t* sorted;   // hashes in bucket order
+  const uint32_t* rows;     // sorted position -> row
+  const cb_scan_tile* items;
+  unsigned long long* info;
+  unsigned long long max_tests;  // 0 = never decline
+  MihPlan plan;             // unit tables already shifted to this batch
+  int threshold;
+  MihOut out;
+};
 
-__global__ void __launch_bounds__(kSmallThreads)
-    mih_small_kernel(const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ rows,
-                     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ofs, uint32_t m, MihPlan plan,
-                     int threshold, cb_pair* __restrict__ out, unsigned long long cap,
-                     unsigned long long* __restrict__ count) {
-  __shared__ uint2 win[kWin + 4];  // +4: the 4-row steps may read past the last bucket
-  __shared__ uint32_t hitbuf[kHitBuf];  // (a - base) | (b - base + kSmallMax) << 9 | distance << 21
-  __shared__ unsigned n_hit;
-  __shared__ unsigned long long g_base;
-  const uint32_t base = blockIdx.x * kSmallRows;
-  const long long w0 = (long long)base - (long long)kSmallMax;
-  for (int i = threadIdx.x; i < kWin; i += kSmallThreads) {
-    const long long pos = w0 + i;
-    uint64_t v = 0;
-    if (pos >= 0 && pos < (long long)m) v = sorted[pos];
-    win[i] = make_uint2(uint32_t(v), uint32_t(v >> 32));
+// everything the rare paths need lives in shared memory: the hot loops keep only the block rows in registers
+struct BucketShared {
+  MihPlan plan;
+  MihOut out;
+  const uint32_t* rows;
+  int threshold;
+  struct Warp {
+    uint32_t a_end, b_end, unit;
+    unsigned n_staged;
+  } warp[kBkWarps];
+  uint4 stage[kBkWarps][kStage];   // staged pairs (pa, pb, dist)
+  uint4 tile[kBkWarps][kBlk / 2];  // 256 hashes per warp
+};
+
+// records (0..2) a staged pair (pa, pb, d) produces
+__device__ __forceinline__ int translate(const BucketShared& sh, uint32_t pa, uint32_t pb, uint32_t d, uint4* r0, uint4* r1) {
+  const uint32_t ra = sh.rows[pa], rb = sh.rows[pb];
+  if (sh.out.mode == 0) {
+    *r0 = make_uint4(ra, rb, d, 0u);
+    *r1 = make_uint4(rb, ra, d, 0u);
+    return 2;
   }
-  if (threadIdx.x < 4) win[kWin + threadIdx.x] = make_uint2(0u, 0u);
-  if (threadIdx.x == 0) n_hit = 0;
-  __syncthreads();
-  for (int r = 0; r < kSmallRows / kSmallThreads; ++r) {
-    const uint32_t a = base + threadIdx.x + r * kSmallThreads;
-    if (a >= m) continue;
-    const uint32_t key = keys[a];
-    const uint32_t bs = ofs[key], be = ofs[key + 1];
-    if (be - bs > kSmallMax) continue;  // a large bucket: the tile-list kernel has it
-    const int chunk = int(key >> plan.key_shift);
-    const uint2 av = win[a - base + kSmallMax];
-    auto stage = [&](uint32_t b, uint32_t d) {
-      // positions are translated to row numbers when the CTA flushes: no global load on this path
-      const unsigned at = atomicAdd(&n_hit, 1u);
-      if (at < kHitBuf) {
-        hitbuf[at] = (a - base) | ((b - base + kSmallMax) << 9) | (d << 21);
-      } else {  // staging full (a cluster of near-duplicates): straight to the list
-        const unsigned long long pos = atomicAdd(count, 1ull);
-        if (pos < cap) *reinterpret_cast<uint4*>(out + pos) = make_uint4(rows[a], rows[b], d, 0u);
-      }
-    };
-    auto emit = [&](uint32_t b, uint32_t xlo, uint32_t xhi) {
-      if (b == a) {  // every row meets itself in every chunk: settle that before anything else
-        if (chunk == 0) stage(b, 0u);
-        return;
-      }
-      const int d = __popc(xlo) + __popc(xhi);
-      if (d >= threshold) return;
-      const uint64_t x = (uint64_t(xhi) << 32) | xlo;
+  const uint32_t ia = sh.out.ids[ra], ib = sh.out.ids[rb];
+  int k = 0;
+  if (ib) {  // needle a finds b
+    const unsigned long long key = ((unsigned long long)ra << sh.out.needle_shift) | ((unsigned long long)d << 32) | ib;
+    *r0 = make_uint4(uint32_t(key), uint32_t(key >> 32), 0u, 0u);
+    k = 1;
+  }
+  if (ia) {
+    const unsigned long long key = ((unsigned long long)rb << sh.out.needle_shift) | ((unsigned long long)d << 32) | ia;
+    (k ? *r1 : *r0) = make_uint4(uint32_t(key), uint32_t(key >> 32), 0u, 0u);
+    ++k;
+  }
+  return k;
+}
+
+__device__ __forceinline__ void store_record(const BucketShared& sh, unsigned long long at, const uint4& r) {
+  if (at >= sh.out.cap) return;
+  if (sh.out.mode == 0) reinterpret_cast<uint4*>(sh.out.out)[at] = r;
+  else reinterpret_cast<uint2*>(sh.out.out)[at] = make_uint2(r.x, r.y);
+}
+
+// the warp's staged pairs to the global list: one atomic per 32 staged pairs
+__device__ __noinline__ void flush_stage(BucketShared& sh, unsigned warp, unsigned lane) {
+  __syncwarp();
+  const unsigned n = min(sh.warp[warp].n_staged, unsigned(kStage));
+  for (unsigned i0 = 0; i0 < n; i0 += 32) {
+    const unsigned i = i0 + lane;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    int k = 0;
+    if (i < n) {
+      const uint4 e = sh.stage[warp][i];
+      k = translate(sh, e.x, e.y, e.z, &r0, &r1);
+    }
+    int incl = k;  // inclusive prefix over the lanes
 #pragma unroll
-      for (int c = 0; c < kMihMaxThreshold - 1; ++c)  // unrolled: the plan stays in the constant bank
-        if (c < chunk && ((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) return;  // an earlier chunk reports it
-      stage(b, uint32_t(d));
-    };
-    // four B rows per step: independent loads and pre-filters, one branch; rows past the bucket's end are
-    // read from the (padded) window but never reported
-    const uint2* wb = win + (bs - base + kSmallMax);
-    const uint32_t s = be - bs;
-    for (uint32_t j = 0; j < s; j += 4) {
-      const uint2 b0 = wb[j], b1 = wb[j + 1], b2 = wb[j + 2], b3 = wb[j + 3];
-      const uint32_t x0l = av.x ^ b0.x, x0h = av.y ^ b0.y, x1l = av.x ^ b1.x, x1h = av.y ^ b1.y;
-      const uint32_t x2l = av.x ^ b2.x, x2h = av.y ^ b2.y, x3l = av.x ^ b3.x, x3h = av.y ^ b3.y;
-      const int p0 = __popc(x0l | x0h), p1 = __popc(x1l | x1h), p2 = __popc(x2l | x2h), p3 = __popc(x3l | x3h);
-      if (min(min(p0, p1), min(p2, p3)) >= threshold) continue;
-      if (p0 < threshold) emit(bs + j, x0l, x0h);
-      if (p1 < threshold && j + 1 < s) emit(bs + j + 1, x1l, x1h);
-      if (p2 < threshold && j + 2 < s) emit(bs + j + 2, x2l, x2h);
-      if (p3 < threshold && j + 3 < s) emit(bs + j + 3, x3l, x3h);
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (int(lane) >= off) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(sh.out.count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k) {
+      store_record(sh, base + incl - k, r0);
+      if (k > 1) store_record(sh, base + incl - k + 1, r1);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) sh.warp[warp].n_staged = 0;
+  __syncwarp();
+}
+
+// exact re-test of one pre-filter survivor; pa < pb are sorted positions in the same bucket. Rare: kept out of
+// line so that the hot loops stay small.
+__device__ __noinline__ void exact_emit(BucketShared& sh, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t pa,
+                                        uint32_t pb) {
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t xlo = alo ^ blo, xhi = ahi ^ bhi;
+  const int d = __popc(xlo) + __popc(xhi);
+  if (d >= sh.threshold) return;
+  if (pa >= sh.warp[warp].a_end || pb >= sh.warp[warp].b_end) return;  // padding rows
+  // reported by the first unit in which the two hashes share a bucket: no chunk below this unit's last one,
+  // other than the unit's own, may agree
+  const uint64_t x = (uint64_t(xhi) << 32) | xlo;
+  const uint32_t unit = sh.warp[warp].unit;
+  const int c1 = sh.plan.u_c1[unit], c2 = sh.plan.u_c2[unit];
+  for (int c = 0; c < c2; ++c)
+    if (c != c1 && ((uint32_t(x >> sh.plan.shift[c])) & sh.plan.mask[c]) == 0) return;
+  const unsigned at = atomicAdd(&sh.warp[warp].n_staged, 1u);
+  if (at < unsigned(kStage)) {
+    sh.stage[warp][at] = make_uint4(pa, pb, uint32_t(d), 0u);
+  } else {  // staging full (a cluster of near-duplicates): straight to the list
+    uint4 r0, r1;
+    const int k = translate(sh, pa, pb, uint32_t(d), &r0, &r1);
+    if (!k) return;
+    const unsigned long long pos = atomicAdd(sh.out.count, (unsigned long long)k);
+    store_record(sh, pos, r0);
+    if (k > 1) store_record(sh, pos + 1, r1);
+  }
+}
+
+// lower bound of min(distance to b0, distance to b1), d = {b0.lo, b0.hi, b1.lo, b1.hi}
+template <int V>
+__device__ __forceinline__ uint32_t bound2(uint32_t alo, uint32_t ahi, const uint4& d) {
+  if (V == 1) return min(__popc((alo ^ d.x) | (ahi ^ d.y)), __popc((alo ^ d.z) | (ahi ^ d.w)));  // 1 POPC / pair
+  if (V == 2) return __popc(((alo ^ d.x) & (alo ^ d.z)) | ((ahi ^ d.y) & (ahi ^ d.w)));              // AND-fold of two rows
+  return __popc(((alo ^ d.x) | (ahi ^ d.y)) & ((alo ^ d.z) | (ahi ^ d.w)));                         // AND of the two OR-folds
+}
+
+// tile entries [j0, j1) (two rows each, positions t_pos + 2j, + 1) against block registers 0..NR-1 in full and,
+// when DIAG, register NR restricted to pairs whose block position is below the tile position (the 32 x 32
+// sub-block on the diagonal; lane l of register NR sits at tile position 32 NR + l)
+template <int V, int NR, bool DIAG>
+__device__ __forceinline__ void scan_rows(BucketShared& sh, const uint4* __restrict__ tile, const uint32_t (&alo)[kR],
+                                          const uint32_t (&ahi)[kR], int j0, int j1, uint32_t a_begin, uint32_t t_pos,
+                                          unsigned lane) {
+  const int T = sh.threshold;
+#pragma unroll 2
+  for (int j = j0; j < j1; ++j) {
+    const uint4 d = tile[j];
+    uint32_t p[NR + 1];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) p[r] = bound2<V>(alo[r], ahi[r], d);
+    uint32_t mn = 64;
+    if (DIAG) {
+      const int q0 = 2 * j - 32 * NR;  // sub-block position of the entry's first row
+      const uint32_t p0 = __popc((alo[NR] ^ d.x) | (ahi[NR] ^ d.y)), p1 = __popc((alo[NR] ^ d.z) | (ahi[NR] ^ d.w));
+      p[NR] = min(int(lane) < q0 ? p0 : 64u, int(lane) < q0 + 1 ? p1 : 64u);
+      mn = p[NR];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) mn = min(mn, p[r]);
+    if (int(mn) < T) {
+      const uint32_t pb = t_pos + 2 * j;
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (int(p[r]) < T) {
+          const uint32_t pa = a_begin + lane + 32 * r;
+          exact_emit(sh, alo[r], ahi[r], d.x, d.y, pa, pb);
+          exact_emit(sh, alo[r], ahi[r], d.z, d.w, pa, pb + 1);
+        }
+      if (DIAG && int(p[NR]) < T) {
+        const int q0 = 2 * j - 32 * NR;
+        const uint32_t pa = a_begin + lane + 32 * NR;
+        if (int(lane) < q0) exact_emit(sh, alo[NR], ahi[NR], d.x, d.y, pa, pb);
+        if (int(lane) < q0 + 1) exact_emit(sh, alo[NR], ahi[NR], d.z, d.w, pa, pb + 1);
+      }
+    }
+  }
+}
+
+// rows [pos, pos + 256) of the sorted array into the warp's tile, padded past `end`
+__device__ __forceinline__ void load_tile(uint4* tile, const uint64_t* __restrict__ sorted, uint32_t pos, uint32_t end,
+                                          unsigned lane) {
+  uint64_t* t64 = reinterpret_cast<uint64_t*>(tile);
+#pragma unroll
+  for (int i = 0; i < kR; ++i) {
+    const uint32_t q = pos + lane + 32 * i;
+    t64[lane + 32 * i] = q < end ? sorted[q] : kPadB;
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void diag_subblock(int jb, BucketShared& sh, const uint4* tile, const uint32_t (&alo)[kR],
+                                              const uint32_t (&ahi)[kR], uint32_t a_begin, unsigned lane) {
+  const int j0 = 16 * jb, j1 = j0 + 16;
+  switch (jb) {
+    case 0: scan_rows<V, 0, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 1: scan_rows<V, 1, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 2: scan_rows<V, 2, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 3: scan_rows<V, 3, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 4: scan_rows<V, 4, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 5: scan_rows<V, 5, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    case 6: scan_rows<V, 6, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+    default: scan_rows<V, 7, true>(sh, tile, alo, ahi, j0, j1, a_begin, a_begin, lane); break;
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kBkThreads, 3) mih_bucket_kernel(const BucketArgs A) {
+  __shared__ BucketShared sh;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (A.max_tests && A.info[kTests] > A.max_tests) {  // too skewed: the caller runs the brute-force scan instead
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.info[kDeclined] = 1;
+    return;
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.plan);
+    for (unsigned i = threadIdx.x; i < sizeof(MihPlan) / 4; i += kBkThreads) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+      sh.out = A.out;
+      sh.rows = A.rows;
+      sh.threshold = A.threshold;
+    }
+    if (lane == 0) sh.warp[warp].n_staged = 0;
+  }
+  __syncthreads();
+  uint4* tile = sh.tile[warp];
+  const unsigned long long n_items = A.info[kItems];
+  for (;;) {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(A.info + kNext, 1ull);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (v >= n_items) break;
+    const cb_scan_tile it = A.items[v];
+    const uint32_t a_count = it.a_count & 0xFFFFu;
+    const uint32_t a_begin = it.a_begin, a_end = it.a_begin + a_count;
+    const uint32_t b_end = it.b_begin + it.b_count;
+    uint32_t pos = it.b_begin;
+    const bool diag = pos == a_begin;
+    __syncwarp();
+    if (lane == 0) {
+      sh.warp[warp].a_end = a_end;
+      sh.warp[warp].b_end = diag ? a_end : b_end;
+      sh.warp[warp].unit = it.a_count >> 16;
+    }
+    uint32_t alo[kR], ahi[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const uint32_t pa = a_begin + lane + 32 * r;
+      const uint64_t h = pa < a_end ? A.sorted[pa] : kPadA;
+      alo[r] = uint32_t(h);
+      ahi[r] = uint32_t(h >> 32);
+    }
+    if (diag) {  // the block against itself: upper triangle by 32-row sub-blocks
+      load_tile(tile, A.sorted, pos, a_end, lane);
+      __syncwarp();
+      const int n_sub = int((a_count + 31) >> 5);
+      for (int jb = 0; jb < n_sub; ++jb) diag_subblock<V>(jb, sh, tile, alo, ahi, a_begin, lane);
+      __syncwarp();
+      if (sh.warp[warp].n_staged >= unsigned(kStage / 2)) flush_stage(sh, warp, lane);
+      if (lane == 0) sh.warp[warp].b_end = b_end;
+      pos += kBlk;
+    }
+    for (; pos < b_end; pos += kBlk) {
+      __syncwarp();
+      load_tile(tile, A.sorted, pos, b_end, lane);
+      __syncwarp();
+      const int entries = int((min(kBlk, b_end - pos) + 1) >> 1);
+      scan_rows<V, kR, false>(sh, tile, alo, ahi, 0, entries, a_begin, pos, lane);
+      __syncwarp();
+      if (sh.warp[warp].n_staged >= unsigned(kStage / 2)) flush_stage(sh, warp, lane);
+    }
+  }
+  flush_stage(sh, warp, lane);
+}
+
+// ---- need == 2: buckets of a handful of rows -------------------------------------------------------
+// With two chunks per bucket key the buckets hold n / 2^21 rows or so: too small to give a warp each. One
+// thread per sorted position walks the rows after it while they share its key (a run of the sorted keys is a
+// bucket), OR-fold pre-filter, exact re-test, same first-unit rule. Runs are short, so neighbouring lanes
+// read the same few cache lines. Hits are staged per CTA.
+constexpr int kWalkThreads = 256, kWalkStage = 512;
+
+// pair tests of the batch: every run start adds len * (len - 1) / 2 (binary search for the run's end)
+__global__ void mih_run_tests_kernel(const uint32_t* __restrict__ key, uint32_t m, unsigned long long* __restrict__ info) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long tests = 0;
+  if (j < m && (j == 0 || key[j - 1] != key[j])) {
+    const uint32_t k = key[j];
+    uint32_t lo = j + 1, hi = m;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (key[mid] <= k) lo = mid + 1; else hi = mid;
+    }
+    const unsigned long long len = lo - j;
+    tests = len * (len - 1) / 2;
+  }
+  __shared__ unsigned long long red[8];
+  for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tests;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) t += red[w];
+    if (t) atomicAdd(info + kTests, t);
+  }
+}
+
+struct WalkArgs {
+  const uint64_t* sorted;
+  const uint32_t* key;
+  const uint32_t* rows;
+  uint32_t m;
+  unsigned long long* info;
+  unsigned long long max_tests;
+  MihPlan plan;
+  int threshold;
+  MihOut out;
+};
+
+__global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A) {
+  __shared__ MihPlan plan;
+  __shared__ uint4 stage[kWalkStage];
+  __shared__ unsigned n_staged;
+  __shared__ unsigned long long g_base;
+  if (A.max_tests && A.info[kTests] > A.max_tests) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.info[kDeclined] = 1;
+    return;
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
+    for (unsigned i = threadIdx.x; i < sizeof(MihPlan) / 4; i += kWalkThreads) dst[i] = src[i];
+    if (threadIdx.x == 0) n_staged = 0;
+  }
+  __syncthreads();
+  const uint32_t j = blockIdx.x * kWalkThreads + threadIdx.x;
+  if (j < A.m) {
+    const uint32_t k = A.key[j];
+    const uint64_t a = A.sorted[j];
+    const uint32_t alo = uint32_t(a), ahi = uint32_t(a >> 32);
+    const uint32_t unit = k >> A.plan.key_shift;
+    const int c1 = plan.u_c1[unit], c2 = plan.u_c2[unit];
+    const int T = A.threshold;
+    for (uint32_t q = j + 1; q < A.m && A.key[q] == k; ++q) {
+      const uint64_t b = A.sorted[q];
+      const uint32_t xlo = alo ^ uint32_t(b), xhi = ahi ^ uint32_t(b >> 32);
+      if (__popc(xlo | xhi) >= T) continue;
+      const int d = __popc(xlo) + __popc(xhi);
+      if (d >= T) continue;
+      const uint64_t x = (uint64_t(xhi) << 32) | xlo;
+      bool first = true;
+      for (int c = 0; c < c2; ++c)
+        if (c != c1 && ((uint32_t(x >> plan.shift[c])) & plan.mask[c]) == 0) first = false;
+      if (!first) continue;
+      const unsigned at = atomicAdd(&n_staged, 1u);
+      if (at < unsigned(kWalkStage)) {
+        stage[at] = make_uint4(j, q, uint32_t(d), 0u);
+      } else {
+        const uint32_t ra = A.rows[j], rb = A.rows[q];
+        if (A.out.mode == 0) {
+          const unsigned long long pos = atomicAdd(A.out.count, 2ull);
+          if (pos < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos] = make_uint4(ra, rb, uint32_t(d), 0u);
+          if (pos + 1 < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos + 1] = make_uint4(rb, ra, uint32_t(d), 0u);
+        } else {
+          const uint32_t ia = A.out.ids[ra], ib = A.out.ids[rb];
+          const unsigned long long kk = (ia ? 1 : 0) + (ib ? 1 : 0);
+          if (kk) {
+            unsigned long long pos = atomicAdd(A.out.count, kk);
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(A.out.out);
+            if (ib) {
+              if (pos < A.out.cap) o[pos] = ((unsigned long long)ra << A.out.needle_shift) | ((unsigned long long)d << 32) | ib;
+              ++pos;
+            }
+            if (ia && pos < A.out.cap) o[pos] = ((unsigned long long)rb << A.out.needle_shift) | ((unsigned long long)d << 32) | ia;
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  const unsigned staged = min(n_hit, unsigned(kHitBuf));
-  if (threadIdx.x == 0 && staged) g_base = atomicAdd(count, (unsigned long long)staged);
+  // flush: two records per staged pair in mode 0; in mode 1 rows without id drop out, so count first
+  const unsigned n = min(n_staged, unsigned(kWalkStage));
+  if (!n) return;
+  __shared__ unsigned kept;
+  if (threadIdx.x == 0) kept = 0;
   __syncthreads();
-  for (unsigned i = threadIdx.x; i < staged; i += kSmallThreads)
-    if (g_base + i < cap) {
-      const uint32_t e = hitbuf[i];
-      const uint32_t a = base + (e & 511u), b = base + ((e >> 9) & 4095u) - kSmallMax;
-      *reinterpret_cast<uint4*>(out + g_base + i) = make_uint4(rows[a], rows[b], e >> 21, 0u);
+  for (unsigned i = threadIdx.x; i < n; i += kWalkThreads) {
+    const uint4 e = stage[i];
+    const uint32_t ra = A.rows[e.x], rb = A.rows[e.y];
+    unsigned k2 = 2;
+    uint32_t ia = 1, ib = 1;
+    if (A.out.mode == 1) {
+      ia = A.out.ids[ra];
+      ib = A.out.ids[rb];
+      k2 = (ia ? 1 : 0) + (ib ? 1 : 0);
     }
+    const unsigned at = k2 ? atomicAdd(&kept, k2) : 0;
+    stage[i] = make_uint4(ra, rb, e.z | (at << 8), (ia ? 1u : 0u) | (ib ? 2u : 0u));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && kept) g_base = atomicAdd(A.out.count, (unsigned long long)kept);
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < n; i += kWalkThreads) {
+    const uint4 e = stage[i];
+    const uint32_t d = e.z & 0xFFu;
+    unsigned long long pos = g_base + (e.z >> 8);
+    if (A.out.mode == 0) {
+      if (pos < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos] = make_uint4(e.x, e.y, d, 0u);
+      if (pos + 1 < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos + 1] = make_uint4(e.y, e.x, d, 0u);
+    } else {
+      unsigned long long* o = reinterpret_cast<unsigned long long*>(A.out.out);
+      if (e.w & 2u) {
+        if (pos < A.out.cap) o[pos] = ((unsigned long long)e.x << A.out.needle_shift) | ((unsigned long long)d << 32) | A.out.ids[e.y];
+        ++pos;
+      }
+      if ((e.w & 1u) && pos < A.out.cap)
+        o[pos] = ((unsigned long long)e.y << A.out.needle_shift) | ((unsigned long long)d << 32) | A.out.ids[e.x];
+    }
+  }
+}
+
+// every row matches itself at distance 0: rows [lo, hi), for n_parts > 1 only those whose unit-0 bucket is `part`'s
+__global__ void mih_self_kernel(const uint64_t* __restrict__ hash, uint32_t lo, uint32_t hi, MihPlan plan, uint32_t part,
+                                uint32_t n_parts, MihOut o) {
+  const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  bool emit = i < hi;
+  uint32_t id = 0;
+  if (emit && n_parts > 1) emit = unit_bucket(plan, 0, hash[i]) % n_parts == part;
+  if (emit && o.mode == 1) {
+    id = o.ids[i];
+    emit = id != 0;
+  }
+  __shared__ unsigned wcount[8];
+  __shared__ unsigned long long base;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, emit);
+  if (lane == 0) wcount[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) {
+      const unsigned c = wcount[w];
+      wcount[w] = t;
+      t += c;
+    }
+    base = t ? atomicAdd(o.count, (unsigned long long)t) : 0ull;
+  }
+  __syncthreads();
+  if (!emit) return;
+  const unsigned long long at = base + wcount[warp] + __popc(m & ((1u << lane) - 1u));
+  if (at >= o.cap) return;
+  if (o.mode == 0) reinterpret_cast<uint4*>(o.out)[at] = make_uint4(i, i, 0u, 0u);
+  else reinterpret_cast<unsigned long long*>(o.out)[at] = ((unsigned long long)i << o.needle_shift) | id;
+}
+
+int g_forced_bucket_variant = 0;
+int g_forced_need = 0;
+
+int bucket_variant_for(const MihPlan& plan, int threshold) {
+  if (g_forced_bucket_variant >= 1 && g_forced_bucket_variant <= 3) return g_forced_bucket_variant;
+  static const int env = getenv("CB_MIH_VARIANT") ? atoi(getenv("CB_MIH_VARIANT")) : 0;
+  if (env >= 1 && env <= 3) return env;
+  // rows of a bucket agree on the unit's chunk bits, so the folds see fewer random bits than in the dense scan:
+  // the AND of two OR-folds keeps the false-positive rate of a warp step at a few percent up to T = 5
+  // (tools/mih_bench.py measures all three); above that only the plain OR-fold stays selective
+  (void)plan;
+  return threshold <= 6 ? 3 : 1;
 }
 
 }  // namespace
 
-MihPlan mih_plan(int threshold) {
+MihPlan mih_plan(int threshold, int need) {
   MihPlan p;
-  const int chunks = std::max(1, std::min(threshold, kMihMaxThreshold));
+  memset(&p, 0, sizeof(p));
+  const int t = std::max(1, std::min(threshold, kMihMaxThreshold));
+  need = need == 2 ? 2 : 1;
+  const int chunks = t - 1 + need;  // at most t - 1 chunks can hold a differing bit
   p.chunks = chunks;
-  p.key_shift = 0;
+  p.need = need;
+  const int cap = need == 2 ? 12 : 16;  // bucket-index bits taken from one chunk
   const int base = 63 / chunks, rem = 63 % chunks;
   int start = 1;  // bit 0 of a dct hash carries no information (src/cvutil.cpp:537-538)
-  for (int c = 0; c < kMihMaxThreshold; ++c) {
-    const int len = c < chunks ? base + (c < rem ? 1 : 0) : 0;
-    p.shift[c] = c < chunks ? start : 0;
-    p.mask[c] = c < chunks ? ((1u << std::min(len, 16)) - 1u) : 0u;
-    p.key_shift = std::max(p.key_shift, std::min(len, 16));
+  int widest = 0;
+  for (int c = 0; c < chunks; ++c) {
+    const int len = base + (c < rem ? 1 : 0);
+    p.shift[c] = start;
+    p.bits[c] = std::min(len, cap);
+    p.mask[c] = (1u << p.bits[c]) - 1u;
+    widest = std::max(widest, p.bits[c]);
     start += len;
   }
+  int u = 0;
+  if (need == 1) {
+    for (int c = 0; c < chunks; ++c, ++u) p.u_c1[u] = p.u_c2[u] = int8_t(c);
+    p.key_shift = widest;
+  } else {
+    int wide2 = 0;
+    for (int a = 0; a < chunks; ++a)
+      for (int b = a + 1; b < chunks; ++b, ++u) {
+        p.u_c1[u] = int8_t(a);
+        p.u_c2[u] = int8_t(b);
+        wide2 = std::max(wide2, p.bits[a] + p.bits[b]);
+      }
+    p.key_shift = wide2;
+  }
+  p.units = u;
   return p;
 }
 
 bool mih_applicable(uint64_t n, int threshold) {
-  return threshold >= 1 && threshold <= kMihMaxThreshold && n >= (1u << 15) &&
-         n * uint64_t(threshold) < 0xFFFF0000ull;
+  if (g_forced_need < 0) return false;  // measurement aid: brute-force scan only
+  return threshold >= 1 && threshold <= kMihMaxThreshold && n >= (1u << 15) && n <= (1ull << 30);
+}
+
+// chunks that must agree: 1 = T chunks / T units (big buckets, little sorting), 2 = T + 1 chunks / T(T+1)/2 units
+// (tiny buckets, more sorting). Cost model in sorted items + pair tests, constants from tools/mih_bench.py.
+int mih_need_for(uint64_t n, int threshold) {
+  if (g_forced_need == 1 || g_forced_need == 2) return g_forced_need;
+  static const int env = getenv("CB_MIH_NEED") ? atoi(getenv("CB_MIH_NEED")) : 0;
+  if (env == 1 || env == 2) return env;
+  double best = 0;
+  int best_need = 1;
+  for (int need = 1; need <= 2; ++need) {
+    const MihPlan p = mih_plan(threshold, need);
+    double tests = 0;
+    for (int u = 0; u < p.units; ++u) {
+      const int bits = need == 1 ? p.bits[p.u_c1[u]] : p.bits[p.u_c1[u]] + p.bits[p.u_c2[u]];
+      const double s = double(n) / double(1u << bits);  // rows per bucket on uniformly random hashes
+      tests += double(n) * (s + 256.0) / 2.0;
+    }
+    const double cost = double(n) * p.units * 60.0 + tests;  // one sorted item ~ 60 pair tests
+    if (need == 1 || cost < best) {
+      best = cost;
+      best_need = need;
+    }
+  }
+  return best_need;
 }
 
 MihWorkspace::~MihWorkspace() {
@@ -241,86 +724,157 @@ MihWorkspace::~MihWorkspace() {
 }
 
 // every ordered pair (a, b), a == b included, with hamm64 < threshold whose first shared bucket belongs to
-// `part`; appended to out (count is always the total). *declined = 1 (nothing emitted) when the buckets are so
-// skewed that the pass would cost more than `max_tests` pair tests (0 = never decline).
-int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, cb_pair* out,
-                    unsigned long long cap, unsigned long long* d_count, MihWorkspace& ws, unsigned long long max_tests,
-                    int* declined, cudaStream_t stream) {
-  if (declined) *declined = 0;
+// `part`; appended to out (count is always the total). When the buckets are so skewed that a batch would cost
+// more than `max_tests` pair tests (0 = never decline) its scan kernel leaves at once and flags it: the caller
+// reads that with mih_read_info after its own synchronisation, discards the list and runs the brute-force scan.
+// No host synchronisation in here for n_parts == 1.
+int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, const MihOut& out,
+                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream) {
   if (n == 0 || threshold <= 0) return CB_OK;
-  if (threshold > kMihMaxThreshold || uint64_t(n) * uint64_t(threshold) >= 0xFFFF0000ull || n_parts == 0 || part >= n_parts) {
+  if (threshold > kMihMaxThreshold || n > (1u << 30) || n_parts == 0 || part >= n_parts) {
     set_error("scan64_self_mih: threshold %d / %u rows / part %u of %u outside the supported range", threshold, n, part,
               n_parts);
     return CB_ERR_UNSUPPORTED;
   }
-  const MihPlan plan = mih_plan(threshold);
-  const size_t total = size_t(n) * plan.chunks;
-  const uint32_t n_buckets = uint32_t(plan.chunks) << plan.key_shift;
+  const MihPlan plan = mih_plan(threshold, mih_need_for(n, threshold));
+  // units are processed in batches that keep the sort below 2^29 items
+  int per_batch = std::max<int>(1, int((1ull << 29) / n));
+  per_batch = std::min(per_batch, plan.units);
+  const size_t total = size_t(n) * per_batch;
   int rc;
+  // bucket tables exist only for need 1 (need 2 walks the runs of the sorted keys)
+  const uint32_t n_buckets_max = plan.need == 1 ? uint32_t(per_batch) << plan.key_shift : 0u;
+  const uint32_t n_blocks_bound_max = plan.need == 1 ? uint32_t(total / kBlk) + n_buckets_max / 2 + 2 : 0u;
   if ((rc = ws.key.reserve(total)) != CB_OK || (rc = ws.key2.reserve(total)) != CB_OK || (rc = ws.val.reserve(total)) != CB_OK ||
       (rc = ws.val2.reserve(total)) != CB_OK || (rc = ws.sorted.reserve(total + 2)) != CB_OK ||
-      (rc = ws.ofs.reserve(n_buckets + 2)) != CB_OK || (rc = ws.n_big.reserve(n_buckets + 2)) != CB_OK ||
-      (rc = ws.big_at.reserve(n_buckets + 2)) != CB_OK || (rc = ws.info.reserve(4)) != CB_OK)
+      (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK || (rc = ws.nblk.reserve(n_buckets_max + 2)) != CB_OK ||
+      (rc = ws.blk_at.reserve(n_buckets_max + 2)) != CB_OK || (rc = ws.nitems.reserve(n_blocks_bound_max + 2)) != CB_OK ||
+      (rc = ws.item_at.reserve(n_blocks_bound_max + 2)) != CB_OK || (rc = ws.info.reserve(kInfoSlots * 64)) != CB_OK)
     return rc;
-  if (!ws.h_info) CB_CUDA(cudaMallocHost(&ws.h_info, 4 * sizeof(unsigned long long)));
-  CB_CUDA(cudaMemsetAsync(ws.info.p, 0, 4 * sizeof(unsigned long long), stream));
-  mih_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan, part, n_parts, ws.key.p, ws.val.p, ws.info.p + 3);
-  CB_CUDA(cudaGetLastError());
-  uint32_t m = uint32_t(total);
-  if (n_parts > 1) {  // only this rank's share of the (row, chunk) items was written
-    CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    CB_CUDA(cudaStreamSynchronize(stream));
-    m = uint32_t(ws.h_info[0]);
+  if (!ws.h_info) CB_CUDA(cudaMallocHost(&ws.h_info, 64 * kInfoSlots * sizeof(unsigned long long)));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device());
+  const int variant = bucket_variant_for(plan, threshold);
+  ws.n_batches = 0;
+  int batch_no = 0;
+  for (int u0 = 0; u0 < plan.units; u0 += per_batch, ++batch_no) {
+    const int u1 = std::min(plan.units, u0 + per_batch);
+    if (batch_no >= 64) {
+      set_error("scan64_self_mih: too many unit batches");
+      return CB_ERR_UNSUPPORTED;
+    }
+    unsigned long long* info = ws.info.p + size_t(batch_no) * kInfoSlots;  // one slot set per batch: nothing is reused in flight
+    const uint32_t n_buckets = uint32_t(u1 - u0) << plan.key_shift;
+    CB_CUDA(cudaMemsetAsync(info, 0, kInfoSlots * sizeof(unsigned long long), stream));
+    mih_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan, u0, u1, part, n_parts, ws.key.p, ws.val.p, info + kKept);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+    uint32_t m = uint32_t(size_t(n) * (u1 - u0));
+    if (n_parts > 1) {  // only this rank's share of the (row, unit) items was written: the sort needs the count
+      CB_CUDA(cudaMemcpyAsync(ws.h_info, info + kKept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaStreamSynchronize(stream));
+      m = uint32_t(ws.h_info[0]);
+    }
+    if (m == 0) continue;
+    int key_bits = plan.key_shift;  // (unit << key_shift) | bucket: as few radix passes as the plan allows
+    while ((1 << (key_bits - plan.key_shift)) < (u1 - u0)) ++key_bits;
+    const uint32_t n_blocks_bound = m / kBlk + std::min<uint32_t>(n_buckets, m / 2) + 1;
+    size_t tb = 0, tb2 = 0, tb3 = 0;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                            key_bits, stream));
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, ws.nblk.p, ws.blk_at.p, int(n_buckets + 1), stream));
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb3, ws.nitems.p, ws.item_at.p, int(n_blocks_bound + 1), stream));
+    if ((rc = ws.temp.reserve(std::max(tb, std::max(tb2, tb3)) + 16)) != CB_OK) return rc;
+    prof_begin(kProfMihSort, stream);
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(ws.temp.p, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                            key_bits, stream));
+    prof_end(kProfMihSort, stream);
+    mih_gather_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_hashes, ws.val2.p, nullptr, m, ws.sorted.p);
+    CB_CUDA(cudaGetLastError());
+    if (plan.need == 2) {  // tiny buckets: one thread per sorted position, runs of equal keys are the buckets
+      if (max_tests) {
+        mih_run_tests_kernel<<<(m + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, info);
+        CB_CUDA(cudaGetLastError());
+      }
+      WalkArgs WA{ws.sorted.p, ws.key2.p, ws.val2.p, m, info, max_tests, plan, threshold, out};
+      for (int u = 0; u + u0 < plan.units; ++u) {
+        WA.plan.u_c1[u] = plan.u_c1[u + u0];
+        WA.plan.u_c2[u] = plan.u_c2[u + u0];
+      }
+      prof_begin(kProfMihBucket, stream);
+      mih_walk_kernel<<<(m + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, stream>>>(WA);
+      CB_CUDA(cudaGetLastError());
+      prof_end(kProfMihBucket, stream);
+      counters().launches += 4;
+      ws.n_batches = batch_no + 1;
+      continue;
+    }
+    const unsigned bblocks = (n_buckets + 1 + 255) / 256;
+    mih_bounds_kernel<<<bblocks, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
+    CB_CUDA(cudaGetLastError());
+    mih_blocks_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.nblk.p, info);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.nblk.p, ws.blk_at.p, int(n_buckets + 1), stream));
+    const unsigned gblocks = (n_blocks_bound + 1 + 255) / 256;
+    mih_item_counts_kernel<<<gblocks, 256, 0, stream>>>(ws.ofs.p, ws.blk_at.p, n_buckets, plan.key_shift, n_blocks_bound,
+                                                       ws.nitems.p, info);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb3, ws.nitems.p, ws.item_at.p, int(n_blocks_bound + 1), stream));
+    // a block has at most kSegsPerBlock + 1 items and more than one only when its range exceeds kSegMin rows: a
+    // bucket of s rows adds at most s / 32 items beyond its blocks
+    if ((rc = ws.items.reserve(size_t(n_blocks_bound) + size_t(m) / 32 + 16)) != CB_OK) return rc;
+    mih_item_write_kernel<<<gblocks, 256, 0, stream>>>(ws.ofs.p, ws.blk_at.p, n_buckets, plan.key_shift, n_blocks_bound,
+                                                      ws.item_at.p, ws.items.p, info);
+    CB_CUDA(cudaGetLastError());
+    BucketArgs A{ws.sorted.p, ws.val2.p, ws.items.p, info, max_tests, plan, threshold, out};
+    // the unit numbers in the items are batch-local: shift the plan's unit tables
+    if (u0) {
+      for (int u = 0; u + u0 < plan.units; ++u) {
+        A.plan.u_c1[u] = plan.u_c1[u + u0];
+        A.plan.u_c2[u] = plan.u_c2[u + u0];
+      }
+    }
+    const int grid = sm_count * 3;
+    prof_begin(kProfMihBucket, stream);
+    switch (variant) {
+      case 1: mih_bucket_kernel<1><<<grid, kBkThreads, 0, stream>>>(A); break;
+      case 2: mih_bucket_kernel<2><<<grid, kBkThreads, 0, stream>>>(A); break;
+      default: mih_bucket_kernel<3><<<grid, kBkThreads, 0, stream>>>(A); break;
+    }
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfMihBucket, stream);
+    counters().launches += 7;
+    ws.n_batches = batch_no + 1;  // the next batch reuses the sort buffers: stream order keeps that safe
   }
+  // self pairs: rows [0, n) (dealt by their unit-0 bucket when the buckets are dealt)
+  mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
+  CB_CUDA(cudaGetLastError());
   counters().launches += 1;
-  if (m == 0) return CB_OK;
-  int key_bits = plan.key_shift;  // (chunk << key_shift) | bucket: as few radix passes as the threshold allows
-  while ((1 << (key_bits - plan.key_shift)) < plan.chunks) ++key_bits;
-  size_t tb = 0, tb2 = 0;
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
-                                          key_bits, stream));
-  CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
-  if ((rc = ws.temp.reserve(std::max(tb, tb2) + 16)) != CB_OK) return rc;
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(ws.temp.p, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
-                                          key_bits, stream));
-  mih_gather_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_hashes, ws.val2.p, m, ws.sorted.p);
-  CB_CUDA(cudaGetLastError());
-  const unsigned bblocks = (n_buckets + 1 + 255) / 256;
-  mih_bounds_kernel<<<bblocks, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
-  CB_CUDA(cudaGetLastError());
-  mih_tile_counts_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.n_big.p, ws.info.p);
-  CB_CUDA(cudaGetLastError());
-  CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb2, ws.n_big.p, ws.big_at.p, int(n_buckets + 1), stream));
-  // upper bound of the tile list: ceil(s / 2048) items per bucket of more than 1024 rows
-  if ((rc = ws.big_tiles.reserve(size_t(m) / kSmallMax + 2)) != CB_OK) return rc;
-  mih_tile_write_kernel<<<bblocks, 256, 0, stream>>>(ws.ofs.p, n_buckets, ws.big_at.p, ws.big_tiles.p, ws.info.p);
-  CB_CUDA(cudaGetLastError());
-  CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  return CB_OK;
+}
+
+int mih_read_info(MihWorkspace& ws, cudaStream_t stream, unsigned long long* tests, int* declined) {
+  if (tests) *tests = 0;
+  if (declined) *declined = 0;
+  if (!ws.n_batches || !ws.h_info) return CB_OK;
+  CB_CUDA(cudaMemcpyAsync(ws.h_info, ws.info.p, size_t(ws.n_batches) * kInfoSlots * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, stream));
   CB_CUDA(cudaStreamSynchronize(stream));
-  counters().launches += 4;
-  const uint32_t n_big = uint32_t(ws.h_info[1]);
-  const unsigned long long tests = ws.h_info[2];
-  if (max_tests && tests > max_tests) {
-    if (declined) *declined = 1;
-    return CB_OK;
+  for (int b = 0; b < ws.n_batches; ++b) {
+    if (tests) *tests += ws.h_info[b * kInfoSlots + kTests];
+    if (declined && ws.h_info[b * kInfoSlots + kDeclined]) *declined = 1;
   }
-  mih_small_kernel<<<(m + kSmallRows - 1) / kSmallRows, kSmallThreads, 0, stream>>>(ws.sorted.p, ws.val2.p, ws.key2.p, ws.ofs.p, m,
-                                                                                   plan, threshold, out, cap, d_count);
-  CB_CUDA(cudaGetLastError());
-  counters().launches += 1;
-  if (n_big) {
-    Scan64Launch L{ws.sorted.p, m, ws.sorted.p, m, threshold, 0, out, cap, d_count};
-    MihEmit E{ws.val2.p, ws.key2.p, plan};
-    rc = scan64_tiles_mih_launch(L, ws.big_tiles.p, n_big, E, stream);
-    if (rc != CB_OK) return rc;
-  }
-  counters().comparisons += tests;
   return CB_OK;
 }
 
 }  // namespace cbird
 
 using namespace cbird;
+
+static MihWorkspace* raw_ws() {
+  static thread_local MihWorkspace ws[16];  // per calling thread and device
+  return ws;
+}
 
 extern "C" {
 
@@ -332,9 +886,18 @@ int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, 
     set_error("cb_scan64_self_mih_dev: null pointer argument");
     return CB_ERR_INVALID;
   }
-  static thread_local MihWorkspace ws[16];  // per calling thread and device
-  return scan64_self_mih(d_hashes, n, threshold, part, n_parts, d_out, cap, d_count, ws[current_device() & 15], 0, nullptr,
+  MihOut out{0, d_out, cap, d_count, nullptr, 0};
+  return scan64_self_mih(d_hashes, n, threshold, part, n_parts, out, raw_ws()[current_device() & 15], 0,
                          static_cast<cudaStream_t>(stream));
+}
+
+int cb_scan64_mih_last_tests(void* stream, uint64_t* tests_out) {
+  int rc = ensure_device();
+  if (rc != CB_OK) return rc;
+  unsigned long long t = 0;
+  rc = mih_read_info(raw_ws()[current_device() & 15], static_cast<cudaStream_t>(stream), &t, nullptr);
+  if (tests_out) *tests_out = t;
+  return rc;
 }
 
 int cb_scan64_mih_max_threshold(void) { return kMihMaxThreshold; }
@@ -344,12 +907,25 @@ int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks) {
     set_error("cb_scan64_mih_plan: threshold %d outside [1, %d]", threshold, kMihMaxThreshold);
     return CB_ERR_UNSUPPORTED;
   }
-  const MihPlan p = mih_plan(threshold);
+  const MihPlan p = mih_plan(threshold, 1);
   for (int c = 0; c < p.chunks; ++c) {
     if (shifts) shifts[c] = p.shift[c];
     if (masks) masks[c] = p.mask[c];
   }
   return p.chunks;
+}
+
+void cb_scan64_mih_force(int variant, int need) {
+  g_forced_bucket_variant = variant;
+  g_forced_need = need;
+}
+
+int cb_scan64_mih_config(uint64_t n, int threshold, int* variant, int* need) {
+  if (!mih_applicable(n, threshold)) return 0;
+  const int nd = mih_need_for(n, threshold);
+  if (need) *need = nd;
+  if (variant) *variant = nd == 2 ? 1 : bucket_variant_for(mih_plan(threshold, nd), threshold);
+  return 1;
 }
 
 }  // extern "C"

@@ -57,13 +57,8 @@ struct TileBounds {
   uint32_t mirror_above;  // B tiles starting above this row also emit the mirrored pair (0xFFFFFFFF = never)
 };
 
-// MIH = tile list of a multi-index self-join (mih.cu): positions are bucket-sorted, a hit is reported as original
-// row numbers and only from the first chunk in which the two hashes share a bucket. Dense scans instantiate
-// MIH = false and compile to the same code as before.
-template <bool MIH>
 __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds& B, uint32_t alo, uint32_t ahi,
-                                           uint32_t blo, uint32_t bhi, uint32_t ai, uint32_t bi, bool mirror,
-                                           const MihEmit* M) {
+                                           uint32_t blo, uint32_t bhi, uint32_t ai, uint32_t bi, bool mirror) {
   // opaque copies: without them the compiler shares the XORs of this rare path with the pre-filter
   // and the hot loop grows from 3 to 6 LOP3 per pair of pairs (seen in SASS / ncu: ALU pipe 92 %)
   asm volatile("" : "+r"(alo), "+r"(ahi));
@@ -72,14 +67,6 @@ __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds
   // most entries are false positives of the pre-filter: leave through the cheapest test first
   if (d >= P.threshold) return;
   if (ai < B.a_limit && bi < B.b_end && ((xlo >> 1) & P.radix_mask) == 0) {
-    if constexpr (MIH) {
-      const uint64_t x = (uint64_t(ahi ^ bhi) << 32) | xlo;
-      const int chunk = int(M->keys[ai] >> M->plan.key_shift);
-      for (int c = 0; c < chunk; ++c)
-        if ((uint32_t(x >> M->plan.shift[c]) & M->plan.mask[c]) == 0) return;
-      ai = M->rows[ai];
-      bi = M->rows[bi];
-    }
     const unsigned long long pos = atomicAdd(P.count, mirror ? 2ull : 1ull);
     if (pos < P.cap) *reinterpret_cast<uint4*>(P.out + pos) = make_uint4(ai, bi, uint32_t(d), 0u);
     if (mirror && pos + 1 < P.cap) *reinterpret_cast<uint4*>(P.out + pos + 1) = make_uint4(bi, ai, uint32_t(d), 0u);
@@ -88,8 +75,8 @@ __device__ __forceinline__ void emit_exact(const ScanParams& P, const TileBounds
 
 // one CTA-level tile: A rows [B.a_base + tid + r*256) held in registers against B rows [b_begin,b_end)
 // streamed through `tile`.
-template <int VARIANT, bool MIH = false>
-__device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds& B, uint4* tile, const MihEmit* M = nullptr) {
+template <int VARIANT>
+__device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds& B, uint4* tile) {
   uint32_t alo[kR], ahi[kR];
   const uint32_t a_base = B.a_base + threadIdx.x;
 #pragma unroll
@@ -138,8 +125,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
           for (int r = 0; r < kR; ++r)
             if (int(p[r]) < T) {
               const uint32_t ai = a_base + r * kThreads;
-              emit_exact<MIH>(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror, M);
-              emit_exact<MIH>(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror, M);
+              emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+              emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
             }
         }
       } else if (VARIANT == 1) {
@@ -157,8 +144,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact<MIH>(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror, M);
-            if (int(p1[r]) < T) emit_exact<MIH>(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror, M);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
           }
         }
       } else {
@@ -176,8 +163,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const TileBounds&
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
             const uint32_t ai = a_base + r * kThreads;
-            if (int(p0[r]) < T) emit_exact<MIH>(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror, M);
-            if (int(p1[r]) < T) emit_exact<MIH>(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror, M);
+            if (int(p0[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.x, d.y, ai, bi, mirror);
+            if (int(p1[r]) < T) emit_exact(P, B, alo[r], ahi[r], d.z, d.w, ai, bi + 1, mirror);
           }
         }
       }
@@ -218,21 +205,6 @@ __global__ void __launch_bounds__(kThreads, 3)
   B.b_end = t.b_begin + t.b_count;
   B.mirror_above = 0xFFFFFFFFu;
   scan_tile<VARIANT>(P, B, tile);
-}
-
-// the large buckets of a multi-index self-join: same loop, MIH reporting
-template <int VARIANT>
-__global__ void __launch_bounds__(kThreads, 3)
-    scan64_tiles_mih_kernel(const ScanParams P, const cb_scan_tile* __restrict__ tiles, const MihEmit M) {
-  __shared__ uint4 tile[kBTile / 2];
-  const cb_scan_tile t = tiles[blockIdx.x];
-  TileBounds B;
-  B.a_base = t.a_begin;
-  B.a_limit = t.a_begin + t.a_count;
-  B.b_begin = t.b_begin;
-  B.b_end = t.b_begin + t.b_count;
-  B.mirror_above = 0xFFFFFFFFu;
-  scan_tile<VARIANT, true>(P, B, tile, &M);
 }
 
 std::atomic<int> g_forced_variant{-1};
@@ -293,11 +265,13 @@ int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
   P.slab = tiles_per_slab * kBTile;
 
   dim3 grid(a_blocks, slabs), block(kThreads);
+  prof_begin(kProfScan, stream);
   switch (scan64_variant_for(P.threshold)) {
     case 2: scan64_kernel<2><<<grid, block, 0, stream>>>(P); break;
     case 1: scan64_kernel<1><<<grid, block, 0, stream>>>(P); break;
     default: scan64_kernel<0><<<grid, block, 0, stream>>>(P); break;
   }
+  prof_end(kProfScan, stream);
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
   counters().comparisons += uint64_t(L.n_a) * uint64_t(L.n_b - L.b_lo);  // nominal (reference semantics)
@@ -332,32 +306,6 @@ int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
   counters().comparisons += pair_tests;
-  return CB_OK;
-}
-
-int scan64_tiles_mih_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint32_t n_tiles, const MihEmit& E,
-                            cudaStream_t stream) {
-  if (n_tiles == 0 || L.threshold <= 0) return CB_OK;
-  ScanParams P;
-  P.a = L.a;
-  P.b = L.b;
-  P.n_a = L.n_a;
-  P.n_b = L.n_b;
-  P.slab = 0;
-  P.b_lo = 0;
-  P.symmetric = 0;
-  P.threshold = L.threshold > 65 ? 65 : L.threshold;
-  P.radix_mask = 0u;
-  P.out = L.out;
-  P.cap = L.cap;
-  P.count = L.count;
-  switch (scan64_variant_for(P.threshold)) {
-    case 2: scan64_tiles_mih_kernel<2><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles, E); break;
-    case 1: scan64_tiles_mih_kernel<1><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles, E); break;
-    default: scan64_tiles_mih_kernel<0><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles, E); break;
-  }
-  CB_CUDA(cudaGetLastError());
-  counters().launches += 1;
   return CB_OK;
 }
 

@@ -176,9 +176,23 @@ class DctHashIndex:
         p = params.to_c()
         po, ph, n = C.c_void_p(), C.c_void_p(), C.c_int64(0)
         check(self._L.cb_dct_index_similar_alloc(self._h, C.byref(p), C.byref(po), C.byref(ph), C.byref(n)))
-        offsets = _lib.take_array(po.value, self.count() + 1, np.dtype(np.int64))
+        r0, r1 = self.shard_rows()
+        offsets = _lib.take_array(po.value, r1 - r0 + 1, np.dtype(np.int64))
         hits = _lib.take_array(ph.value, n.value, _lib.HIT_DTYPE)
         return offsets, hits
+
+    def shard_rows(self):
+        """rows whose results this process's similar() returns: all of them, except one-process-per-GPU runs."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self._L.cb_dct_index_shard_rows(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def similar_count(self, params: SearchParams):
+        """the -similar pass without the result copy: (kept hits, pair tests issued)."""
+        p = params.to_c()
+        n, t = C.c_int64(0), C.c_uint64(0)
+        check(self._L.cb_dct_index_similar_count(self._h, C.byref(p), C.byref(n), C.byref(t)))
+        return int(n.value), int(t.value)
 
     def similar_shard(self, params: SearchParams, row_begin: int, row_end: int) -> np.ndarray:
         """all rows as needles against this rank's row shard; unsorted across ranks, no post step."""

@@ -24,8 +24,10 @@ def dct_hashes(n, seed, planted_frac=0.2, max_flips=6):
     return h, ids
 
 
-def dct_hashes_fast(n, seed, planted_frac=0.1, max_flips=6):
-    """vectorised variant for 10^6..10^8 rows (sources are drawn from the random part only)."""
+def dct_hashes_fast(n, seed, planted_frac=0.1, max_flips=6, return_plan=False):
+    """vectorised variant for 10^6..10^8 rows: a planted row is a copy of the ORIGINAL random value of another
+    row with 1..max_flips random bits flipped. return_plan adds (planted rows, their source rows), which is
+    what an exact expected hit count needs (rows planted from the same source form a cluster)."""
     rng = np.random.default_rng(seed)
     h = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) << _U64(1)
     n_plant = int(n * planted_frac)
@@ -39,7 +41,11 @@ def dct_hashes_fast(n, seed, planted_frac=0.1, max_flips=6):
             mask = np.where(flips > k, _U64(1) << bits, _U64(0)).astype(np.uint64)
             v ^= mask
         h[dst] = v
+    else:
+        dst = src = np.zeros(0, np.int64)
     ids = np.arange(1, n + 1, dtype=np.uint32)
+    if return_plan:
+        return h, ids, dst, src
     return h, ids
 
 

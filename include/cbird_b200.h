@@ -104,10 +104,38 @@ void cb_params_default(cb_params* p);           /* SearchParams() defaults, src/
 int cb_stats_get(cb_stats* out);
 void cb_stats_reset(void);
 void cb_free(void* p);                           /* frees buffers returned by *_alloc calls */
+/* ---- multi-GPU (one box, NVLink): the indexes of this process are replicated / sharded over several GPUs and
+ * the sharded calls (cb_dct_index_load, cb_dct_index_similar_alloc) fan out over them, exchanging hit lists
+ * with NCCL. Call once, before any index is created; without it every handle lives on the device selected
+ * with cb_set_device. Where a cbird build would call it: Engine::Engine (src/engine.cpp:38-45), before the
+ * Index objects are made.
+ *   cb_init            this process drives all the listed devices (one host thread per device inside the calls)
+ *   cb_comm_unique_id + cb_comm_init_rank   one process per GPU (e.g. torchrun): rank 0 makes the id, the
+ *                      launcher's transport carries it to the others, every process then joins with its rank.
+ *                      In this mode sharded results cover the calling rank's rows only (cb_dct_index_shard_rows)
+ *                      and load/add/remove must be called with the same data by every rank. */
+int cb_init(const int* devices, int n_devices);
+int cb_comm_unique_id(uint8_t* id_out, int cap);  /* returns the id size (128) or a negative status */
+int cb_comm_init_rank(const uint8_t* id, int id_bytes, int rank, int world, int device);
+int cb_comm_info(int* world, int* n_local, int* first_rank);
+void cb_shutdown(void);                          /* destroys the communicator; indexes must be destroyed first */
+
+/* Measurement aid: CUDA-event timing of the library's dominant kernels on the streams they are launched on
+ * (bench.py's roofline numbers). Disabled by default; when enabled every bracketed launch records two events,
+ * nothing is synchronised until cb_profile_get. Slots: 0 mih_bucket_kernel, 1 radix sort of the bucket keys,
+ * 2 radix sort of the hit keys, 3 scan64_kernel, 4 dct_hash32_kernel. */
+#define CB_PROFILE_SLOTS 8
+typedef struct cb_profile {
+  double ms[CB_PROFILE_SLOTS];        /* summed durations */
+  uint64_t launches[CB_PROFILE_SLOTS];
+} cb_profile;
+void cb_profile_enable(int on);
+int cb_profile_get(cb_profile* out, int reset); /* waits for the recorded events; call after synchronising */
 
 /* ---- kernel (a): dctHash64, replaces src/cvutil.cpp:435-545 (called from src/scanner.cpp:862 and
  * src/media.cpp:996) — batched: n 8-bit luma frames of w x h, rows `row_stride` bytes apart, frames
- * `frame_stride` bytes apart. out[i] is never 0 on success. w,h >= 32; w*h <= 1024*1024. ----------- */
+ * `frame_stride` bytes apart. out[i] is never 0 on success. w,h >= 32 (smaller frames: CB_ERR_UNSUPPORTED); frames
+ * of any larger size are accepted (tested up to 4000 x 3000). ------------------------------------------------ */
 int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                   uint64_t* out);
 /* device-resident variant on a caller stream (cudaStream_t passed as void*); asynchronous */
@@ -181,6 +209,15 @@ int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, 
 int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts,
                            cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream);
 int cb_scan64_mih_max_threshold(void);
+/* pair tests issued by the last cb_scan64_self_mih_dev of the calling thread (synchronises `stream`) */
+int cb_scan64_mih_last_tests(void* stream, uint64_t* tests_out);
+/* measurement / parity aid: force the pre-filter of the bucket scan (1 OR-fold, 2 AND-fold of two rows, 3 AND of
+ * two OR-folds; 0 = automatic) and the number of chunks a bucket key is built from (1 or 2; 0 = automatic).
+ * Every combination reports the identical hit set. */
+void cb_scan64_mih_force(int variant, int need); /* need = -1: no multi-index pass at all (brute-force scan) */
+/* what a self-join over n rows at this threshold would use: returns 1 and fills *variant / *need, or 0 when the
+ * brute-force scan runs instead (threshold > 10, fewer than 2^15 rows) */
+int cb_scan64_mih_config(uint64_t n, int threshold, int* variant, int* need);
 /* the bucket layout the self-join uses for a threshold (host only, no device needed): chunk c of a hash is
  * (h >> shifts[c]) & masks[c]; returns the number of chunks (== threshold) or a negative status */
 int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks);
@@ -195,6 +232,8 @@ typedef struct cb_dct_index cb_dct_index;
 cb_dct_index* cb_dct_index_create(void);                   /* DctHashIndex()            :40-43   */
 void cb_dct_index_destroy(cb_dct_index* ix);               /* ~DctHashIndex/unload      :53-65   */
 /* load(): the (id, phash_dct) rows the reference reads from SQL            :70-114  */
+/* n < 2^31 - 4096. The rows live on the device; a host copy is made only by the calls that need one
+ * (slice, mediaIds). With a communicator every rank uploads its share and an all-gather replicates it. */
 int cb_dct_index_load(cb_dct_index* ix, const uint32_t* ids, const uint64_t* hashes, int64_t n);
 int cb_dct_index_is_loaded(const cb_dct_index* ix);        /* isLoaded()                         */
 int64_t cb_dct_index_count(const cb_dct_index* ix);        /* count()                            */
@@ -206,9 +245,16 @@ cb_dct_index* cb_dct_index_slice(const cb_dct_index* ix, const uint32_t* ids, in
 /* mediaIds() for a loaded index: ids whose hash != 0                        :128-132 */
 int cb_dct_index_media_ids(const cb_dct_index* ix, uint32_t* out, int64_t cap, int64_t* n_out);
 /* find(): all rows with distance < p->dctThresh, ascending (score, mediaId); needle hash 0 -> none.
- * srcIn/dstIn/len are -1/-1/0.                                               :193-220 */
+ * srcIn/dstIn/len are -1/-1/0.                                               :193-220
+ * The reference calls find() from every thread of its pool at once (src/database.cpp:1400-1432 under the read
+ * lock of :1698). Concurrent callers are combined: whoever arrives while no launch is in flight leads a batch of
+ * up to 128 waiting needles through ONE kernel launch (needles travel as kernel arguments, hits come back
+ * through mapped host memory, no copy or stream synchronisation), hands the results out and passes the lead on.
+ * Results are identical to calling one at a time. */
 int cb_dct_index_find(cb_dct_index* ix, uint64_t needle_hash, const cb_params* p, cb_match* out, int64_t cap,
                       int64_t* n_out);
+/* launches and needles served by the find() queue so far */
+int cb_dct_index_find_queue_stats(const cb_dct_index* ix, uint64_t* batches, uint64_t* needles);
 /* N independent find() calls in one launch; hits sorted by (needle, score, mediaId). Returns a
  * library-allocated array in *out (release with cb_free). */
 int cb_dct_index_find_batch_alloc(cb_dct_index* ix, const uint64_t* needle_hashes, int64_t n_needles,
@@ -218,6 +264,15 @@ int cb_dct_index_find_batch_alloc(cb_dct_index* ix, const uint64_t* needle_hashe
  * Result: CSR over rows — offsets[count+1] and hits (needle = row index). Library-allocated. */
 int cb_dct_index_similar_alloc(cb_dct_index* ix, const cb_params* p, int64_t** offsets_out, cb_hit** hits_out,
                                int64_t* n_hits_out);
+/* With a communicator (cb_init / cb_comm_init_rank) the pass is sharded: hashes replicated on every rank, the
+ * bucket scans dealt to the ranks, every hit sent to the rank owning its needle row (NCCL all-to-all), sort and
+ * post step per rank. cb_init: the CSR covers all rows, like the single-GPU call. cb_comm_init_rank: it covers
+ * the calling rank's rows [row_begin, row_end) (offsets has row_end - row_begin + 1 entries starting at 0,
+ * hits carry global row numbers as `needle`). */
+int cb_dct_index_shard_rows(const cb_dct_index* ix, int64_t* row_begin, int64_t* row_end);
+/* the same pass without the result copy: kept hits of this process's rows and the pair tests its ranks issued
+ * (device-resident timing; the lists stay on the device) */
+int cb_dct_index_similar_count(cb_dct_index* ix, const cb_params* p, int64_t* n_hits_out, uint64_t* pair_tests_out);
 /* multi-GPU sharding hook: `-similar` needles are all rows, but only rows [row_begin,row_end) of the
  * index are searched (this rank's shard); hits carry GLOBAL row indices as `needle`, no post step.
  * Sorted by (needle, score, mediaId). */

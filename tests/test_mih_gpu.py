@@ -114,3 +114,32 @@ def test_index_similar_through_multi_index_path(cb, po, dht, max_thresh):
         assert g["mediaId"].tolist() == oi[:k].tolist(), row
         found += k
     assert found > 50
+
+
+@pytest.mark.parametrize("variant,need", [(1, 1), (2, 1), (3, 1), (0, 2)])
+def test_every_prefilter_and_key_width(cb, variant, need):
+    # the three pre-filters of the bucket scan and the two-chunk bucket keys (one thread per sorted position) must all
+    # report the brute-force hit set: random rows, one huge bucket, exact duplicates, removed rows
+    L = cb.lib()
+    h, _ = synth.dct_hashes_fast(200_000, seed=17, planted_frac=0.3)
+    h[:9000] = (h[:9000] & ~np.uint64(0x3FFE)) | np.uint64(0x2AAA)   # 9000 rows in one chunk-0 bucket (35 blocks, 2 segments)
+    h[20000:20700] = h[20000]                                          # 700 identical hashes
+    h[30000:30050] = 0
+    np.random.default_rng(1).shuffle(h)
+    try:
+        L.cb_scan64_mih_force(variant, need)
+        for thr in (3, 5, 8):
+            want, got, _ = both(cb, h, thr, cap=1 << 23)
+            assert np.array_equal(got, want), (variant, need, thr)
+        want, got, per_part = both(cb, h, 5, parts=3, cap=1 << 23)
+        assert np.array_equal(got, want) and sum(len(p) for p in per_part) == len(want)
+    finally:
+        L.cb_scan64_mih_force(0, 0)
+
+
+def test_bucket_of_many_segments(cb):
+    # a bucket larger than 8 segments of 8192 rows: blocks whose range is cut into proportional segments
+    h, _ = synth.dct_hashes_fast(140_000, seed=23, planted_frac=0.2)
+    h[:100_000] = (h[:100_000] & ~np.uint64(0x3FFE)) | np.uint64(0x0F0E)
+    want, got, _ = both(cb, h, 5, cap=1 << 23)
+    assert np.array_equal(got, want)
