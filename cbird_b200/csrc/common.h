@@ -160,13 +160,15 @@ struct MihWorkspace {
   DevBuf<unsigned long long> info;  // 8 slots per unit batch, see mih.cu
   unsigned long long* h_info = nullptr;
   int n_batches = 0;
+  int last_need = 1;
   ~MihWorkspace();
 };
 MihPlan mih_plan(int threshold, int need);
 int mih_need_for(uint64_t n, int threshold);
 bool mih_applicable(uint64_t n, int threshold);
+// need: chunks per bucket key, 0 = by the cost model (ws.last_need tells which one ran)
 int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, const MihOut& out,
-                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream);
+                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream, int need = 0);
 // after the stream has been synchronised: pair tests of the last pass and whether it declined (copies ws.info)
 int mih_read_info(MihWorkspace& ws, cudaStream_t stream, unsigned long long* tests, int* declined);
 

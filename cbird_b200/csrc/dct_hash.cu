@@ -1232,6 +1232,7 @@ void cb_hash_tables(float* basis_9x32, int32_t* zigzag81) {
 
 int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                       uint64_t* d_out, void* stream) {
+  CB_API_BEGIN
   int rc = check_geometry(w, h, n, row_stride, frame_stride);
   if (rc != CB_OK) return rc;
   if (n == 0) return CB_OK;
@@ -1243,10 +1244,12 @@ int cb_hash_batch_dev(const uint8_t* d_frames, int64_t n, int w, int h, int64_t 
   if (rc != CB_OK) return rc;
   return hash_frames_device(d_frames, n, w, h, row_stride, frame_stride, d_out, &tl_ws,
                             static_cast<cudaStream_t>(stream));
+  CB_API_END
 }
 
 int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                   uint64_t* out) {
+  CB_API_BEGIN
   int rc = check_geometry(w, h, n, row_stride, frame_stride);
   if (rc != CB_OK) return rc;
   if (n == 0) return CB_OK;
@@ -1284,6 +1287,7 @@ int cb_hash_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_st
     CB_CUDA(cudaStreamSynchronize(ctx.stream));
   }
   return CB_OK;
+  CB_API_END
 }
 
 
@@ -1374,6 +1378,7 @@ extern "C" {
 
 int cb_gray_batch(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride, int64_t frame_stride,
                   int gray_mode, uint8_t* out) {
+  CB_API_BEGIN
   if (n > 0 && !out) {
     set_error("cb_gray_batch: null output");
     return CB_ERR_INVALID;
@@ -1395,10 +1400,12 @@ int cb_gray_batch(const uint8_t* frames, int64_t n, int w, int h, int channels, 
                                                     ctx.stream));
                             return CB_OK;
                           });
+  CB_API_END
 }
 
 int cb_hash_batch_color(const uint8_t* frames, int64_t n, int w, int h, int channels, int64_t row_stride,
                         int64_t frame_stride, int gray_mode, uint64_t* out) {
+  CB_API_BEGIN
   if (channels == 1) return cb_hash_batch(frames, n, w, h, row_stride, frame_stride, out);
   if (n > 0 && !out) {
     set_error("cb_hash_batch_color: null output");
@@ -1417,6 +1424,7 @@ int cb_hash_batch_color(const uint8_t* frames, int64_t n, int w, int h, int chan
                             CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
                             return CB_OK;
                           });
+  CB_API_END
 }
 
 }  // extern "C"
@@ -1425,6 +1433,7 @@ extern "C" {
 
 int cb_autocrop_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride, int range,
                       int32_t* rects) {
+  CB_API_BEGIN
   if (n > 0 && !rects) {
     set_error("cb_autocrop_batch: null output");
     return CB_ERR_INVALID;
@@ -1438,10 +1447,12 @@ int cb_autocrop_batch(const uint8_t* frames, int64_t n, int w, int h, int64_t ro
                               CB_CUDA(cudaMemcpyAsync(rects + 4 * i0, ctx.ws.rects.p, size_t(m) * 16, cudaMemcpyDeviceToHost, ctx.stream));
                               return int(CB_OK);
                             });
+  CB_API_END
 }
 
 int cb_hash_batch_rects(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                         const int32_t* rects, uint64_t* out) {
+  CB_API_BEGIN
   if (n > 0 && (!rects || !out)) {
     set_error("cb_hash_batch_rects: null pointer");
     return CB_ERR_INVALID;
@@ -1464,6 +1475,7 @@ int cb_hash_batch_rects(const uint8_t* frames, int64_t n, int w, int h, int64_t 
                               CB_CUDA(cudaMemcpyAsync(out + i0, ctx.d_out.p, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx.stream));
                               return int(CB_OK);
                             });
+  CB_API_END
 }
 
 // near-frame compression of Media::makeVideoIndex (src/media.cpp:958-1031): frame 0 is always kept and
@@ -1471,6 +1483,7 @@ int cb_hash_batch_rects(const uint8_t* frames, int64_t n, int w, int h, int64_t 
 // >= threshold (which also clears the window); the last frame is always kept.
 int cb_video_compress(const uint64_t* hashes, int64_t n, int threshold, int32_t* out_frames, uint64_t* out_hashes,
                       int64_t* n_out) {
+  CB_API_BEGIN
   if (n < 0 || !n_out || (n && (!hashes || !out_frames || !out_hashes))) {
     set_error("cb_video_compress: invalid argument");
     return CB_ERR_INVALID;
@@ -1509,11 +1522,13 @@ int cb_video_compress(const uint64_t* hashes, int64_t n, int threshold, int32_t*
   }
   *n_out = k;
   return CB_OK;
+  CB_API_END
 }
 
 // Media::makeVideoIndex on a video's decoded luma frames: autocrop(20) -> dctHash64 -> compression
 int cb_make_video_index_alloc(const uint8_t* frames, int64_t n, int w, int h, int64_t row_stride, int64_t frame_stride,
                               int threshold, int32_t** out_frames, uint64_t** out_hashes, int64_t* n_out) {
+  CB_API_BEGIN
   if (!out_frames || !out_hashes || !n_out) {
     set_error("cb_make_video_index_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -1556,6 +1571,7 @@ int cb_make_video_index_alloc(const uint8_t* frames, int64_t n, int w, int h, in
   *out_frames = f;
   *out_hashes = hh;
   return CB_OK;
+  CB_API_END
 }
 
 }  // extern "C"

@@ -392,10 +392,22 @@ struct FindSlot {
   uint64_t hash = 0;
   int threshold = 0;
   int rc = CB_OK;
-  std::atomic<int> state{0};     // 0 pending, 1 done, 2 promoted: the owner leads the next batch
+  std::atomic<int> state{0};     // 0 pending, 1 done, 2 promoted: the owner collects and launches the next batch
   std::atomic<int> sleeping{0};
+  FindSlot* wake[2] = {nullptr, nullptr};  // requests of the same batch this one wakes once it is done (a tree)
   std::vector<cb_hit> hits;      // (needle unused, mediaId, score), unsorted
   char err[160] = "";
+};
+
+constexpr int kFindCtxMax = 8;
+
+struct FindCtx {  // one batch in flight
+  cudaStream_t stream = nullptr;
+  FindOut* h_out = nullptr;
+  FindOut* d_out = nullptr;  // the same memory as the device sees it
+  unsigned long long* d_ctr = nullptr;
+  unsigned long long seq = 0;
+  bool busy = false;
 };
 
 struct FindQueue {
@@ -404,20 +416,19 @@ struct FindQueue {
   std::vector<FindSlot*> free_slots;
   std::vector<std::unique_ptr<FindSlot>> all_slots;
   bool leader_active = false;
-  // GPU side, owned by whoever leads
-  cudaStream_t stream = nullptr;
-  FindOut* h_out = nullptr;
-  FindOut* d_out = nullptr;  // the same memory as the device sees it
-  unsigned long long* d_ctr = nullptr;
-  unsigned long long seq = 0;
+  FindCtx ctx[kFindCtxMax];
+  int n_ctx = 2;       // batches in flight at most (CB_FIND_CTX)
+  int spin_us = 25;    // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
   int device = 0;
   bool ready = false;
   std::atomic<uint64_t> batches{0}, needles{0};
   ~FindQueue() {
     if (ready) cudaSetDevice(device);
-    if (h_out) cudaFreeHost(h_out);
-    if (d_ctr) cudaFree(d_ctr);
-    if (stream) cudaStreamDestroy(stream);
+    for (FindCtx& c : ctx) {
+      if (c.h_out) cudaFreeHost(c.h_out);
+      if (c.d_ctr) cudaFree(c.d_ctr);
+      if (c.stream) cudaStreamDestroy(c.stream);
+    }
   }
 };
 
@@ -547,7 +558,8 @@ struct DctIndex {
     unsigned long long cap = std::max<unsigned long long>(S.d_pairs.cap, guess);
     static const bool no_mih = getenv("CB_NO_MIH") != nullptr;  // measurement / parity aid: brute-force scan only
     bool mih_declined = no_mih;
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    int mih_need = 0;  // by the cost model first; two-chunk keys that meet skewed buckets fall back to one-chunk keys
+    for (int attempt = 0; attempt < 6; ++attempt) {
       int rc = S.d_pairs.reserve(cap);
       if (rc != CB_OK) return rc;
       cap = S.d_pairs.cap;
@@ -558,7 +570,8 @@ struct DctIndex {
         // small thresholds: multi-index self-join (same hit set from a fraction of the pair tests); declined
         // when the buckets are so skewed that it would cost more than half of the symmetric brute-force scan
         MihOut out{0, S.d_pairs.p, cap, S.d_counts.p, nullptr, 0};
-        rc = scan64_self_mih(S.d_hashes.p, n_rows, threshold, 0, 1, out, S.mih, (unsigned long long)n_rows * n_rows / 4, stream);
+        rc = scan64_self_mih(S.d_hashes.p, n_rows, threshold, 0, 1, out, S.mih, (unsigned long long)n_rows * n_rows / 4, stream,
+                             mih_need);
         if (rc != CB_OK) return rc;
         used_mih = true;
       } else if (symmetric_self) {
@@ -588,7 +601,8 @@ struct DctIndex {
         rc = mih_read_info(S.mih, stream, &tests, &declined);
         if (rc != CB_OK) return rc;
         if (declined) {
-          mih_declined = true;
+          if (S.mih.last_need == 2) mih_need = 1;
+          else mih_declined = true;
           continue;
         }
         counters().comparisons += tests;
@@ -615,7 +629,7 @@ struct DctIndex {
       }
       if (S.h_counts[0] <= cap) break;
       cap = S.h_counts[0] + S.h_counts[0] / 8 + 1024;  // overflow: exact size is known now, run again
-      if (attempt == 3) {
+      if (attempt == 5) {
         set_error("scan64: hit list overflow persisted");
         return CB_ERR_CUDA;
       }
@@ -684,17 +698,25 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
   unsigned long long* keys = nullptr;
   const unsigned post_blocks = unsigned((size_t(n_rows) + 1 + 255) / 256);
 
+  // how the pair tests are done: two-chunk bucket keys that meet skewed buckets fall back to one-chunk keys, those to
+  // the brute-force scan. The buckets are dealt to the ranks by the plan, so every rank must take the same path: with
+  // several ranks a decline is agreed on in the count exchange below and all of them repeat phase 1.
+  static const bool no_mih = getenv("CB_NO_MIH") != nullptr;
+  bool use_mih = !no_mih && mih_applicable(n, J.scan_thresh);
+  int mih_need = 0;  // 0 = by the cost model
+  int declined_local = 0;
+
   // ---- 1. this rank's share of the pair tests -> keys of the hits ----
   auto phase1 = [&]() -> int {
     int rc;
+    declined_local = 0;
+    n_keys = 0;
     CB_CUDA(cudaMemsetAsync(S.d_counts.p, 0, 64 * sizeof(unsigned long long), st));
     if (!n || J.scan_thresh <= 0) return CB_OK;
-    static const bool no_mih = getenv("CB_NO_MIH") != nullptr;
-    bool use_mih = !no_mih && mih_applicable(n, J.scan_thresh);
     unsigned long long guess = 3ull * n / world + (1ull << 16);
     unsigned long long cap = std::max<unsigned long long>(S.d_keys.cap, guess);
     for (int attempt = 0;; ++attempt) {
-      if (attempt == 5) {
+      if (attempt == 7) {
         set_error("similar: hit list overflow persisted");
         return CB_ERR_CUDA;
       }
@@ -705,14 +727,19 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
         MihOut out{1, S.d_keys.p, cap, S.d_counts.p, S.d_ids.p, J.L.needle_shift};
         // declined when the buckets are so skewed that the pass would cost more than half the symmetric scan
         rc = scan64_self_mih(S.d_hashes.p, n, J.scan_thresh, uint32_t(rank), uint32_t(world), out, S.mih,
-                             (unsigned long long)n * n / 4 / world, st);
+                             (unsigned long long)n * n / 4 / world, st, mih_need);
         if (rc != CB_OK) return rc;
         CB_CUDA(cudaMemcpyAsync(S.h_counts, S.d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         unsigned long long tests = 0;
         int declined = 0;
         if ((rc = mih_read_info(S.mih, st, &tests, &declined)) != CB_OK) return rc;  // synchronises
         if (declined) {
-          use_mih = false;
+          if (world > 1) {  // agreed on with the other ranks before anybody retries
+            declined_local = 1;
+            return CB_OK;
+          }
+          if (S.mih.last_need == 2) mih_need = 1;
+          else use_mih = false;
           continue;
         }
         J.issued[local_index] = tests;
@@ -755,27 +782,40 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
     return CB_OK;
   };
 
-  // ---- 2. every key to the rank that owns its needle row; 3. sort; 4. post step counts ----
+  // ---- 2a. (several ranks) how many keys go where, and whether any rank declined its bucket pass ----
+  constexpr int kGw = kMaxRanks + 1;  // per-rank vector: keys per destination rank, then the declined flag
+  int any_declined = 0;
+  auto exchange_counts = [&]() -> int {
+    int rc;
+    any_declined = 0;
+    const uint32_t per = I.rows_per_rank();
+    unsigned long long* dest_count = S.d_counts.p + 8;  // [17], zeroed in phase 1
+    unsigned long long* gathered = S.d_counts.p + 64;   // [world][17]
+    if (n_keys && !declined_local) {
+      keys_dest_count<<<unsigned((n_keys + 255) / 256), 256, 0, st>>>(S.d_keys.p, n_keys, J.L.needle_shift, per, world, dest_count);
+      CB_CUDA(cudaGetLastError());
+    }
+    S.h_counts[8] = (unsigned long long)declined_local;
+    CB_CUDA(cudaMemcpyAsync(dest_count + kMaxRanks, S.h_counts + 8, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    if ((rc = comm_all_gather(S.R, dest_count, gathered, kGw * sizeof(unsigned long long), st)) != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(S.h_counts + 64, gathered, size_t(world) * kGw * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < world; ++q)
+      if (S.h_counts[64 + q * kGw + kMaxRanks]) any_declined = 1;
+    return CB_OK;
+  };
+
+  // ---- 2b. every key to the rank that owns its needle row; 3. sort; 4. post step counts ----
   auto phase2 = [&]() -> int {
     int rc;
     keys = S.d_keys.p;
     if (world > 1) {
       const uint32_t per = I.rows_per_rank();
-      unsigned long long* dest_count = S.d_counts.p + 8;  // [16], zeroed in phase 1
-      unsigned long long* cursor = S.d_counts.p + 24;     // [16]
-      unsigned long long* gathered = S.d_counts.p + 64;   // [world][16]
-      if (n_keys) {
-        keys_dest_count<<<unsigned((n_keys + 255) / 256), 256, 0, st>>>(S.d_keys.p, n_keys, J.L.needle_shift, per, world, dest_count);
-        CB_CUDA(cudaGetLastError());
-      }
-      if ((rc = comm_all_gather(S.R, dest_count, gathered, kMaxRanks * sizeof(unsigned long long), st)) != CB_OK) return rc;
-      CB_CUDA(cudaMemcpyAsync(S.h_counts + 64, gathered, size_t(world) * kMaxRanks * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, st));
-      CB_CUDA(cudaStreamSynchronize(st));
-      const unsigned long long* G = S.h_counts + 64;  // G[src * 16 + dst]
+      unsigned long long* cursor = S.d_counts.p + 40;  // [16]
+      const unsigned long long* G = S.h_counts + 64;   // G[src * 17 + dst], from exchange_counts
       unsigned long long send_off[kMaxRanks + 1] = {0}, recv_off[kMaxRanks + 1] = {0};
-      for (int d = 0; d < world; ++d) send_off[d + 1] = send_off[d] + G[rank * kMaxRanks + d];
-      for (int q = 0; q < world; ++q) recv_off[q + 1] = recv_off[q] + G[q * kMaxRanks + rank];
+      for (int d = 0; d < world; ++d) send_off[d + 1] = send_off[d] + G[rank * kGw + d];
+      for (int q = 0; q < world; ++q) recv_off[q + 1] = recv_off[q] + G[q * kGw + rank];
       if (send_off[world] != n_keys) {
         set_error("similar: destination counts do not add up");
         return CB_ERR_CUDA;
@@ -859,10 +899,26 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
 
   // the shard threads of one call move in lockstep; a failure is published before the next barrier so that
   // no local rank waits for a collective that another one will never enter
-  int rc = phase1();
-  if (rc != CB_OK) J.failed.store(rc);
-  J.bar.wait();
-  if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
+  int rc = CB_OK;
+  for (int round = 0;; ++round) {
+    rc = phase1();
+    if (rc != CB_OK) J.failed.store(rc);
+    J.bar.wait();
+    if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
+    if (world == 1) break;
+    rc = exchange_counts();
+    if (rc != CB_OK) J.failed.store(rc);
+    J.bar.wait();
+    if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
+    if (!any_declined) break;
+    if (round >= 2) {
+      set_error("similar: the ranks could not agree on a scan path");
+      return CB_ERR_CUDA;
+    }
+    // every rank ran the same plan, so every rank takes the same step down
+    if (use_mih && S.mih.last_need == 2 && mih_need != 1) mih_need = 1;
+    else use_mih = false;
+  }
   rc = phase2();
   if (rc != CB_OK) J.failed.store(rc);
   if (!J.want_lists) return rc;
@@ -945,19 +1001,29 @@ int fq_init(DctIndex& I) {
   if (Q.ready) return CB_OK;
   DctShard& S = I.s0();
   Q.device = S.R.device;
+  if (const char* e = getenv("CB_FIND_CTX")) Q.n_ctx = std::max(1, std::min(kFindCtxMax, atoi(e)));
+  if (const char* e = getenv("CB_FIND_SPIN_US")) Q.spin_us = std::max(0, atoi(e));
   CB_CUDA(cudaSetDevice(Q.device));
-  CB_CUDA(cudaStreamCreateWithFlags(&Q.stream, cudaStreamNonBlocking));
-  CB_CUDA(cudaHostAlloc(&Q.h_out, sizeof(FindOut), cudaHostAllocMapped | cudaHostAllocPortable));
-  memset(Q.h_out, 0, sizeof(FindOut));
-  CB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&Q.d_out), Q.h_out, 0));
-  CB_CUDA(cudaMalloc(&Q.d_ctr, 2 * sizeof(unsigned long long)));
-  CB_CUDA(cudaMemset(Q.d_ctr, 0, 2 * sizeof(unsigned long long)));
+  for (int i = 0; i < Q.n_ctx; ++i) {
+    FindCtx& c = Q.ctx[i];
+    CB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaHostAlloc(&c.h_out, sizeof(FindOut), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c.h_out, 0, sizeof(FindOut));
+    CB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c.d_out), c.h_out, 0));
+    CB_CUDA(cudaMalloc(&c.d_ctr, 2 * sizeof(unsigned long long)));
+    CB_CUDA(cudaMemset(c.d_ctr, 0, 2 * sizeof(unsigned long long)));
+  }
   Q.ready = true;
   return CB_OK;
 }
 
-// one launch for up to kFindBatch requests of the same threshold; the caller holds leadership
-void fq_run_batch(DctIndex& I, FindSlot** batch, int nb, int threshold) {
+void fq_wake(FindSlot* s) {
+  if (s && s->sleeping.load()) futex_wake(&s->state);
+}
+
+// one launch for up to kFindBatch requests of the same threshold on context c; the caller shepherds the batch:
+// launches, waits for the kernel's completion word, hands the hits out and wakes the owners
+void fq_run_batch(DctIndex& I, FindCtx& c, FindSlot** batch, int nb, int threshold) {
   FindQueue& Q = I.fq;
   int rc = CB_OK;
   {
@@ -975,22 +1041,21 @@ void fq_run_batch(DctIndex& I, FindSlot** batch, int nb, int threshold) {
       for (int i = 0; i < nb; ++i) N.h[i] = batch[i]->hash;
       const int T = std::min(threshold, 65);
       const unsigned grid = (n + kFindRows - 1) / kFindRows;
-      const unsigned long long seq = ++Q.seq;
-      FindOut* d_out = Q.d_out;
-      if (T <= 5) find_small_kernel<2><<<grid, 256, 0, Q.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, d_out, Q.d_ctr, seq);
-      else if (T <= 13) find_small_kernel<1><<<grid, 256, 0, Q.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, d_out, Q.d_ctr, seq);
-      else find_small_kernel<0><<<grid, 256, 0, Q.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, d_out, Q.d_ctr, seq);
+      const unsigned long long seq = ++c.seq;
+      if (T <= 5) find_small_kernel<2><<<grid, 256, 0, c.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, c.d_out, c.d_ctr, seq);
+      else if (T <= 13) find_small_kernel<1><<<grid, 256, 0, c.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, c.d_out, c.d_ctr, seq);
+      else find_small_kernel<0><<<grid, 256, 0, c.stream>>>(S.d_hashes.p, S.d_ids.p, n, N, nb, T, c.d_out, c.d_ctr, seq);
       CB_CUDA(cudaGetLastError());
       counters().launches += 1;
       counters().comparisons += uint64_t(n) * uint64_t(nb);
       // wait for the kernel's own completion word: no stream synchronisation, no copy
-      volatile unsigned long long* done = &Q.h_out->done_seq;
+      volatile unsigned long long* done = &c.h_out->done_seq;
       const auto t0 = std::chrono::steady_clock::now();
       for (unsigned spin = 0; *done != seq; ++spin) {
         _mm_pause();
         if ((spin & 1023) == 1023) {
-          if (cudaStreamQuery(Q.stream) != cudaErrorNotReady && *done != seq) {  // finished (or failed) without publishing
-            cudaError_t e = cudaStreamSynchronize(Q.stream);
+          if (cudaStreamQuery(c.stream) != cudaErrorNotReady && *done != seq) {  // finished (or failed) without publishing
+            cudaError_t e = cudaStreamSynchronize(c.stream);
             if (e != cudaSuccess) return cuda_fail(e, "find queue kernel", __FILE__, __LINE__);
             if (*done != seq) {
               set_error("find queue: kernel finished without publishing its result");
@@ -1008,13 +1073,13 @@ void fq_run_batch(DctIndex& I, FindSlot** batch, int nb, int threshold) {
     };
     rc = launch();
     if (rc == CB_OK && n && threshold > 0) {
-      const unsigned long long c = Q.h_out->count;
-      if (c > kFindOutCap) {
-        rc = 1;  // too many hits for the mapped buffer: each request goes through the general path below
+      const unsigned long long cnt = c.h_out->count;
+      if (cnt > kFindOutCap) {
+        rc = 1;  // too many hits for the mapped buffer: the batch goes through the general path below
       } else {
-        counters().hits += c;
-        for (unsigned long long i = 0; i < c; ++i) {
-          const cb_pair& h = Q.h_out->hits[i];
+        counters().hits += cnt;
+        for (unsigned long long i = 0; i < cnt; ++i) {
+          const cb_pair& h = c.h_out->hits[i];
           if (h.a < uint32_t(nb)) batch[h.a]->hits.push_back(cb_hit{0, h.pad_, int32_t(h.dist)});
         }
       }
@@ -1029,15 +1094,24 @@ void fq_run_batch(DctIndex& I, FindSlot** batch, int nb, int threshold) {
         for (const cb_hit& h : all) batch[h.needle]->hits.push_back(h);
     }
   }
+  {
+    std::lock_guard<std::mutex> lock(Q.mu);
+    c.busy = false;  // the next batch may use this context while the owners are being woken
+  }
   Q.batches.fetch_add(1, std::memory_order_relaxed);
   Q.needles.fetch_add(uint64_t(nb), std::memory_order_relaxed);
+  // done: states are published last slot first, so that whoever sees its own request done also sees the requests
+  // it has to wake done; sleepers are woken along a binary tree (request i wakes 2i + 1 and 2i + 2), which keeps the
+  // wake-up of a large batch off the shepherd's critical path
   for (int i = 0; i < nb; ++i) {
     FindSlot* s = batch[i];
     s->rc = rc;
     if (rc != CB_OK) snprintf(s->err, sizeof(s->err), "%s", cb_last_error());
-    s->state.store(1);
-    if (s->sleeping.load()) futex_wake(&s->state);
+    s->wake[0] = 2 * i + 1 < nb ? batch[2 * i + 1] : nullptr;
+    s->wake[1] = 2 * i + 2 < nb ? batch[2 * i + 2] : nullptr;
   }
+  for (int i = nb - 1; i >= 0; --i) batch[i]->state.store(1);
+  if (nb) fq_wake(batch[0]);
 }
 
 int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit>& out) {
@@ -1061,6 +1135,7 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
     me->threshold = threshold;
     me->rc = CB_OK;
     me->hits.clear();
+    me->wake[0] = me->wake[1] = nullptr;
     me->sleeping.store(0);
     me->state.store(0);
     Q.waiting.push_back(me);
@@ -1071,12 +1146,12 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
   }
   for (;;) {
     if (!lead) {
-      // wait for a leader to serve (1) or promote (2) this request: spin for about the time of a launch, then sleep
+      // wait for a shepherd to serve (1) or promote (2) this request: spin for about the time of a launch, then sleep
       const auto t0 = std::chrono::steady_clock::now();
       int st = 0;
       for (unsigned spin = 0; (st = me->state.load()) == 0; ++spin) {
         _mm_pause();
-        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(60)) {
+        if ((spin & 15) == 15 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(Q.spin_us)) {
           me->sleeping.store(1);
           while ((st = me->state.load()) == 0) futex_wait(&me->state, 0);
           me->sleeping.store(0);
@@ -1087,11 +1162,21 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
       me->state.store(0);  // promoted: still queued, now leading
       lead = true;
     }
-    // leader: one batch of same-threshold requests from the head of the queue
+    // leader: take a free context (at most n_ctx batches are in flight; while they all are, requests pile up and
+    // the next batch gets larger), collect the same-threshold requests at the head of the queue, pass the lead on
     FindSlot* batch[kFindBatch];
     int nb = 0, thr = 0;
-    {
-      std::lock_guard<std::mutex> lock(Q.mu);
+    FindCtx* c = nullptr;
+    for (unsigned spin = 0; !c; ++spin) {
+      std::unique_lock<std::mutex> lock(Q.mu);
+      for (int i = 0; i < Q.n_ctx && !c; ++i)
+        if (!Q.ctx[i].busy) c = &Q.ctx[i];
+      if (!c) {
+        lock.unlock();
+        _mm_pause();
+        if ((spin & 255) == 255) std::this_thread::yield();
+        continue;
+      }
       if (!Q.waiting.empty()) {
         thr = Q.waiting.front()->threshold;
         for (auto it = Q.waiting.begin(); it != Q.waiting.end() && nb < kFindBatch;) {
@@ -1103,29 +1188,25 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
           }
         }
       }
-    }
-    bool mine_done = me->state.load() == 1;
-    if (nb) {
-      bool has_me = false;
-      for (int i = 0; i < nb; ++i) has_me = has_me || batch[i] == me;
-      fq_run_batch(I, batch, nb, thr);
-      mine_done = mine_done || has_me;
-    }
-    {
-      std::lock_guard<std::mutex> lock(Q.mu);
+      if (nb) c->busy = true;
       if (Q.waiting.empty()) {
         Q.leader_active = false;
-        lead = false;
-      } else if (mine_done) {  // hand the lead to the oldest waiting request's owner
+      } else {  // the oldest request left behind leads the next batch
         FindSlot* next = Q.waiting.front();
         next->state.store(2);
-        if (next->sleeping.load()) futex_wake(&next->state);
-        lead = false;
+        fq_wake(next);
       }
+      lead = false;
     }
-    if (mine_done && !lead) break;
-    if (!lead && !mine_done) continue;  // queue emptied by someone else while mine is pending: cannot happen, wait again
+    bool has_me = false;
+    for (int i = 0; i < nb; ++i) has_me = has_me || batch[i] == me;
+    if (nb) fq_run_batch(I, *c, batch, nb, thr);
+    if (has_me) break;
+    // this request's threshold differs from the batch just served: it is still queued, wait for its turn
   }
+  // this request is done: wake the requests of the batch that hang below it
+  fq_wake(me->wake[0]);
+  fq_wake(me->wake[1]);
   int rc = me->rc;
   if (rc != CB_OK) set_error("%s", me->err);
   out.swap(me->hits);

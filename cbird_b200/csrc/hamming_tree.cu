@@ -246,6 +246,7 @@ void cb_hamming_tree_destroy(cb_hamming_tree* t) {
 }
 
 int cb_hamming_tree_insert(cb_hamming_tree* t, const uint32_t* indices, const uint64_t* hashes, int64_t n) {
+  CB_API_BEGIN
   if (!t || n < 0 || (n && (!indices || !hashes))) {
     set_error("cb_hamming_tree_insert: invalid argument");
     return CB_ERR_INVALID;
@@ -260,9 +261,11 @@ int cb_hamming_tree_insert(cb_hamming_tree* t, const uint32_t* indices, const ui
   T.hash.insert(T.hash.end(), hashes, hashes + n);
   T.built = false;
   return CB_OK;
+  CB_API_END
 }
 
 int cb_hamming_tree_remove(cb_hamming_tree* t, const uint32_t* indices, int64_t n) {
+  CB_API_BEGIN
   if (!t || n < 0 || (n && !indices)) {
     set_error("cb_hamming_tree_remove: invalid argument");
     return CB_ERR_INVALID;
@@ -275,9 +278,11 @@ int cb_hamming_tree_remove(cb_hamming_tree* t, const uint32_t* indices, int64_t 
   for (auto& ix : T.s_index)
     if (gone.count(ix)) ix = 0;
   return CB_OK;
+  CB_API_END
 }
 
 int cb_hamming_tree_stats(cb_hamming_tree* t, int32_t* num_nodes, int32_t* max_height, int64_t* num_values) {
+  CB_API_BEGIN
   if (!t) return CB_ERR_INVALID;
   HammingTree& T = t->impl;
   std::lock_guard<std::mutex> lock(T.mu);
@@ -287,11 +292,13 @@ int cb_hamming_tree_stats(cb_hamming_tree* t, int32_t* num_nodes, int32_t* max_h
   if (max_height) *max_height = T.max_height;
   if (num_values) *num_values = int64_t(T.hash.size());
   return CB_OK;
+  CB_API_END
 }
 
 // search(): every value of the needle's leaf with distance < threshold, sorted by distance (:99-108)
 int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needles, int64_t n_needles, int threshold,
                                        cb_tree_match** out, int64_t* n_out) {
+  CB_API_BEGIN
   if (!t || !out || !n_out || n_needles < 0 || (n_needles && !needles)) {
     set_error("cb_hamming_tree_search_batch_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -318,6 +325,7 @@ int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needl
   }
   if (!m.empty()) memcpy(*out, m.data(), m.size() * sizeof(cb_tree_match));
   return CB_OK;
+  CB_API_END
 }
 
 // DctFeaturesIndex::find (src/dctfeaturesindex.cpp:260-358) on top of the tree: every needle hash votes
@@ -327,6 +335,7 @@ int cb_hamming_tree_search_batch_alloc(cb_hamming_tree* t, const uint64_t* needl
 // (distance, index, hash).
 int cb_hamming_tree_find_votes(cb_hamming_tree* t, const uint64_t* needle_hashes, int64_t n, uint32_t needle_id,
                                int threshold, cb_match* out, int64_t cap, int64_t* n_out) {
+  CB_API_BEGIN
   if (!t || !n_out || n < 0 || (n && !needle_hashes)) {
     set_error("cb_hamming_tree_find_votes: invalid argument");
     return CB_ERR_INVALID;
@@ -388,11 +397,13 @@ int cb_hamming_tree_find_votes(cb_hamming_tree* t, const uint64_t* needle_hashes
   }
   *n_out = w;
   return w > cap ? CB_ERR_CAPACITY : CB_OK;
+  CB_API_END
 }
 
 // cache file v2 (:156-200, :472-521): "cbird hamming tree:2:<sizeof index>:8:65536\n" + pre-order nodes:
 // bool isLeaf; inner: int bit, set-child ("left"), clear-child ("right"); leaf: u32 count, index[count], hash[count]
 int cb_hamming_tree_write(cb_hamming_tree* t, const char* path) {
+  CB_API_BEGIN
   if (!t || !path) return CB_ERR_INVALID;
   HammingTree& T = t->impl;
   std::lock_guard<std::mutex> lock(T.mu);
@@ -420,6 +431,7 @@ int cb_hamming_tree_write(cb_hamming_tree* t, const char* path) {
   }
   fclose(f);
   return CB_OK;
+  CB_API_END
 }
 
 static bool read_node(FILE* f, HammingTree& T, int depth) {
@@ -455,6 +467,7 @@ static bool read_node(FILE* f, HammingTree& T, int depth) {
 }
 
 int cb_hamming_tree_read(cb_hamming_tree* t, const char* path) {
+  CB_API_BEGIN
   if (!t || !path) return CB_ERR_INVALID;
   HammingTree& T = t->impl;
   std::lock_guard<std::mutex> lock(T.mu);
@@ -502,6 +515,7 @@ int cb_hamming_tree_read(cb_hamming_tree* t, const char* path) {
   }
   T.built = true;
   return CB_OK;
+  CB_API_END
 }
 
 }  // extern "C"

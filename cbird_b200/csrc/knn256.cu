@@ -331,6 +331,7 @@ static int check_media_args(const char* fn, const void* ix, const uint32_t* ids,
 
 int cb_orb_index_load(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
                       int64_t n_media) {
+  CB_API_BEGIN
   int rc = check_media_args("cb_orb_index_load", ix, media_ids, row_offsets, desc, n_media);
   if (rc != CB_OK) return rc;
   OrbIndex& I = ix->impl;
@@ -347,10 +348,12 @@ int cb_orb_index_load(cb_orb_index* ix, const uint32_t* media_ids, const int64_t
   }
   I.loaded = true;
   return I.sync_to_device();
+  CB_API_END
 }
 
 int cb_orb_index_add(cb_orb_index* ix, const uint32_t* media_ids, const int64_t* row_offsets, const uint8_t* desc,
                      int64_t n_media) {
+  CB_API_BEGIN
   int rc = check_media_args("cb_orb_index_add", ix, media_ids, row_offsets, desc, n_media);
   if (rc != CB_OK) return rc;
   OrbIndex& I = ix->impl;
@@ -358,9 +361,11 @@ int cb_orb_index_add(cb_orb_index* ix, const uint32_t* media_ids, const int64_t*
   I.append(media_ids, row_offsets, desc, n_media, false);  // :122-152
   I.loaded = true;
   return I.sync_to_device();
+  CB_API_END
 }
 
 int cb_orb_index_remove(cb_orb_index* ix, const int32_t* ids, int64_t n) {
+  CB_API_BEGIN
   if (!ix || n < 0 || (n && !ids)) {
     set_error("cb_orb_index_remove: invalid argument");
     return CB_ERR_INVALID;
@@ -374,6 +379,7 @@ int cb_orb_index_remove(cb_orb_index* ix, const int32_t* ids, int64_t n) {
     if (b != I.first_row.end() && *b == it->second.first) I.media[size_t(b - I.first_row.begin())] = 0;
   }
   return CB_OK;
+  CB_API_END
 }
 
 /* isLoaded(): `_index != nullptr`, i.e. a search structure exists: loaded and at least one row (:102, :320-323) */
@@ -384,6 +390,7 @@ size_t cb_orb_index_memory_usage(const cb_orb_index* ix) {                      
 }
 
 int cb_orb_index_descriptors(const cb_orb_index* ix, uint32_t media_id, uint8_t* out, int64_t cap_rows, int64_t* n_rows) {
+  CB_API_BEGIN
   if (!ix || !n_rows) return CB_ERR_INVALID;
   const OrbIndex& I = ix->impl;
   *n_rows = 0;
@@ -395,9 +402,11 @@ int cb_orb_index_descriptors(const cb_orb_index* ix, uint32_t media_id, uint8_t*
     memcpy(out, I.desc.data() + size_t(it->second.first) * 32, size_t(it->second.second) * 32);
   }
   return CB_OK;
+  CB_API_END
 }
 
 cb_orb_index* cb_orb_index_slice(const cb_orb_index* ix, const uint32_t* ids, int64_t n) {
+  try {
   if (!ix || n < 0 || (n && !ids)) return nullptr;
   cb_orb_index* out = new (std::nothrow) cb_orb_index;
   if (!out) return nullptr;
@@ -419,10 +428,15 @@ cb_orb_index* cb_orb_index_slice(const cb_orb_index* ix, const uint32_t* ids, in
     return nullptr;
   }
   return out;
+  } catch (...) {
+    set_error("cb_orb_index_slice: out of memory or internal error");
+    return nullptr;
+  }
 }
 
 int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, int k, int threshold, cb_pair** out,
                            int64_t* n_out) {
+  CB_API_BEGIN
   if (!ix || !out || !n_out || n_rows < 0 || (n_rows && !desc)) {
     set_error("cb_orb_index_knn_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -441,10 +455,12 @@ int cb_orb_index_knn_alloc(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows
   }
   if (!hits.empty()) memcpy(*out, hits.data(), hits.size() * sizeof(cb_pair));
   return CB_OK;
+  CB_API_END
 }
 
 int cb_orb_radius_match_alloc(const uint8_t* train, int64_t n_train, const uint8_t* query, int64_t n_query,
                               int max_distance, cb_pair** out, int64_t* n_out) {
+  CB_API_BEGIN
   if (!out || !n_out || n_train < 0 || n_query < 0 || (n_train && !train) || (n_query && !query) ||
       n_train > 0xffffffffll || n_query > 0xffffffffll) {
     set_error("cb_orb_radius_match_alloc: invalid argument");
@@ -468,10 +484,12 @@ int cb_orb_radius_match_alloc(const uint8_t* train, int64_t n_train, const uint8
   }
   if (!hits.empty()) memcpy(*out, hits.data(), hits.size() * sizeof(cb_pair));
   return CB_OK;
+  CB_API_END
 }
 
 int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uint32_t needle_id, const cb_params* p,
                       cb_match* out, int64_t cap, int64_t* n_out) {
+  CB_API_BEGIN
   if (!ix || !p || !n_out || n_rows < 0) {
     set_error("cb_orb_index_find: invalid argument");
     return CB_ERR_INVALID;
@@ -513,6 +531,7 @@ int cb_orb_index_find(cb_orb_index* ix, const uint8_t* desc, int64_t n_rows, uin
   }
   *n_out = k;
   return k > cap ? CB_ERR_CAPACITY : CB_OK;
+  CB_API_END
 }
 
 
@@ -548,6 +567,7 @@ bool read_all(const std::string& path, std::vector<uint8_t>& out) {
 }  // namespace
 
 int cb_orb_index_save_cache(cb_orb_index* ix, const char* cache_dir) {
+  CB_API_BEGIN
   if (!ix || !cache_dir) {
     set_error("cb_orb_index_save_cache: invalid argument");
     return CB_ERR_INVALID;
@@ -578,9 +598,11 @@ int cb_orb_index_save_cache(cb_orb_index* ix, const char* cache_dir) {
     return CB_ERR_INVALID;
   }
   return CB_OK;
+  CB_API_END
 }
 
 int cb_orb_index_load_cache(cb_orb_index* ix, const char* cache_dir) {
+  CB_API_BEGIN
   if (!ix || !cache_dir) {
     set_error("cb_orb_index_load_cache: invalid argument");
     return CB_ERR_INVALID;
@@ -627,6 +649,7 @@ int cb_orb_index_load_cache(cb_orb_index* ix, const char* cache_dir) {
   }
   I.loaded = true;
   return I.sync_to_device();
+  CB_API_END
 }
 
 }  // extern "C"

@@ -461,31 +461,7 @@ __global__ void __launch_bounds__(kBkThreads, 3) mih_bucket_kernel(const BucketA
 // bucket), OR-fold pre-filter, exact re-test, same first-unit rule. Runs are short, so neighbouring lanes
 // read the same few cache lines. Hits are staged per CTA.
 constexpr int kWalkThreads = 256, kWalkStage = 512;
-
-// pair tests of the batch: every run start adds len * (len - 1) / 2 (binary search for the run's end)
-__global__ void mih_run_tests_kernel(const uint32_t* __restrict__ key, uint32_t m, unsigned long long* __restrict__ info) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long tests = 0;
-  if (j < m && (j == 0 || key[j - 1] != key[j])) {
-    const uint32_t k = key[j];
-    uint32_t lo = j + 1, hi = m;
-    while (lo < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (key[mid] <= k) lo = mid + 1; else hi = mid;
-    }
-    const unsigned long long len = lo - j;
-    tests = len * (len - 1) / 2;
-  }
-  __shared__ unsigned long long red[8];
-  for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tests;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
-    for (int w = 0; w < int(blockDim.x >> 5); ++w) t += red[w];
-    if (t) atomicAdd(info + kTests, t);
-  }
-}
+constexpr uint32_t kWalkCap = 4096;  // a row walks at most this far: longer runs mean skewed buckets, the pass is declined
 
 struct WalkArgs {
   const uint64_t* sorted;
@@ -504,10 +480,7 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
   __shared__ uint4 stage[kWalkStage];
   __shared__ unsigned n_staged;
   __shared__ unsigned long long g_base;
-  if (A.max_tests && A.info[kTests] > A.max_tests) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.info[kDeclined] = 1;
-    return;
-  }
+  if (A.max_tests && A.info[kDeclined]) return;  // an earlier CTA met a run too long to walk
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.plan);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
@@ -516,6 +489,7 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
   }
   __syncthreads();
   const uint32_t j = blockIdx.x * kWalkThreads + threadIdx.x;
+  unsigned long long walked = 0;
   if (j < A.m) {
     const uint32_t k = A.key[j];
     const uint64_t a = A.sorted[j];
@@ -524,6 +498,11 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
     const int c1 = plan.u_c1[unit], c2 = plan.u_c2[unit];
     const int T = A.threshold;
     for (uint32_t q = j + 1; q < A.m && A.key[q] == k; ++q) {
+      if (A.max_tests && q - j > kWalkCap) {  // skewed buckets: the caller falls back to the one-chunk keys
+        A.info[kDeclined] = 1;
+        break;
+      }
+      ++walked;
       const uint64_t b = A.sorted[q];
       const uint32_t xlo = alo ^ uint32_t(b), xhi = ahi ^ uint32_t(b >> 32);
       if (__popc(xlo | xhi) >= T) continue;
@@ -559,6 +538,8 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
       }
     }
   }
+  for (int off = 16; off; off >>= 1) walked += __shfl_down_sync(0xffffffffu, walked, off);
+  if ((threadIdx.x & 31) == 0 && walked) atomicAdd(A.info + kTests, walked);
   __syncthreads();
   // flush: two records per staged pair in mode 0; in mode 1 rows without id drop out, so count first
   const unsigned n = min(n_staged, unsigned(kWalkStage));
@@ -642,11 +623,13 @@ int bucket_variant_for(const MihPlan& plan, int threshold) {
   if (g_forced_bucket_variant >= 1 && g_forced_bucket_variant <= 3) return g_forced_bucket_variant;
   static const int env = getenv("CB_MIH_VARIANT") ? atoi(getenv("CB_MIH_VARIANT")) : 0;
   if (env >= 1 && env <= 3) return env;
-  // rows of a bucket agree on the unit's chunk bits, so the folds see fewer random bits than in the dense scan:
-  // the AND of two OR-folds keeps the false-positive rate of a warp step at a few percent up to T = 5
-  // (tools/mih_bench.py measures all three); above that only the plain OR-fold stays selective
+  // rows of a bucket agree on the unit's chunk bits, so the folds see fewer random bits than in the dense scan.
+  // Measured (tools/mih_bench.py, 10^7 rows, T = 5; profiles/mih_bench_r02.jsonl): OR-fold 11.6 ms = 0.91 of the POPC
+  // pipe; AND of two OR-folds 12.1 ms (2.5 LOP3 per pair: the ALU pipe binds instead); AND-fold of two rows 72 ms
+  // (half of its warp steps fall into the exact re-test)
   (void)plan;
-  return threshold <= 6 ? 3 : 1;
+  (void)threshold;
+  return 1;
 }
 
 }  // namespace
@@ -729,14 +712,15 @@ MihWorkspace::~MihWorkspace() {
 // reads that with mih_read_info after its own synchronisation, discards the list and runs the brute-force scan.
 // No host synchronisation in here for n_parts == 1.
 int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, const MihOut& out,
-                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream) {
+                    MihWorkspace& ws, unsigned long long max_tests, cudaStream_t stream, int need) {
   if (n == 0 || threshold <= 0) return CB_OK;
   if (threshold > kMihMaxThreshold || n > (1u << 30) || n_parts == 0 || part >= n_parts) {
     set_error("scan64_self_mih: threshold %d / %u rows / part %u of %u outside the supported range", threshold, n, part,
               n_parts);
     return CB_ERR_UNSUPPORTED;
   }
-  const MihPlan plan = mih_plan(threshold, mih_need_for(n, threshold));
+  const MihPlan plan = mih_plan(threshold, need == 1 || need == 2 ? need : mih_need_for(n, threshold));
+  ws.last_need = plan.need;
   // units are processed in batches that keep the sort below 2^29 items
   int per_batch = std::max<int>(1, int((1ull << 29) / n));
   per_batch = std::min(per_batch, plan.units);
@@ -744,7 +728,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   int rc;
   // bucket tables exist only for need 1 (need 2 walks the runs of the sorted keys)
   const uint32_t n_buckets_max = plan.need == 1 ? uint32_t(per_batch) << plan.key_shift : 0u;
-  const uint32_t n_blocks_bound_max = plan.need == 1 ? uint32_t(total / kBlk) + n_buckets_max / 2 + 2 : 0u;
+  const uint32_t n_blocks_bound_max = plan.need == 1 ? uint32_t(total / kBlk) + n_buckets_max + 2 : 0u;
   if ((rc = ws.key.reserve(total)) != CB_OK || (rc = ws.key2.reserve(total)) != CB_OK || (rc = ws.val.reserve(total)) != CB_OK ||
       (rc = ws.val2.reserve(total)) != CB_OK || (rc = ws.sorted.reserve(total + 2)) != CB_OK ||
       (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK || (rc = ws.nblk.reserve(n_buckets_max + 2)) != CB_OK ||
@@ -792,10 +776,6 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
     mih_gather_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_hashes, ws.val2.p, nullptr, m, ws.sorted.p);
     CB_CUDA(cudaGetLastError());
     if (plan.need == 2) {  // tiny buckets: one thread per sorted position, runs of equal keys are the buckets
-      if (max_tests) {
-        mih_run_tests_kernel<<<(m + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, info);
-        CB_CUDA(cudaGetLastError());
-      }
       WalkArgs WA{ws.sorted.p, ws.key2.p, ws.val2.p, m, info, max_tests, plan, threshold, out};
       for (int u = 0; u + u0 < plan.units; ++u) {
         WA.plan.u_c1[u] = plan.u_c1[u + u0];
@@ -805,7 +785,7 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
       mih_walk_kernel<<<(m + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, stream>>>(WA);
       CB_CUDA(cudaGetLastError());
       prof_end(kProfMihBucket, stream);
-      counters().launches += 4;
+      counters().launches += 3;
       ws.n_batches = batch_no + 1;
       continue;
     }
@@ -880,6 +860,7 @@ extern "C" {
 
 int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts,
                            cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  CB_API_BEGIN
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
   if (!d_hashes || !d_count || (!d_out && cap)) {
@@ -889,20 +870,24 @@ int cb_scan64_self_mih_dev(const uint64_t* d_hashes, uint32_t n, int threshold, 
   MihOut out{0, d_out, cap, d_count, nullptr, 0};
   return scan64_self_mih(d_hashes, n, threshold, part, n_parts, out, raw_ws()[current_device() & 15], 0,
                          static_cast<cudaStream_t>(stream));
+  CB_API_END
 }
 
 int cb_scan64_mih_last_tests(void* stream, uint64_t* tests_out) {
+  CB_API_BEGIN
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
   unsigned long long t = 0;
   rc = mih_read_info(raw_ws()[current_device() & 15], static_cast<cudaStream_t>(stream), &t, nullptr);
   if (tests_out) *tests_out = t;
   return rc;
+  CB_API_END
 }
 
 int cb_scan64_mih_max_threshold(void) { return kMihMaxThreshold; }
 
 int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks) {
+  CB_API_BEGIN
   if (threshold < 1 || threshold > kMihMaxThreshold) {
     set_error("cb_scan64_mih_plan: threshold %d outside [1, %d]", threshold, kMihMaxThreshold);
     return CB_ERR_UNSUPPORTED;
@@ -913,6 +898,7 @@ int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks) {
     if (masks) masks[c] = p.mask[c];
   }
   return p.chunks;
+  CB_API_END
 }
 
 void cb_scan64_mih_force(int variant, int need) {
@@ -921,11 +907,13 @@ void cb_scan64_mih_force(int variant, int need) {
 }
 
 int cb_scan64_mih_config(uint64_t n, int threshold, int* variant, int* need) {
+  CB_API_BEGIN
   if (!mih_applicable(n, threshold)) return 0;
   const int nd = mih_need_for(n, threshold);
   if (need) *need = nd;
   if (variant) *variant = nd == 2 ? 1 : bucket_variant_for(mih_plan(threshold, nd), threshold);
   return 1;
+  CB_API_END
 }
 
 }  // extern "C"

@@ -318,22 +318,27 @@ extern "C" {
 int cb_scan64_tiles_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, const cb_scan_tile* d_tiles,
                         uint32_t n_tiles, int threshold, cb_pair* d_out, uint64_t cap, unsigned long long* d_count,
                         void* stream) {
+  CB_API_BEGIN
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
   Scan64Launch L{d_a, n_a, d_b, n_b, threshold, 0, d_out, cap, d_count, 0, false};
   return scan64_tiles_launch(L, d_tiles, n_tiles, 0, static_cast<cudaStream_t>(stream));
+  CB_API_END
 }
 
 int cb_scan64_dev(const uint64_t* d_a, uint32_t n_a, const uint64_t* d_b, uint32_t n_b, int threshold,
                   int radix_bits, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  CB_API_BEGIN
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
   Scan64Launch L{d_a, n_a, d_b, n_b, threshold, radix_bits, d_out, cap, d_count, 0, false};
   return scan64_launch(L, static_cast<cudaStream_t>(stream));
+  CB_API_END
 }
 
 int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin, uint32_t row_end, int threshold,
                        int symmetric, cb_pair* d_out, uint64_t cap, unsigned long long* d_count, void* stream) {
+  CB_API_BEGIN
   int rc = ensure_device();
   if (rc != CB_OK) return rc;
   if (row_end > n || row_begin > row_end) {
@@ -348,6 +353,7 @@ int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin,
     L.n_a = row_end;
   }
   return scan64_launch(L, static_cast<cudaStream_t>(stream));
+  CB_API_END
 }
 
 int cb_scan64_variant(int threshold) { return scan64_variant_for(threshold > 65 ? 65 : threshold); }

@@ -182,6 +182,7 @@ using namespace cbird;
 extern "C" {
 
 int cb_vdx_decode_alloc(const uint8_t* data, int64_t size, int32_t** frames, uint64_t** hashes, int64_t* n, int* version) {
+  CB_API_BEGIN
   if (!data || size < 0 || !frames || !hashes || !n) {
     set_error("cb_vdx_decode_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -196,10 +197,12 @@ int cb_vdx_decode_alloc(const uint8_t* data, int64_t size, int32_t** frames, uin
   *hashes = export_array(h);
   *n = int64_t(f.size());
   return CB_OK;
+  CB_API_END
 }
 
 // VideoIndex::isValid (:90-102): header + trailer (v2) or exact file size (v1)
 int cb_vdx_is_valid(const uint8_t* data, int64_t size) {
+  CB_API_BEGIN
   if (!data || size < 0) return 0;
   if (size >= 5 && memcmp(data, "cbird", 5) == 0) {
     size_t nl = 0;
@@ -214,11 +217,13 @@ int cb_vdx_is_valid(const uint8_t* data, int64_t size) {
   uint16_t num = 0;
   memcpy(&num, data, 2);
   return size_t(size) == 2 + size_t(num) * 2 + size_t(num) * 8;
+  CB_API_END
 }
 
 // VideoIndex::save_v2 (:271-349)
 int cb_vdx_encode_alloc(const int32_t* frames, const uint64_t* hashes, int64_t n, const char* writer_version,
                         uint8_t** data, int64_t* size) {
+  CB_API_BEGIN
   if (n < 0 || (n && (!frames || !hashes)) || !data || !size) {
     set_error("cb_vdx_encode_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -266,16 +271,20 @@ int cb_vdx_encode_alloc(const int32_t* frames, const uint64_t* hashes, int64_t n
   *data = export_array(out);
   *size = int64_t(out.size());
   return *data ? CB_OK : CB_ERR_INVALID;
+  CB_API_END
 }
 
 int cb_vdx_load_alloc(const char* path, int32_t** frames, uint64_t** hashes, int64_t* n, int* version) {
+  CB_API_BEGIN
   if (!path) return CB_ERR_INVALID;
   std::vector<uint8_t> buf;
   if (!read_file(path, buf)) return CB_ERR_INVALID;
   return cb_vdx_decode_alloc(buf.data(), int64_t(buf.size()), frames, hashes, n, version);
+  CB_API_END
 }
 
 int cb_vdx_save(const char* path, const int32_t* frames, const uint64_t* hashes, int64_t n, const char* writer_version) {
+  CB_API_BEGIN
   if (!path) return CB_ERR_INVALID;
   uint8_t* data = nullptr;
   int64_t size = 0;
@@ -295,6 +304,7 @@ int cb_vdx_save(const char* path, const int32_t* frames, const uint64_t* hashes,
     return CB_ERR_INVALID;
   }
   return CB_OK;
+  CB_API_END
 }
 
 }  // extern "C"

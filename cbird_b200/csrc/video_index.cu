@@ -518,6 +518,7 @@ void cb_video_index_destroy(cb_video_index* ix) {
 }
 
 int cb_video_index_load(cb_video_index* ix, const uint32_t* ids, int64_t n) {
+  CB_API_BEGIN
   if (!ix || n < 0 || (n && !ids)) {
     set_error("cb_video_index_load: invalid argument");
     return CB_ERR_INVALID;
@@ -529,10 +530,12 @@ int cb_video_index_load(cb_video_index* ix, const uint32_t* ids, int64_t n) {
   I.built = false;
   I.loaded = true;  // lazy: the tree is built by the first search (:204-205)
   return CB_OK;
+  CB_API_END
 }
 
 int cb_video_index_set_video(cb_video_index* ix, uint32_t media_id, const int32_t* frames, const uint64_t* hashes,
                              int64_t n) {
+  CB_API_BEGIN
   if (!ix || n < 0 || (n && (!frames || !hashes))) {
     set_error("cb_video_index_set_video: invalid argument");
     return CB_ERR_INVALID;
@@ -544,9 +547,11 @@ int cb_video_index_set_video(cb_video_index* ix, uint32_t media_id, const int32_
   t.hashes.assign(hashes, hashes + n);
   I.built = false;
   return CB_OK;
+  CB_API_END
 }
 
 int cb_video_index_set_video_file(cb_video_index* ix, uint32_t media_id, const char* vdx_path) {
+  CB_API_BEGIN
   if (!ix || !vdx_path) {
     set_error("cb_video_index_set_video_file: invalid argument");
     return CB_ERR_INVALID;
@@ -561,6 +566,7 @@ int cb_video_index_set_video_file(cb_video_index* ix, uint32_t media_id, const c
   free(frames);
   free(hashes);
   return rc;
+  CB_API_END
 }
 
 int cb_video_index_is_loaded(const cb_video_index* ix) { return ix && ix->impl.loaded ? 1 : 0; }
@@ -571,6 +577,7 @@ size_t cb_video_index_memory_usage(const cb_video_index* ix) {
 }
 
 int cb_video_index_add(cb_video_index* ix, const uint32_t* ids, int64_t n) {
+  CB_API_BEGIN
   if (!ix || n < 0 || (n && !ids)) {
     set_error("cb_video_index_add: invalid argument");
     return CB_ERR_INVALID;
@@ -580,9 +587,11 @@ int cb_video_index_add(cb_video_index* ix, const uint32_t* ids, int64_t n) {
   I.mediaId.insert(I.mediaId.end(), ids, ids + n);  // :256-260
   I.built = false;
   return CB_OK;
+  CB_API_END
 }
 
 int cb_video_index_remove(cb_video_index* ix, const int32_t* ids, int64_t n) {
+  CB_API_BEGIN
   if (!ix || n < 0 || (n && !ids)) {
     set_error("cb_video_index_remove: invalid argument");
     return CB_ERR_INVALID;
@@ -596,9 +605,11 @@ int cb_video_index_remove(cb_video_index* ix, const int32_t* ids, int64_t n) {
   I.mediaId.swap(keep);
   I.built = false;
   return CB_OK;
+  CB_API_END
 }
 
 cb_video_index* cb_video_index_slice(const cb_video_index* ix, const uint32_t* ids, int64_t n) {
+  try {
   if (!ix || n < 0 || (n && !ids)) return nullptr;
   cb_video_index* out = new (std::nothrow) cb_video_index;
   if (!out) return nullptr;
@@ -611,6 +622,10 @@ cb_video_index* cb_video_index_slice(const cb_video_index* ix, const uint32_t* i
   }
   out->impl.loaded = true;
   return out;
+  } catch (...) {
+    set_error("cb_video_index_slice: out of memory or internal error");
+    return nullptr;
+  }
 }
 
 static int export_matches(const std::vector<cb_match>& m, cb_match* out, int64_t cap, int64_t* n_out) {
@@ -621,6 +636,7 @@ static int export_matches(const std::vector<cb_match>& m, cb_match* out, int64_t
 
 int cb_video_index_find_video(cb_video_index* ix, const int32_t* frames, const uint64_t* hashes, int64_t n,
                               uint32_t needle_id, const cb_params* p, cb_match* out, int64_t cap, int64_t* n_out) {
+  CB_API_BEGIN
   if (!ix || !p || !n_out || n < 0) {
     set_error("cb_video_index_find_video: invalid argument");
     return CB_ERR_INVALID;
@@ -633,12 +649,14 @@ int cb_video_index_find_video(cb_video_index* ix, const int32_t* frames, const u
   int rc = find_videos(I, needles, *p, res);
   if (rc != CB_OK) return rc;
   return export_matches(res[0], out, cap, n_out);
+  CB_API_END
 }
 
 int cb_video_index_find_videos_alloc(cb_video_index* ix, const int64_t* needle_offsets, const int32_t* frames,
                                      const uint64_t* hashes, const uint32_t* needle_ids, int64_t n_needles,
                                      const cb_params* p, int64_t** result_offsets, cb_match** matches,
                                      int64_t* n_matches) {
+  CB_API_BEGIN
   if (!ix || !p || !needle_offsets || !needle_ids || !result_offsets || !matches || !n_matches || n_needles < 0) {
     set_error("cb_video_index_find_videos_alloc: invalid argument");
     return CB_ERR_INVALID;
@@ -674,11 +692,13 @@ int cb_video_index_find_videos_alloc(cb_video_index* ix, const int64_t* needle_o
   *matches = m;
   *n_matches = int64_t(total);
   return CB_OK;
+  CB_API_END
 }
 
 // DctVideoIndex::findFrame (dctvideoindex.cpp:291-387): one image hash; the nearest frame per video
 int cb_video_index_find_frame(cb_video_index* ix, uint64_t hash, int32_t needle_dst_in, const cb_params* p,
                               cb_match* out, int64_t cap, int64_t* n_out) {
+  CB_API_BEGIN
   if (!ix || !p || !n_out) {
     set_error("cb_video_index_find_frame: invalid argument");
     return CB_ERR_INVALID;
@@ -738,6 +758,7 @@ int cb_video_index_find_frame(cb_video_index* ix, uint64_t hash, int32_t needle_
     res.push_back(m);
   }
   return export_matches(res, out, cap, n_out);
+  CB_API_END
 }
 
 }  // extern "C"
