@@ -417,8 +417,10 @@ struct FindQueue {
   std::vector<std::unique_ptr<FindSlot>> all_slots;
   bool leader_active = false;
   FindCtx ctx[kFindCtxMax];
-  int n_ctx = 2;       // batches in flight at most (CB_FIND_CTX)
-  int spin_us = 25;    // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
+  // measured with tools/find_bench.cpp on a 16-core host (profiles/find_bench_r02.txt): waiting callers that spin
+  // longer than a few microseconds take the cores the shepherds need
+  int n_ctx = 3;       // batches in flight at most (CB_FIND_CTX)
+  int spin_us = 5;     // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
   int device = 0;
   bool ready = false;
   std::atomic<uint64_t> batches{0}, needles{0};

@@ -434,32 +434,48 @@ int cb_hamming_tree_write(cb_hamming_tree* t, const char* path) {
   CB_API_END
 }
 
-static bool read_node(FILE* f, HammingTree& T, int depth) {
-  bool leaf = false;
-  if (fread(&leaf, sizeof(bool), 1, f) != 1) return false;
+// The cache file is untrusted input: every count is checked against the bytes left in the file, split bits
+// against [0, 63] (leaf_for shifts by them) and the recursion against the deepest tree 64-bit hashes can
+// make, so a corrupt or truncated file is rejected instead of exhausting the stack or the heap.
+struct TreeReader {
+  FILE* f;
+  long long left;  // bytes not yet consumed
+  bool take(void* dst, size_t bytes) {
+    if ((long long)bytes > left) return false;
+    if (bytes && fread(dst, 1, bytes, f) != bytes) return false;
+    left -= (long long)bytes;
+    return true;
+  }
+};
+
+static bool read_node(TreeReader& R, HammingTree& T, int depth) {
+  if (depth > 64) return false;
+  uint8_t leaf = 0;
+  if (!R.take(&leaf, 1) || leaf > 1) return false;
   const int id = int(T.nodes.size());
   T.nodes.push_back(HammingTree::Node());
   T.max_height = std::max(T.max_height, depth);
   if (!leaf) {
     int bit = 0;
-    if (fread(&bit, sizeof(int), 1, f) != 1) return false;
+    if (!R.take(&bit, sizeof(int)) || bit < 0 || bit > 63) return false;
     T.nodes[id].bit = bit;
     const int a = int(T.nodes.size());
-    if (!read_node(f, T, depth + 1)) return false;
+    if (!read_node(R, T, depth + 1)) return false;
     const int b = int(T.nodes.size());
-    if (!read_node(f, T, depth + 1)) return false;
+    if (!read_node(R, T, depth + 1)) return false;
     T.nodes[id].set_child = a;
     T.nodes[id].clear_child = b;
   } else {
     uint32_t count = 0;
-    if (fread(&count, sizeof(uint32_t), 1, f) != 1) return false;
+    if (!R.take(&count, sizeof(uint32_t))) return false;
+    if ((long long)count * 12 > R.left || T.s_hash.size() + count > 0xFFFFF000ull) return false;
     T.nodes[id].row_begin = uint32_t(T.s_hash.size());
     if (count) {
       const size_t at = T.s_hash.size();
       T.s_index.resize(at + count);
       T.s_hash.resize(at + count);
-      if (fread(T.s_index.data() + at, sizeof(uint32_t), count, f) != count) return false;
-      if (fread(T.s_hash.data() + at, sizeof(uint64_t), count, f) != count) return false;
+      if (!R.take(T.s_index.data() + at, sizeof(uint32_t) * size_t(count))) return false;
+      if (!R.take(T.s_hash.data() + at, sizeof(uint64_t) * size_t(count))) return false;
     }
     T.nodes[id].row_end = uint32_t(T.s_hash.size());
   }
@@ -486,7 +502,16 @@ int cb_hamming_tree_read(cb_hamming_tree* t, const char* path) {
   T.s_hash.clear();
   T.s_index.clear();
   T.max_height = 0;
-  const bool ok = read_node(f, T, 0);
+  const long at = ftell(f);
+  fseek(f, 0, SEEK_END);
+  TreeReader R{f, (long long)ftell(f) - at};
+  fseek(f, at, SEEK_SET);
+  bool ok = false;
+  try {
+    ok = read_node(R, T, 0);  // bytes after the root's subtree are ignored, as the reference's reader does
+  } catch (...) {
+    ok = false;
+  }
   fclose(f);
   if (!ok) {
     T.nodes.clear();
@@ -495,7 +520,7 @@ int cb_hamming_tree_read(cb_hamming_tree* t, const char* path) {
     T.hash.clear();
     T.index.clear();
     T.built = false;
-    set_error("%s: truncated hamming tree file", path);
+    set_error("%s: truncated or corrupt hamming tree file", path);
     return CB_ERR_INVALID;
   }
   // the file's shape is authoritative until the next insert

@@ -47,7 +47,9 @@ constexpr int kStage = 64;                     // staged hits per warp
 constexpr uint64_t kPadA = 0x5555555555555555ull, kPadB = 0xAAAAAAAAAAAAAAAAull;
 
 // info[] slots (device, zeroed at the start of every batch)
-enum { kNext = 0, kItems = 1, kTests = 2, kKept = 3, kDeclined = 4, kBlocks = 5, kInfoSlots = 8 };
+// kSpread.. : pair-test counters of the walk kernel, spread over 64 words so that one atomic per CTA does not queue up
+// on a single address (summed by mih_read_info)
+enum { kNext = 0, kItems = 1, kTests = 2, kKept = 3, kDeclined = 4, kBlocks = 5, kSpread = 16, kInfoSlots = 80 };
 
 __device__ __forceinline__ uint32_t unit_bucket(const MihPlan& plan, int u, uint64_t h) {
   const int c1 = plan.u_c1[u];
@@ -538,9 +540,13 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
       }
     }
   }
-  for (int off = 16; off; off >>= 1) walked += __shfl_down_sync(0xffffffffu, walked, off);
-  if ((threadIdx.x & 31) == 0 && walked) atomicAdd(A.info + kTests, walked);
+  __shared__ unsigned long long walked_cta;
+  if (threadIdx.x == 0) walked_cta = 0;
   __syncthreads();
+  for (int off = 16; off; off >>= 1) walked += __shfl_down_sync(0xffffffffu, walked, off);
+  if ((threadIdx.x & 31) == 0 && walked) atomicAdd(&walked_cta, walked);
+  __syncthreads();
+  if (threadIdx.x == 0 && walked_cta) atomicAdd(A.info + kSpread + (blockIdx.x & 63), walked_cta);
   // flush: two records per staged pair in mode 0; in mode 1 rows without id drop out, so count first
   const unsigned n = min(n_staged, unsigned(kWalkStage));
   if (!n) return;
@@ -841,7 +847,10 @@ int mih_read_info(MihWorkspace& ws, cudaStream_t stream, unsigned long long* tes
                           cudaMemcpyDeviceToHost, stream));
   CB_CUDA(cudaStreamSynchronize(stream));
   for (int b = 0; b < ws.n_batches; ++b) {
-    if (tests) *tests += ws.h_info[b * kInfoSlots + kTests];
+    if (tests) {
+      *tests += ws.h_info[b * kInfoSlots + kTests];
+      for (int k = 0; k < 64; ++k) *tests += ws.h_info[b * kInfoSlots + kSpread + k];
+    }
     if (declined && ws.h_info[b * kInfoSlots + kDeclined]) *declined = 1;
   }
   return CB_OK;

@@ -397,7 +397,9 @@ static int find_videos(VideoIndex& I, const std::vector<Needle>& needles, const 
   for (size_t k = 0; k < needles.size(); ++k) {
     Needle nd = needles[k];
     needle_ids[k] = nd.id;
-    if (!nd.frames && nd.id != 0) {  // indexed needle: use its stored table (:411-414)
+    if (nd.id != 0) {
+      // indexed needle: the reference ignores the caller's videoIndex() and reads <dataPath>/<id>.vdx (:409-414);
+      // the stored table is that file's stand-in, and a needle without one is "empty" like a missing file (:416-419)
       auto it = I.tables.find(nd.id);
       if (it == I.tables.end()) continue;
       nd.frames = it->second.frames.data();
@@ -603,6 +605,10 @@ int cb_video_index_remove(cb_video_index* ix, const int32_t* ids, int64_t n) {
   for (uint32_t id : I.mediaId)
     if (!gone.count(int32_t(id))) keep.push_back(id);  // :262-280
   I.mediaId.swap(keep);
+  // the frame tables stand for the .vdx files, which cbird deletes with the media: an id added again later must
+  // come with a fresh table instead of silently reusing this one
+  for (int64_t i = 0; i < n; ++i)
+    if (ids[i] > 0) I.tables.erase(uint32_t(ids[i]));
   I.built = false;
   return CB_OK;
   CB_API_END
@@ -616,6 +622,7 @@ cb_video_index* cb_video_index_slice(const cb_video_index* ix, const uint32_t* i
   // replicate load() with the subset; the tree rebuilds on first query (:389-397). Tables travel along
   // (the reference re-reads the .vdx files from the shared data path).
   out->impl.mediaId.assign(ids, ids + n);
+  std::lock_guard<std::mutex> lock(const_cast<cb_video_index*>(ix)->impl.mu);  // add/remove may run beside a slice
   for (int64_t i = 0; i < n; ++i) {
     auto it = ix->impl.tables.find(ids[i]);
     if (it != ix->impl.tables.end()) out->impl.tables[ids[i]] = it->second;

@@ -683,14 +683,15 @@ void orc_video_remove(void* p, const int* ids, long long n) {  // :262-280
 long long orc_video_count(void* p) { return (long long)static_cast<OrcVideoIndex*>(p)->mediaId.size(); }
 
 // DctVideoIndex::findVideo, src/dctvideoindex.cpp:399-657.
-// needle table given explicitly; if frames==NULL the stored table of needle_id is used (:411-414).
+// needle_id == 0: the needle's own table (nframes/nhashes) is used; needle_id != 0: the table stored for that id,
+// whatever the caller passes (the reference loads <dataPath>/<id>.vdx, :409-414).
 long long orc_video_find_video(void* p, const int* nframes, const uint64_t* nhashes, long long nn, uint32_t needle_id,
                                int dctThresh, int skipFrames, int minFramesMatched, int minFramesNear, int videoRadix,
                                int filterSelf, OrcMatch* out, long long cap) {
   OrcVideoIndex* ix = static_cast<OrcVideoIndex*>(p);
   orc_build_tree(ix, videoRadix, skipFrames);
   OrcVideoTable stored;
-  if (!nframes) {
+  if (needle_id != 0) {
     auto it = ix->tables.find(needle_id);
     if (it == ix->tables.end()) return 0;
     stored = it->second;
@@ -698,7 +699,7 @@ long long orc_video_find_video(void* p, const int* nframes, const uint64_t* nhas
     nhashes = stored.hashes.data();
     nn = (long long)stored.frames.size();
   }
-  if (nn == 0) return 0;  // "needle video index is empty" :416-419
+  if (nn == 0 || !nframes) return 0;  // "needle video index is empty" :416-419
   int thr = dctThresh;    // RadixMap_t::distance_t is char (radix.h:44); the boundary clamps to [0,65]
   if (thr < 0) thr = 0;
   if (thr > 65) thr = 65;
