@@ -37,7 +37,8 @@ class cb_profile(C.Structure):
     _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
 
 
-PROFILE_SLOTS = {"mih_bucket_kernel": 0, "mih_sort": 1, "hit_sort": 2, "scan64_kernel": 3, "dct_hash32_kernel": 4}
+PROFILE_SLOTS = {"mih_bucket_kernel": 0, "mih_sort": 1, "hit_sort": 2, "scan64_kernel": 3, "dct_hash32_kernel": 4,
+                 "mih_keys": 5, "mih_gather": 6, "post_step": 7}
 
 HIT_DTYPE = np.dtype([("needle", np.uint32), ("mediaId", np.uint32), ("score", np.int32)])
 PAIR_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("dist", np.uint32), ("pad", np.uint32)])

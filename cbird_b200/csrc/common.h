@@ -126,7 +126,10 @@ int comm_all_to_all(const CommRank& R, const void* const* send, const size_t* se
                     const size_t* recv_bytes, cudaStream_t s);
 
 // ---- optional per-kernel timing (CUDA events on the launching stream, collected by cb_profile_get) ----
-enum ProfId { kProfMihBucket = 0, kProfMihSort = 1, kProfHitSort = 2, kProfScan = 3, kProfHash32 = 4, kProfCount = 8 };
+enum ProfId {
+  kProfMihBucket = 0, kProfMihSort = 1, kProfHitSort = 2, kProfScan = 3, kProfHash32 = 4, kProfKeys = 5, kProfGather = 6, kProfPost = 7,
+  kProfCount = 8
+};
 void prof_begin(int id, cudaStream_t s);  // no-ops unless cb_profile_enable(1)
 void prof_end(int id, cudaStream_t s);
 
@@ -153,7 +156,7 @@ struct MihOut {  // where the self-join reports
   int needle_shift;           // mode 1
 };
 struct MihWorkspace {
-  DevBuf<uint32_t> key, key2, val, val2, ofs, nblk, blk_at, nitems, item_at;
+  DevBuf<uint32_t> key, key2, val, val2, ofs, nblk, blk_at, nitems, item_at, perm;
   DevBuf<uint64_t> sorted;
   DevBuf<cb_scan_tile> items;
   DevBuf<unsigned char> temp;

@@ -862,6 +862,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
     if ((rc = S.d_post_begin.reserve(size_t(n_rows) + 1)) != CB_OK || (rc = S.d_post_kept.reserve(size_t(n_rows) + 1)) != CB_OK ||
         (rc = S.d_post_off.reserve(size_t(n_rows) + 1)) != CB_OK)
       return rc;
+    prof_begin(kProfPost, st);
     similar_post_count<<<post_blocks, 256, 0, st>>>(keys, n_keys, J.L, S.d_hashes.p, S.d_ids.p, r0, n_rows, J.P, S.d_post_begin.p,
                                                    S.d_post_kept.p);
     CB_CUDA(cudaGetLastError());
@@ -869,6 +870,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
     CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, S.d_post_kept.p, S.d_post_off.p, static_cast<long long>(n_rows) + 1, st));
     if ((rc = S.d_temp.reserve(tb + 16)) != CB_OK) return rc;
     CB_CUDA(cub::DeviceScan::ExclusiveSum(S.d_temp.p, tb, S.d_post_kept.p, S.d_post_off.p, static_cast<long long>(n_rows) + 1, st));
+    prof_end(kProfPost, st);
     CB_CUDA(cudaMemcpyAsync(S.h_counts + 3, S.d_post_off.p + n_rows, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
     kept = S.h_counts[3];

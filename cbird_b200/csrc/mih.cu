@@ -588,6 +588,229 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
   }
 }
 
+// ---- need == 2, two levels ---------------------------------------------------------------------------
+// A bucket of the two-chunk plan is (value of chunk c1, value of chunk c2). Sorting every (row, unit) item by
+// the whole key moves 15 items per row through a 4-pass radix sort at T = 5. Instead the rows are grouped by
+// chunk c1 alone, ONCE for all units (c1, c2 > c1) that start with it (k - 1 sorts of n items on ~11 bits), and
+// one CTA per (c1 bucket, c2) finishes the job inside its bucket: histogram of the c2 values in shared memory,
+// scan, a permutation of the bucket's rows by c2 value (scratch in global memory, L2-resident: a bucket is tens
+// of KB), then every bin of equal c2 value is a bucket of the plan: its pairs are tested, OR-fold first, exact
+// re-test, first-unit rule as everywhere. Small bins go one per thread, bins over 32 rows are shared by the CTA.
+constexpr int kL2Threads = 256, kL2Stage = 256, kL2BigMax = 256;
+constexpr uint32_t kL2BinCap = 1u << 16;  // a bin larger than this means heavily skewed data: the pass is declined
+
+__global__ void mih2_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask, uint32_t c1,
+                                 uint32_t part, uint32_t n_parts, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
+                                 unsigned long long* __restrict__ counter) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint32_t k = live ? uint32_t(hash[i] >> shift) & mask : 0u;
+  if (n_parts == 1) {
+    if (live) {
+      key[i] = k;
+      val[i] = i;
+    }
+    return;
+  }
+  const unsigned lane = threadIdx.x & 31;
+  const bool mine = live && (k + c1) % n_parts == part;
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (!m) return;
+  unsigned long long base = 0;
+  if (lane == unsigned(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (mine) {
+    const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+    key[at] = k;
+    val[at] = i;
+  }
+}
+
+// rows of every c1 group dealt to `part`: one pass over the hashes, so that the host needs one read-back
+__global__ void mih2_count_kernel(const uint64_t* __restrict__ hash, uint32_t n, MihPlan plan, uint32_t part, uint32_t n_parts,
+                                  unsigned long long* __restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t h = i < n ? hash[i] : 0;
+  for (int c1 = 0; c1 + 1 < plan.chunks; ++c1) {
+    const uint32_t k = uint32_t(h >> plan.shift[c1]) & plan.mask[c1];
+    const unsigned m = __ballot_sync(0xffffffffu, i < n && (k + uint32_t(c1)) % n_parts == part);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(counts + c1, (unsigned long long)__popc(m));
+  }
+}
+
+struct L2Args {
+  const uint64_t* sorted;   // hashes grouped by the value of chunk c1
+  const uint32_t* rows;     // position -> row
+  const uint32_t* ofs;      // c1 bucket -> first position, [n_buckets + 1]
+  uint32_t* perm;           // scratch, [rounds][m]
+  uint32_t m;
+  unsigned long long* info;
+  MihPlan plan;
+  int c1;
+  int threshold;
+  MihOut out;
+};
+
+__device__ __forceinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned* n_staged, uint32_t pa, uint32_t pb, uint32_t d) {
+  const unsigned at = atomicAdd(n_staged, 1u);
+  if (at < unsigned(kL2Stage)) {
+    stage[at] = make_uint4(pa, pb, d, 0u);
+    return;
+  }
+  // staging full (a cluster of near-duplicates): straight to the list
+  const uint32_t ra = A.rows[pa], rb = A.rows[pb];
+  if (A.out.mode == 0) {
+    const unsigned long long pos = atomicAdd(A.out.count, 2ull);
+    if (pos < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos] = make_uint4(ra, rb, d, 0u);
+    if (pos + 1 < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos + 1] = make_uint4(rb, ra, d, 0u);
+    return;
+  }
+  const uint32_t ia = A.out.ids[ra], ib = A.out.ids[rb];
+  const unsigned long long kk = (ia ? 1 : 0) + (ib ? 1 : 0);
+  if (!kk) return;
+  unsigned long long pos = atomicAdd(A.out.count, kk);
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(A.out.out);
+  if (ib) {
+    if (pos < A.out.cap) o[pos] = ((unsigned long long)ra << A.out.needle_shift) | ((unsigned long long)d << 32) | ib;
+    ++pos;
+  }
+  if (ia && pos < A.out.cap) o[pos] = ((unsigned long long)rb << A.out.needle_shift) | ((unsigned long long)d << 32) | ia;
+}
+
+__global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A) {
+  extern __shared__ uint32_t l2_smem[];  // start[nb + 1], cursor[nb]
+  __shared__ uint4 stage[kL2Stage];
+  __shared__ unsigned n_staged, n_big, kept;
+  __shared__ uint32_t big[kL2BigMax];
+  __shared__ unsigned long long g_base, tests_cta;
+  const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.y);
+  const uint32_t nb = A.plan.mask[c2] + 1u;
+  uint32_t* start = l2_smem;
+  uint32_t* cursor = l2_smem + nb + 1;
+  const uint32_t base = A.ofs[blockIdx.x], s = A.ofs[blockIdx.x + 1] - base;
+  if (s < 2) return;
+  const int sh2 = A.plan.shift[c2];
+  const uint32_t mk2 = A.plan.mask[c2];
+  const int T = A.threshold;
+  const uint64_t* hs = A.sorted + base;
+  uint32_t* perm = A.perm + size_t(blockIdx.y) * A.m + base;
+  for (uint32_t b = threadIdx.x; b <= nb; b += kL2Threads) start[b] = 0;
+  if (threadIdx.x == 0) {
+    n_staged = 0;
+    n_big = 0;
+    kept = 0;
+    tests_cta = 0;
+  }
+  __syncthreads();
+  // histogram of the c2 values (start[b + 1] counts bin b)
+  for (uint32_t i = threadIdx.x; i < s; i += kL2Threads) atomicAdd(&start[1 + (uint32_t(hs[i] >> sh2) & mk2)], 1u);
+  __syncthreads();
+  // inclusive scan of start[1..nb] in place: every thread sums a contiguous slice, then a block scan of the slice sums
+  {
+    __shared__ uint32_t part_sum[kL2Threads];
+    const uint32_t per = (nb + kL2Threads - 1) / kL2Threads;
+    const uint32_t b0 = 1 + threadIdx.x * per, b1 = min(nb + 1, b0 + per);
+    uint32_t acc = 0;
+    for (uint32_t b = b0; b < b1; ++b) acc += start[b];
+    part_sum[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < kL2Threads; off <<= 1) {
+      const uint32_t v = int(threadIdx.x) >= off ? part_sum[threadIdx.x - off] : 0u;
+      __syncthreads();
+      part_sum[threadIdx.x] += v;
+      __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
+    for (uint32_t b = b0; b < b1; ++b) {
+      run += start[b];
+      start[b] = run;
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) cursor[b] = start[b];
+  __syncthreads();
+  // permutation of the bucket's rows by bin
+  for (uint32_t i = threadIdx.x; i < s; i += kL2Threads) perm[atomicAdd(&cursor[uint32_t(hs[i] >> sh2) & mk2], 1u)] = i;
+  __syncthreads();
+  // pairs inside every bin
+  auto test = [&](uint32_t ia, uint32_t ib) {
+    const uint64_t x = hs[ia] ^ hs[ib];
+    const uint32_t xlo = uint32_t(x), xhi = uint32_t(x >> 32);
+    if (__popc(xlo | xhi) >= T) return;
+    const int d = __popc(xlo) + __popc(xhi);
+    if (d >= T) return;
+    for (int c = 0; c < c2; ++c)  // reported by the first unit in which the two hashes share a bucket
+      if (c != c1 && ((uint32_t(x >> A.plan.shift[c])) & A.plan.mask[c]) == 0) return;
+    l2_emit(A, stage, &n_staged, base + ia, base + ib, uint32_t(d));
+  };
+  unsigned long long tests = 0;
+  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) {
+    const uint32_t beg = start[b], cnt = start[b + 1] - beg;
+    if (cnt < 2) continue;
+    tests += (unsigned long long)cnt * (cnt - 1) / 2;
+    if (cnt > 32) {
+      if (cnt > kL2BinCap) A.info[kDeclined] = 1;
+      const unsigned at = atomicAdd(&n_big, 1u);
+      if (at < unsigned(kL2BigMax)) big[at] = b;
+      else A.info[kDeclined] = 1;  // more large bins than the list holds: skewed data
+      continue;
+    }
+    for (uint32_t i = 0; i + 1 < cnt; ++i) {
+      const uint32_t ia = perm[beg + i];
+      for (uint32_t j = i + 1; j < cnt; ++j) test(ia, perm[beg + j]);
+    }
+  }
+  __syncthreads();
+  const unsigned nbig = min(n_big, unsigned(kL2BigMax));
+  for (unsigned k = 0; k < nbig; ++k) {  // a bin of many rows (duplicates): the whole CTA shares it
+    const uint32_t beg = start[big[k]], cnt = min(start[big[k] + 1] - beg, kL2BinCap);
+    for (uint32_t i = threadIdx.x; i + 1 < cnt; i += kL2Threads) {
+      const uint32_t ia = perm[beg + i];
+      for (uint32_t j = i + 1; j < cnt; ++j) test(ia, perm[beg + j]);
+    }
+  }
+  for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
+  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&tests_cta, tests);
+  __syncthreads();
+  if (threadIdx.x == 0 && tests_cta) atomicAdd(A.info + kSpread + ((blockIdx.x + blockIdx.y) & 63), tests_cta);
+  // flush the staged pairs: rows, ids, one global atomic per CTA
+  const unsigned ns = min(n_staged, unsigned(kL2Stage));
+  if (!ns) return;
+  for (unsigned i = threadIdx.x; i < ns; i += kL2Threads) {
+    const uint4 e = stage[i];
+    const uint32_t ra = A.rows[e.x], rb = A.rows[e.y];
+    unsigned k2 = 2;
+    uint32_t ia = 1, ib = 1;
+    if (A.out.mode == 1) {
+      ia = A.out.ids[ra];
+      ib = A.out.ids[rb];
+      k2 = (ia ? 1 : 0) + (ib ? 1 : 0);
+    }
+    const unsigned at = k2 ? atomicAdd(&kept, k2) : 0;
+    stage[i] = make_uint4(ra, rb, e.z | (at << 8), (ia ? 1u : 0u) | (ib ? 2u : 0u));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && kept) g_base = atomicAdd(A.out.count, (unsigned long long)kept);
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < ns; i += kL2Threads) {
+    const uint4 e = stage[i];
+    const uint32_t d = e.z & 0xFFu;
+    unsigned long long pos = g_base + (e.z >> 8);
+    if (A.out.mode == 0) {
+      if (pos < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos] = make_uint4(e.x, e.y, d, 0u);
+      if (pos + 1 < A.out.cap) reinterpret_cast<uint4*>(A.out.out)[pos + 1] = make_uint4(e.y, e.x, d, 0u);
+    } else {
+      unsigned long long* o = reinterpret_cast<unsigned long long*>(A.out.out);
+      if (e.w & 2u) {
+        if (pos < A.out.cap) o[pos] = ((unsigned long long)e.x << A.out.needle_shift) | ((unsigned long long)d << 32) | A.out.ids[e.y];
+        ++pos;
+      }
+      if ((e.w & 1u) && pos < A.out.cap)
+        o[pos] = ((unsigned long long)e.y << A.out.needle_shift) | ((unsigned long long)d << 32) | A.out.ids[e.x];
+    }
+  }
+}
+
 // every row matches itself at distance 0: rows [lo, hi), for n_parts > 1 only those whose unit-0 bucket is `part`'s
 __global__ void mih_self_kernel(const uint64_t* __restrict__ hash, uint32_t lo, uint32_t hi, MihPlan plan, uint32_t part,
                                 uint32_t n_parts, MihOut o) {
@@ -712,6 +935,77 @@ MihWorkspace::~MihWorkspace() {
   if (h_info) cudaFreeHost(h_info);
 }
 
+
+// need == 2 through the two-level grouping above. One info slot set (batch 0).
+static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_t part, uint32_t n_parts, const MihOut& out,
+                            MihWorkspace& ws, const MihPlan& plan, cudaStream_t stream) {
+  int rc;
+  const int groups = plan.chunks - 1;
+  if ((rc = ws.info.reserve(kInfoSlots * 64)) != CB_OK) return rc;
+  if (!ws.h_info) CB_CUDA(cudaMallocHost(&ws.h_info, 64 * kInfoSlots * sizeof(unsigned long long)));
+  unsigned long long* info = ws.info.p;
+  CB_CUDA(cudaMemsetAsync(info, 0, kInfoSlots * sizeof(unsigned long long), stream));
+  ws.n_batches = 1;
+  unsigned long long m_of[kMihMaxChunks];
+  for (int c1 = 0; c1 < groups; ++c1) m_of[c1] = n;
+  if (n_parts > 1) {  // how many rows of every group are dealt to this rank: one kernel, one read-back
+    if ((rc = ws.nblk.reserve(2 * kMihMaxChunks)) != CB_OK) return rc;
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ws.nblk.p);
+    CB_CUDA(cudaMemsetAsync(d_counts, 0, kMihMaxChunks * sizeof(unsigned long long), stream));
+    mih2_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan, part, n_parts, d_counts);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemcpyAsync(ws.h_info, d_counts, kMihMaxChunks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    for (int c1 = 0; c1 < groups; ++c1) m_of[c1] = ws.h_info[c1];
+    counters().launches += 1;
+  }
+  unsigned long long m_max = 1;
+  for (int c1 = 0; c1 < groups; ++c1) m_max = std::max(m_max, m_of[c1]);
+  const size_t max_rounds = size_t(groups);
+  uint32_t n_buckets_max = 0;
+  for (int c = 0; c < plan.chunks; ++c) n_buckets_max = std::max(n_buckets_max, plan.mask[c] + 1u);
+  if ((rc = ws.key.reserve(m_max)) != CB_OK || (rc = ws.key2.reserve(m_max)) != CB_OK || (rc = ws.val.reserve(m_max)) != CB_OK ||
+      (rc = ws.val2.reserve(m_max)) != CB_OK || (rc = ws.sorted.reserve(m_max + 2)) != CB_OK ||
+      (rc = ws.perm.reserve(m_max * max_rounds)) != CB_OK || (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK)
+    return rc;
+  for (int c1 = 0; c1 < groups; ++c1) {
+    const uint32_t m = uint32_t(m_of[c1]);
+    if (m < 2) continue;
+    const int rounds = plan.chunks - 1 - c1;
+    const uint32_t n_buckets = plan.mask[c1] + 1u;
+    prof_begin(kProfKeys, stream);
+    mih2_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part, n_parts,
+                                                          ws.key.p, ws.val.p, info + kKept);
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfKeys, stream);
+    if (n_parts > 1) CB_CUDA(cudaMemsetAsync(info + kKept, 0, sizeof(unsigned long long), stream));
+    size_t tb = 0;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                            plan.bits[c1], stream));
+    if ((rc = ws.temp.reserve(tb + 16)) != CB_OK) return rc;
+    prof_begin(kProfMihSort, stream);
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(ws.temp.p, tb, ws.key.p, ws.key2.p, ws.val.p, ws.val2.p, static_cast<long long>(m), 0,
+                                            plan.bits[c1], stream));
+    prof_end(kProfMihSort, stream);
+    prof_begin(kProfGather, stream);
+    mih_gather_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_hashes, ws.val2.p, nullptr, m, ws.sorted.p);
+    CB_CUDA(cudaGetLastError());
+    mih_bounds_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfGather, stream);
+    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.perm.p, m, info, plan, c1, threshold, out};
+    uint32_t nb_max = 0;
+    for (int c2 = c1 + 1; c2 < plan.chunks; ++c2) nb_max = std::max(nb_max, plan.mask[c2] + 1u);
+    const size_t smem = (size_t(nb_max) * 2 + 2) * sizeof(uint32_t);
+    prof_begin(kProfMihBucket, stream);
+    mih2_bucket_kernel<<<dim3(n_buckets, unsigned(rounds)), kL2Threads, smem, stream>>>(A);
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfMihBucket, stream);
+    counters().launches += 5;
+  }
+  return CB_OK;
+}
+
 // every ordered pair (a, b), a == b included, with hamm64 < threshold whose first shared bucket belongs to
 // `part`; appended to out (count is always the total). When the buckets are so skewed that a batch would cost
 // more than `max_tests` pair tests (0 = never decline) its scan kernel leaves at once and flags it: the caller
@@ -727,6 +1021,15 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   }
   const MihPlan plan = mih_plan(threshold, need == 1 || need == 2 ? need : mih_need_for(n, threshold));
   ws.last_need = plan.need;
+  static const bool walk = getenv("CB_MIH_WALK") != nullptr;  // the one-level path for two-chunk keys (comparison only)
+  if (plan.need == 2 && !walk) {
+    int rc2 = scan64_self_mih2(d_hashes, n, threshold, part, n_parts, out, ws, plan, stream);
+    if (rc2 != CB_OK) return rc2;
+    mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+    return CB_OK;
+  }
   // units are processed in batches that keep the sort below 2^29 items
   int per_batch = std::max<int>(1, int((1ull << 29) / n));
   per_batch = std::min(per_batch, plan.units);

@@ -123,7 +123,8 @@ void cb_shutdown(void);                          /* destroys the communicator; i
 /* Measurement aid: CUDA-event timing of the library's dominant kernels on the streams they are launched on
  * (bench.py's roofline numbers). Disabled by default; when enabled every bracketed launch records two events,
  * nothing is synchronised until cb_profile_get. Slots: 0 mih_bucket_kernel, 1 radix sort of the bucket keys,
- * 2 radix sort of the hit keys, 3 scan64_kernel, 4 dct_hash32_kernel. */
+ * 2 radix sort of the hit keys, 3 scan64_kernel, 4 dct_hash32_kernel, 5 bucket-key generation, 6 gather of the hashes
+ * into bucket order + bucket bounds, 7 searchIndex post step (count + scan). */
 #define CB_PROFILE_SLOTS 8
 typedef struct cb_profile {
   double ms[CB_PROFILE_SLOTS];        /* summed durations */

@@ -74,6 +74,7 @@ for n in rows:
                 line = {"rows": n, "thr": thr, "need": need, "variant": variant, "raw_pass_ms": raw_ms, "hits": int(cnt.item()),
                         "pair_tests": int(tests.value), "bucket_kernel_ms": k_ms, "sort_ms": prof.ms[S["mih_sort"]] / 3.0,
                         "tests_per_s_kernel": tests.value / max(k_ms, 1e-9) * 1e3, "similar_count_ms": float(np.mean(ws)),
+                        "keys_ms": prof.ms[S["mih_keys"]] / 3.0, "gather_ms": prof.ms[S["mih_gather"]] / 3.0,
                         "kept": kept, "nominal_cmp_per_s": n * float(n) / np.mean(ws) * 1e3}
                 lines.append(line)
                 print(json.dumps(line), flush=True)
