@@ -157,7 +157,7 @@ struct MihOut {  // where the self-join reports
 };
 struct MihWorkspace {
   DevBuf<uint32_t> key, key2, val, val2, ofs, nblk, blk_at, nitems, item_at, perm;
-  DevBuf<uint64_t> sorted;
+  DevBuf<uint64_t> sorted, bin_hash;
   DevBuf<cb_scan_tile> items;
   DevBuf<unsigned char> temp;
   DevBuf<unsigned long long> info;  // 8 slots per unit batch, see mih.cu

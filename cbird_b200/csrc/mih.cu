@@ -593,10 +593,11 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
 // the whole key moves 15 items per row through a 4-pass radix sort at T = 5. Instead the rows are grouped by
 // chunk c1 alone, ONCE for all units (c1, c2 > c1) that start with it (k - 1 sorts of n items on ~11 bits), and
 // one CTA per (c1 bucket, c2) finishes the job inside its bucket: histogram of the c2 values in shared memory,
-// scan, a permutation of the bucket's rows by c2 value (scratch in global memory, L2-resident: a bucket is tens
+// scan, the bucket's hashes rewritten in c2-bin order (scratch in global memory, L2-resident: a bucket is tens
 // of KB), then every bin of equal c2 value is a bucket of the plan: its pairs are tested, OR-fold first, exact
-// re-test, first-unit rule as everywhere. Small bins go one per thread, bins over 32 rows are shared by the CTA.
-constexpr int kL2Threads = 256, kL2Stage = 256, kL2BigMax = 256;
+// re-test, first-unit rule as everywhere. One thread per bin (bins of up to 8 rows out of registers), bins over
+// 128 rows are shared by the CTA.
+constexpr int kL2Threads = 256, kL2Stage = 256;
 constexpr uint32_t kL2BinCap = 1u << 16;  // a bin larger than this means heavily skewed data: the pass is declined
 
 __global__ void mih2_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask, uint32_t c1,
@@ -642,7 +643,8 @@ struct L2Args {
   const uint64_t* sorted;   // hashes grouped by the value of chunk c1
   const uint32_t* rows;     // position -> row
   const uint32_t* ofs;      // c1 bucket -> first position, [n_buckets + 1]
-  uint32_t* perm;           // scratch, [rounds][m]
+  uint64_t* bin_hash;       // scratch, [rounds][m]: a bucket's hashes in c2-bin order
+  uint32_t* bin_pos;        // scratch, [rounds][m]: their positions in `sorted`
   uint32_t m;
   unsigned long long* info;
   MihPlan plan;
@@ -651,7 +653,7 @@ struct L2Args {
   MihOut out;
 };
 
-__device__ __forceinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned* n_staged, uint32_t pa, uint32_t pb, uint32_t d) {
+__device__ __noinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned* n_staged, uint32_t pa, uint32_t pb, uint32_t d) {
   const unsigned at = atomicAdd(n_staged, 1u);
   if (at < unsigned(kL2Stage)) {
     stage[at] = make_uint4(pa, pb, d, 0u);
@@ -677,12 +679,15 @@ __device__ __forceinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned*
   if (ia && pos < A.out.cap) o[pos] = ((unsigned long long)rb << A.out.needle_shift) | ((unsigned long long)d << 32) | ia;
 }
 
+constexpr uint32_t kL2Small = 8;     // bins up to this many rows are tested out of registers
+constexpr uint32_t kL2Serial = 128;  // bins up to this many rows are walked by one thread, larger ones by the CTA
+
 __global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A) {
   extern __shared__ uint32_t l2_smem[];  // start[nb + 1], cursor[nb]
   __shared__ uint4 stage[kL2Stage];
-  __shared__ unsigned n_staged, n_big, kept;
-  __shared__ uint32_t big[kL2BigMax];
+  __shared__ unsigned n_staged, any_big, kept;
   __shared__ unsigned long long g_base, tests_cta;
+  __shared__ uint32_t part_sum[kL2Threads];
   const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.y);
   const uint32_t nb = A.plan.mask[c2] + 1u;
   uint32_t* start = l2_smem;
@@ -693,21 +698,27 @@ __global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A)
   const uint32_t mk2 = A.plan.mask[c2];
   const int T = A.threshold;
   const uint64_t* hs = A.sorted + base;
-  uint32_t* perm = A.perm + size_t(blockIdx.y) * A.m + base;
+  uint64_t* bh = A.bin_hash + size_t(blockIdx.y) * A.m + base;
+  uint32_t* bp = A.bin_pos + size_t(blockIdx.y) * A.m + base;
   for (uint32_t b = threadIdx.x; b <= nb; b += kL2Threads) start[b] = 0;
   if (threadIdx.x == 0) {
     n_staged = 0;
-    n_big = 0;
+    any_big = 0;
     kept = 0;
     tests_cta = 0;
   }
   __syncthreads();
-  // histogram of the c2 values (start[b + 1] counts bin b)
-  for (uint32_t i = threadIdx.x; i < s; i += kL2Threads) atomicAdd(&start[1 + (uint32_t(hs[i] >> sh2) & mk2)], 1u);
+  // histogram of the c2 values (start[b + 1] counts bin b); four independent loads in flight per thread
+  for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
+    uint64_t h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < s ? hs[i0 + u * kL2Threads] : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * kL2Threads < s) atomicAdd(&start[1 + (uint32_t(h[u] >> sh2) & mk2)], 1u);
+  }
   __syncthreads();
-  // inclusive scan of start[1..nb] in place: every thread sums a contiguous slice, then a block scan of the slice sums
-  {
-    __shared__ uint32_t part_sum[kL2Threads];
+  {  // inclusive scan of start[1..nb] in place: every thread sums a contiguous slice, then a block scan of the slice sums
     const uint32_t per = (nb + kL2Threads - 1) / kL2Threads;
     const uint32_t b0 = 1 + threadIdx.x * per, b1 = min(nb + 1, b0 + per);
     uint32_t acc = 0;
@@ -729,44 +740,64 @@ __global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A)
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) cursor[b] = start[b];
   __syncthreads();
-  // permutation of the bucket's rows by bin
-  for (uint32_t i = threadIdx.x; i < s; i += kL2Threads) perm[atomicAdd(&cursor[uint32_t(hs[i] >> sh2) & mk2], 1u)] = i;
+  // the bucket's hashes (and their positions) in bin order
+  for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
+    uint64_t h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < s ? hs[i0 + u * kL2Threads] : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * kL2Threads < s) {
+        const uint32_t at = atomicAdd(&cursor[uint32_t(h[u] >> sh2) & mk2], 1u);
+        bh[at] = h[u];
+        bp[at] = i0 + u * kL2Threads;
+      }
+  }
   __syncthreads();
-  // pairs inside every bin
-  auto test = [&](uint32_t ia, uint32_t ib) {
-    const uint64_t x = hs[ia] ^ hs[ib];
+  // pairs inside every bin: neighbouring threads own neighbouring bins, so their reads share cache lines
+  auto test = [&](uint64_t ha, uint64_t hb, uint32_t ia, uint32_t ib) {
+    const uint64_t x = ha ^ hb;
     const uint32_t xlo = uint32_t(x), xhi = uint32_t(x >> 32);
     if (__popc(xlo | xhi) >= T) return;
     const int d = __popc(xlo) + __popc(xhi);
     if (d >= T) return;
     for (int c = 0; c < c2; ++c)  // reported by the first unit in which the two hashes share a bucket
       if (c != c1 && ((uint32_t(x >> A.plan.shift[c])) & A.plan.mask[c]) == 0) return;
-    l2_emit(A, stage, &n_staged, base + ia, base + ib, uint32_t(d));
+    l2_emit(A, stage, &n_staged, base + bp[ia], base + bp[ib], uint32_t(d));
   };
   unsigned long long tests = 0;
   for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) {
     const uint32_t beg = start[b], cnt = start[b + 1] - beg;
     if (cnt < 2) continue;
     tests += (unsigned long long)cnt * (cnt - 1) / 2;
-    if (cnt > 32) {
-      if (cnt > kL2BinCap) A.info[kDeclined] = 1;
-      const unsigned at = atomicAdd(&n_big, 1u);
-      if (at < unsigned(kL2BigMax)) big[at] = b;
-      else A.info[kDeclined] = 1;  // more large bins than the list holds: skewed data
-      continue;
-    }
-    for (uint32_t i = 0; i + 1 < cnt; ++i) {
-      const uint32_t ia = perm[beg + i];
-      for (uint32_t j = i + 1; j < cnt; ++j) test(ia, perm[beg + j]);
+    if (cnt <= kL2Small) {
+      uint64_t r[kL2Small];
+#pragma unroll
+      for (uint32_t i = 0; i < kL2Small; ++i) r[i] = i < cnt ? bh[beg + i] : 0;
+#pragma unroll
+      for (uint32_t i = 0; i + 1 < kL2Small; ++i)
+#pragma unroll
+        for (uint32_t j = i + 1; j < kL2Small; ++j)
+          if (j < cnt) test(r[i], r[j], beg + i, beg + j);
+    } else if (cnt <= kL2Serial) {
+      for (uint32_t i = 0; i + 1 < cnt; ++i) {
+        const uint64_t hi = bh[beg + i];
+        for (uint32_t j = i + 1; j < cnt; ++j) test(hi, bh[beg + j], beg + i, beg + j);
+      }
+    } else {
+      if (cnt > kL2BinCap) A.info[kDeclined] = 1;  // heavily skewed data: the caller takes the one-chunk keys
+      any_big = 1;
     }
   }
   __syncthreads();
-  const unsigned nbig = min(n_big, unsigned(kL2BigMax));
-  for (unsigned k = 0; k < nbig; ++k) {  // a bin of many rows (duplicates): the whole CTA shares it
-    const uint32_t beg = start[big[k]], cnt = min(start[big[k] + 1] - beg, kL2BinCap);
-    for (uint32_t i = threadIdx.x; i + 1 < cnt; i += kL2Threads) {
-      const uint32_t ia = perm[beg + i];
-      for (uint32_t j = i + 1; j < cnt; ++j) test(ia, perm[beg + j]);
+  if (any_big) {  // bins of many rows (duplicates, or a chunk value shared by a large part of the index): the CTA shares them
+    for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t beg = start[b], cnt = min(start[b + 1] - beg, kL2BinCap);
+      if (cnt <= kL2Serial) continue;
+      for (uint32_t i = threadIdx.x; i + 1 < cnt; i += kL2Threads) {
+        const uint64_t hi = bh[beg + i];
+        for (uint32_t j = i + 1; j < cnt; ++j) test(hi, bh[beg + j], beg + i, beg + j);
+      }
     }
   }
   for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
@@ -966,7 +997,8 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
   for (int c = 0; c < plan.chunks; ++c) n_buckets_max = std::max(n_buckets_max, plan.mask[c] + 1u);
   if ((rc = ws.key.reserve(m_max)) != CB_OK || (rc = ws.key2.reserve(m_max)) != CB_OK || (rc = ws.val.reserve(m_max)) != CB_OK ||
       (rc = ws.val2.reserve(m_max)) != CB_OK || (rc = ws.sorted.reserve(m_max + 2)) != CB_OK ||
-      (rc = ws.perm.reserve(m_max * max_rounds)) != CB_OK || (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK)
+      (rc = ws.perm.reserve(m_max * max_rounds)) != CB_OK || (rc = ws.bin_hash.reserve(m_max * max_rounds)) != CB_OK ||
+      (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK)
     return rc;
   for (int c1 = 0; c1 < groups; ++c1) {
     const uint32_t m = uint32_t(m_of[c1]);
@@ -993,7 +1025,7 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     mih_bounds_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
     CB_CUDA(cudaGetLastError());
     prof_end(kProfGather, stream);
-    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.perm.p, m, info, plan, c1, threshold, out};
+    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.bin_hash.p, ws.perm.p, m, info, plan, c1, threshold, out};
     uint32_t nb_max = 0;
     for (int c2 = c1 + 1; c2 < plan.chunks; ++c2) nb_max = std::max(nb_max, plan.mask[c2] + 1u);
     const size_t smem = (size_t(nb_max) * 2 + 2) * sizeof(uint32_t);

@@ -298,11 +298,13 @@ int scan64_tiles_launch(const Scan64Launch& L, const cb_scan_tile* d_tiles, uint
   P.out = L.out;
   P.cap = L.cap;
   P.count = L.count;
+  prof_begin(kProfScan, stream);
   switch (scan64_variant_for(P.threshold)) {
     case 2: scan64_tiles_kernel<2><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
     case 1: scan64_tiles_kernel<1><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
     default: scan64_tiles_kernel<0><<<n_tiles, kThreads, 0, stream>>>(P, d_tiles); break;
   }
+  prof_end(kProfScan, stream);
   CB_CUDA(cudaGetLastError());
   counters().launches += 1;
   counters().comparisons += pair_tests;

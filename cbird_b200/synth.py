@@ -83,9 +83,11 @@ def luma_frames(n, seed, w=32, h=32, dup_frac=0.01, lsb_frac=0.01):
     return frames
 
 
-def video_tables(n_videos, frames_per_video, seed, first_id=1):
+def video_tables(n_videos, frames_per_video, seed, first_id=1, max_gap=30):
     """cfg4-style haystack: per-video random-walk frame hashes (each frame = previous with 0-3 bits of
-    1..63 flipped) and strictly increasing frame numbers starting at 0 with gaps 1-30.
+    1..63 flipped) and strictly increasing frame numbers starting at 0 with gaps 1-max_gap (cbird keeps a frame
+    whenever its hash moved away from the last kept one: gaps of a few frames; findVideo's locality score only
+    counts matched frames less than 15 frames apart, src/dctvideoindex.cpp:592-613).
     Returns (ids u32[n], {id: (frames i32, hashes u64)})."""
     rng = np.random.default_rng(seed)
     ids = np.arange(first_id, first_id + n_videos, dtype=np.uint32)
@@ -97,14 +99,14 @@ def video_tables(n_videos, frames_per_video, seed, first_id=1):
         delta ^= np.where(nflip > k, _U64(1) << bits[:, :, k], _U64(0)).astype(np.uint64)
     delta[:, 0] = start
     hashes = np.bitwise_xor.accumulate(delta, axis=1)
-    gaps = rng.integers(1, 31, size=(n_videos, frames_per_video)).astype(np.int64)
+    gaps = rng.integers(1, max_gap + 1, size=(n_videos, frames_per_video)).astype(np.int64)
     gaps[:, 0] = 0
     frames = np.cumsum(gaps, axis=1).astype(np.int32)
     tables = {int(i): (frames[k].copy(), hashes[k].copy()) for k, i in enumerate(ids)}
     return ids, tables
 
 
-def video_needles(ids, tables, n_copies, n_unrelated, frames_per_video, seed):
+def video_needles(ids, tables, n_copies, n_unrelated, frames_per_video, seed, max_gap=30):
     """needle videos: re-timed copies of haystack videos (every 2nd frame kept) + unrelated random walks.
     Returns list of (needle_id, frames, hashes, source_id or 0); needle ids are 0 (not in the index)."""
     rng = np.random.default_rng(seed)
@@ -114,7 +116,7 @@ def video_needles(ids, tables, n_copies, n_unrelated, frames_per_video, seed):
         f, h = tables[int(s)]
         out.append((0, f[::2].copy(), h[::2].copy(), int(s)))
     if n_unrelated:
-        _, other = video_tables(n_unrelated, frames_per_video, seed + 1000, first_id=1)
+        _, other = video_tables(n_unrelated, frames_per_video, seed + 1000, first_id=1, max_gap=max_gap)
         for k in other:
             f, h = other[k]
             out.append((0, f, h, 0))
