@@ -66,6 +66,7 @@ SIGNATURES = {
     "cb_comm_unique_id": (C.c_int, [_vp, C.c_int]),
     "cb_comm_init_rank": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cb_comm_shard_rows": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
     "cb_shutdown": (None, []),
     "cb_profile_enable": (None, [C.c_int]),
     "cb_profile_get": (C.c_int, [C.POINTER(cb_profile), C.c_int]),

@@ -11,6 +11,8 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.h"
 
 namespace cbird {
@@ -218,6 +220,20 @@ int cb_comm_info(int* world, int* n_local, int* first_rank) {
   if (world) *world = g_world.n_local ? g_world.world : 1;
   if (n_local) *n_local = g_world.n_local ? g_world.n_local : 1;
   if (first_rank) *first_rank = g_world.n_local ? g_world.local[0].rank : 0;
+  return CB_OK;
+}
+
+int cb_comm_shard_rows(int64_t n, int rank, int world, int64_t* row_begin, int64_t* row_end) {
+  if (n < 0 || world < 1 || rank < 0 || rank >= world || !row_begin || !row_end) {
+    set_error("cb_comm_shard_rows: invalid argument");
+    return CB_ERR_INVALID;
+  }
+  // the rule every sharded call uses: equal contiguous ranges, even length (16-byte aligned hash rows)
+  int64_t per = (n + world - 1) / world;
+  per = (per + 1) & ~int64_t(1);
+  if (per < 2) per = 2;
+  *row_begin = std::min<int64_t>(n, per * rank);
+  *row_end = std::min<int64_t>(n, *row_begin + per);
   return CB_OK;
 }
 

@@ -480,7 +480,7 @@ struct DctIndex {
   }
 
   int world() const { return shards.empty() ? 1 : shards[0]->R.world; }
-  uint32_t rows_per_rank() const {
+  uint32_t rows_per_rank() const {  // the rule of cb_comm_shard_rows
     const size_t w = size_t(world());
     size_t per = (n + w - 1) / w;
     per = (per + 1) & ~size_t(1);

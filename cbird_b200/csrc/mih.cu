@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
 // of KB), then every bin of equal c2 value is a bucket of the plan: its pairs are tested, OR-fold first, exact
 // re-test, first-unit rule as everywhere. One thread per bin (bins of up to 8 rows out of registers), bins over
 // 128 rows are shared by the CTA.
-constexpr int kL2Threads = 256, kL2Stage = 256;
+constexpr int kL2Threads = 512, kL2Stage = 256;
 constexpr uint32_t kL2BinCap = 1u << 16;  // a bin larger than this means heavily skewed data: the pass is declined
 
 __global__ void mih2_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask, uint32_t c1,
@@ -646,6 +646,8 @@ struct L2Args {
   uint64_t* bin_hash;       // scratch, [rounds][m]: a bucket's hashes in c2-bin order
   uint32_t* bin_pos;        // scratch, [rounds][m]: their positions in `sorted`
   uint32_t m;
+  uint32_t nb_max;          // bins the shared-memory layout reserves (largest 2^bits of the plan's chunks)
+  uint32_t smem_rows;       // buckets up to this many rows are re-ordered in shared memory
   unsigned long long* info;
   MihPlan plan;
   int c1;
@@ -653,7 +655,12 @@ struct L2Args {
   MihOut out;
 };
 
-__device__ __noinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned* n_staged, uint32_t pa, uint32_t pb, uint32_t d) {
+struct L2Emit {  // what the rare paths need, kept in shared memory (a reference to the kernel parameters would force a
+  const uint32_t* rows;  // per-thread copy of the whole parameter block into local memory)
+  MihOut out;
+};
+
+__device__ __noinline__ void l2_emit(const L2Emit& A, uint4* stage, unsigned* n_staged, uint32_t pa, uint32_t pb, uint32_t d) {
   const unsigned at = atomicAdd(n_staged, 1u);
   if (at < unsigned(kL2Stage)) {
     stage[at] = make_uint4(pa, pb, d, 0u);
@@ -679,50 +686,38 @@ __device__ __noinline__ void l2_emit(const L2Args& A, uint4* stage, unsigned* n_
   if (ia && pos < A.out.cap) o[pos] = ((unsigned long long)rb << A.out.needle_shift) | ((unsigned long long)d << 32) | ia;
 }
 
-constexpr uint32_t kL2Small = 8;     // bins up to this many rows are tested out of registers
-constexpr uint32_t kL2Serial = 128;  // bins up to this many rows are walked by one thread, larger ones by the CTA
-
-__global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A) {
-  extern __shared__ uint32_t l2_smem[];  // start[nb + 1], cursor[nb]
-  __shared__ uint4 stage[kL2Stage];
-  __shared__ unsigned n_staged, any_big, kept;
-  __shared__ unsigned long long g_base, tests_cta;
-  __shared__ uint32_t part_sum[kL2Threads];
-  const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.y);
-  const uint32_t nb = A.plan.mask[c2] + 1u;
-  uint32_t* start = l2_smem;
-  uint32_t* cursor = l2_smem + nb + 1;
-  const uint32_t base = A.ofs[blockIdx.x], s = A.ofs[blockIdx.x + 1] - base;
-  if (s < 2) return;
-  const int sh2 = A.plan.shift[c2];
-  const uint32_t mk2 = A.plan.mask[c2];
+// One CTA per (c1 bucket, c2). A bucket that fits the CTA's shared memory (L2Args::smem_rows) is re-ordered there:
+// 8 B of hash + 2 B of position per row; larger buckets use the global scratch (8 + 4 B per row, L2-resident).
+// After the scatter cur[b] is the END of bin b; a row at bin-ordered position p walks the rows after it up to the
+// end of its own bin, so a bin of c rows costs c (c - 1) / 2 tests spread over c threads, whatever c is.
+template <bool SMEM>
+__device__ __forceinline__ void l2_bucket(const L2Args& A, const L2Emit& E, const int* p_shift, const uint32_t* p_mask, uint32_t* cur, uint64_t* H,
+                                          void* Pv, const uint64_t* hs, uint32_t base, uint32_t s, int c1, int c2, uint4* stage,
+                                          unsigned* n_staged, unsigned long long* tests_cta) {
+  const uint32_t nb = p_mask[c2] + 1u;
+  const int sh2 = p_shift[c2];
+  const uint32_t mk2 = p_mask[c2];
   const int T = A.threshold;
-  const uint64_t* hs = A.sorted + base;
-  uint64_t* bh = A.bin_hash + size_t(blockIdx.y) * A.m + base;
-  uint32_t* bp = A.bin_pos + size_t(blockIdx.y) * A.m + base;
-  for (uint32_t b = threadIdx.x; b <= nb; b += kL2Threads) start[b] = 0;
-  if (threadIdx.x == 0) {
-    n_staged = 0;
-    any_big = 0;
-    kept = 0;
-    tests_cta = 0;
-  }
+  uint16_t* P16 = static_cast<uint16_t*>(Pv);
+  uint32_t* P32 = static_cast<uint32_t*>(Pv);
+  __shared__ uint32_t part_sum[kL2Threads];
+  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) cur[b] = 0;
   __syncthreads();
-  // histogram of the c2 values (start[b + 1] counts bin b); four independent loads in flight per thread
+  // histogram of the c2 values; four independent loads in flight per thread
   for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
     uint64_t h[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < s ? hs[i0 + u * kL2Threads] : 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + u * kL2Threads < s) atomicAdd(&start[1 + (uint32_t(h[u] >> sh2) & mk2)], 1u);
+      if (i0 + u * kL2Threads < s) atomicAdd(&cur[uint32_t(h[u] >> sh2) & mk2], 1u);
   }
   __syncthreads();
-  {  // inclusive scan of start[1..nb] in place: every thread sums a contiguous slice, then a block scan of the slice sums
+  {  // exclusive scan of cur[0..nb) in place: every thread sums a contiguous slice, then a block scan of the slice sums
     const uint32_t per = (nb + kL2Threads - 1) / kL2Threads;
-    const uint32_t b0 = 1 + threadIdx.x * per, b1 = min(nb + 1, b0 + per);
+    const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
     uint32_t acc = 0;
-    for (uint32_t b = b0; b < b1; ++b) acc += start[b];
+    for (uint32_t b = b0; b < b1; ++b) acc += cur[b];
     part_sum[threadIdx.x] = acc;
     __syncthreads();
     for (int off = 1; off < kL2Threads; off <<= 1) {
@@ -733,12 +728,11 @@ __global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A)
     }
     uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
     for (uint32_t b = b0; b < b1; ++b) {
-      run += start[b];
-      start[b] = run;
+      const uint32_t c = cur[b];
+      cur[b] = run;
+      run += c;
     }
   }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) cursor[b] = start[b];
   __syncthreads();
   // the bucket's hashes (and their positions) in bin order
   for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
@@ -748,60 +742,76 @@ __global__ void __launch_bounds__(kL2Threads) mih2_bucket_kernel(const L2Args A)
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (i0 + u * kL2Threads < s) {
-        const uint32_t at = atomicAdd(&cursor[uint32_t(h[u] >> sh2) & mk2], 1u);
-        bh[at] = h[u];
-        bp[at] = i0 + u * kL2Threads;
+        const uint32_t at = atomicAdd(&cur[uint32_t(h[u] >> sh2) & mk2], 1u);
+        H[at] = h[u];
+        if (SMEM) P16[at] = uint16_t(i0 + u * kL2Threads);
+        else P32[at] = i0 + u * kL2Threads;
       }
   }
   __syncthreads();
-  // pairs inside every bin: neighbouring threads own neighbouring bins, so their reads share cache lines
-  auto test = [&](uint64_t ha, uint64_t hb, uint32_t ia, uint32_t ib) {
-    const uint64_t x = ha ^ hb;
-    const uint32_t xlo = uint32_t(x), xhi = uint32_t(x >> 32);
-    if (__popc(xlo | xhi) >= T) return;
-    const int d = __popc(xlo) + __popc(xhi);
-    if (d >= T) return;
-    for (int c = 0; c < c2; ++c)  // reported by the first unit in which the two hashes share a bucket
-      if (c != c1 && ((uint32_t(x >> A.plan.shift[c])) & A.plan.mask[c]) == 0) return;
-    l2_emit(A, stage, &n_staged, base + bp[ia], base + bp[ib], uint32_t(d));
-  };
   unsigned long long tests = 0;
-  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) {
-    const uint32_t beg = start[b], cnt = start[b + 1] - beg;
-    if (cnt < 2) continue;
-    tests += (unsigned long long)cnt * (cnt - 1) / 2;
-    if (cnt <= kL2Small) {
-      uint64_t r[kL2Small];
-#pragma unroll
-      for (uint32_t i = 0; i < kL2Small; ++i) r[i] = i < cnt ? bh[beg + i] : 0;
-#pragma unroll
-      for (uint32_t i = 0; i + 1 < kL2Small; ++i)
-#pragma unroll
-        for (uint32_t j = i + 1; j < kL2Small; ++j)
-          if (j < cnt) test(r[i], r[j], beg + i, beg + j);
-    } else if (cnt <= kL2Serial) {
-      for (uint32_t i = 0; i + 1 < cnt; ++i) {
-        const uint64_t hi = bh[beg + i];
-        for (uint32_t j = i + 1; j < cnt; ++j) test(hi, bh[beg + j], beg + i, beg + j);
-      }
-    } else {
-      if (cnt > kL2BinCap) A.info[kDeclined] = 1;  // heavily skewed data: the caller takes the one-chunk keys
-      any_big = 1;
+  for (uint32_t p = threadIdx.x; p < s; p += kL2Threads) {
+    const uint64_t hp = H[p];
+    const uint32_t end = cur[uint32_t(hp >> sh2) & mk2];
+    if (end - p > kL2BinCap) {  // heavily skewed data: the caller takes the one-chunk keys
+      A.info[kDeclined] = 1;
+      continue;
     }
-  }
-  __syncthreads();
-  if (any_big) {  // bins of many rows (duplicates, or a chunk value shared by a large part of the index): the CTA shares them
-    for (uint32_t b = 0; b < nb; ++b) {
-      const uint32_t beg = start[b], cnt = min(start[b + 1] - beg, kL2BinCap);
-      if (cnt <= kL2Serial) continue;
-      for (uint32_t i = threadIdx.x; i + 1 < cnt; i += kL2Threads) {
-        const uint64_t hi = bh[beg + i];
-        for (uint32_t j = i + 1; j < cnt; ++j) test(hi, bh[beg + j], beg + i, beg + j);
-      }
+    tests += end - p - 1;
+    for (uint32_t q = p + 1; q < end; ++q) {
+      const uint64_t x = hp ^ H[q];
+      const uint32_t xlo = uint32_t(x), xhi = uint32_t(x >> 32);
+      if (__popc(xlo | xhi) >= T) continue;
+      const int d = __popc(xlo) + __popc(xhi);
+      if (d >= T) continue;
+      bool first = true;  // reported by the first unit in which the two hashes share a bucket
+      for (int c = 0; c < c2; ++c)
+        if (c != c1 && ((uint32_t(x >> p_shift[c])) & p_mask[c]) == 0) first = false;
+      if (!first) continue;
+      const uint32_t ia = SMEM ? uint32_t(P16[p]) : P32[p], ib = SMEM ? uint32_t(P16[q]) : P32[q];
+      l2_emit(E, stage, n_staged, base + ia, base + ib, uint32_t(d));
     }
   }
   for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
-  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&tests_cta, tests);
+  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(tests_cta, tests);
+}
+
+__global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args A) {
+  extern __shared__ __align__(16) unsigned char l2_smem[];  // cur[nb_max] | hashes[smem_rows] | positions u16[smem_rows]
+  __shared__ uint4 stage[kL2Stage];
+  __shared__ unsigned n_staged, kept;
+  __shared__ unsigned long long g_base, tests_cta;
+  const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.y);
+  const uint32_t base = A.ofs[blockIdx.x], s = A.ofs[blockIdx.x + 1] - base;
+  if (s < 2) return;
+  __shared__ int p_shift[kMihMaxChunks + 1];  // the plan's chunk table out of the parameter space (dynamic indexing)
+  __shared__ uint32_t p_mask[kMihMaxChunks + 1];
+  __shared__ L2Emit E;
+  if (threadIdx.x == 32) {
+    E.rows = A.rows;
+    E.out = A.out;
+  }
+  if (threadIdx.x <= kMihMaxChunks) {
+    p_shift[threadIdx.x] = A.plan.shift[threadIdx.x];
+    p_mask[threadIdx.x] = A.plan.mask[threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    n_staged = 0;
+    kept = 0;
+    tests_cta = 0;
+  }
+  __syncthreads();
+  uint32_t* cur = reinterpret_cast<uint32_t*>(l2_smem);
+  const uint64_t* hs = A.sorted + base;
+  if (s <= A.smem_rows) {
+    uint64_t* H = reinterpret_cast<uint64_t*>(l2_smem + size_t(A.nb_max) * 4);
+    uint16_t* P = reinterpret_cast<uint16_t*>(l2_smem + size_t(A.nb_max) * 4 + size_t(A.smem_rows) * 8);
+    l2_bucket<true>(A, E, p_shift, p_mask, cur, H, P, hs, base, s, c1, c2, stage, &n_staged, &tests_cta);
+  } else {
+    uint64_t* H = A.bin_hash + size_t(blockIdx.y) * A.m + base;
+    uint32_t* P = A.bin_pos + size_t(blockIdx.y) * A.m + base;
+    l2_bucket<false>(A, E, p_shift, p_mask, cur, H, P, hs, base, s, c1, c2, stage, &n_staged, &tests_cta);
+  }
   __syncthreads();
   if (threadIdx.x == 0 && tests_cta) atomicAdd(A.info + kSpread + ((blockIdx.x + blockIdx.y) & 63), tests_cta);
   // flush the staged pairs: rows, ids, one global atomic per CTA
@@ -1025,10 +1035,11 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     mih_bounds_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
     CB_CUDA(cudaGetLastError());
     prof_end(kProfGather, stream);
-    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.bin_hash.p, ws.perm.p, m, info, plan, c1, threshold, out};
-    uint32_t nb_max = 0;
-    for (int c2 = c1 + 1; c2 < plan.chunks; ++c2) nb_max = std::max(nb_max, plan.mask[c2] + 1u);
-    const size_t smem = (size_t(nb_max) * 2 + 2) * sizeof(uint32_t);
+    // two CTAs per SM: each gets half of the SM's shared memory for the bin table and the re-ordered bucket
+    const size_t smem = 108 * 1024;
+    const uint32_t smem_rows = uint32_t((smem - size_t(n_buckets_max) * 4) / 10) & ~31u;
+    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.bin_hash.p, ws.perm.p, m, n_buckets_max, smem_rows, info, plan, c1, threshold, out};
+    CB_CUDA(cudaFuncSetAttribute(mih2_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     prof_begin(kProfMihBucket, stream);
     mih2_bucket_kernel<<<dim3(n_buckets, unsigned(rounds)), kL2Threads, smem, stream>>>(A);
     CB_CUDA(cudaGetLastError());

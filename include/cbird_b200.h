@@ -118,6 +118,8 @@ int cb_init(const int* devices, int n_devices);
 int cb_comm_unique_id(uint8_t* id_out, int cap);  /* returns the id size (128) or a negative status */
 int cb_comm_init_rank(const uint8_t* id, int id_bytes, int rank, int world, int device);
 int cb_comm_info(int* world, int* n_local, int* first_rank);
+/* rows [row_begin, row_end) of an n-row index whose results rank `rank` of `world` owns (host only, no device) */
+int cb_comm_shard_rows(int64_t n, int rank, int world, int64_t* row_begin, int64_t* row_end);
 void cb_shutdown(void);                          /* destroys the communicator; indexes must be destroyed first */
 
 /* Measurement aid: CUDA-event timing of the library's dominant kernels on the streams they are launched on

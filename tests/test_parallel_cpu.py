@@ -151,3 +151,100 @@ def test_bucket_dealt_multi_index_merge(tmp_path, po):
         m = np.load(tmp_path / ("mih_%d.npy" % r)).astype(np.int64)
         m = m[np.lexsort((m[:, 2], m[:, 1], m[:, 0]))][:, :3]
         assert np.array_equal(m, want)
+
+
+def _worker_exchange(rank, world, port, n, t, out_dir):
+    """the sharded -similar protocol of cbird_b200/csrc/dct_index.cu on the host: this rank's share of the bucket scans
+    (numpy), every hit routed to the rank that owns its needle row (cb_comm_shard_rows), exact counts exchanged first,
+    point-to-point transfers, then sort by (needle, score, id) — gloo stands in for the NCCL all-to-all."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+
+    import cbird_b200 as cb
+    from cbird_b200 import synth
+
+    L = cb.lib()
+    shifts, masks = np.zeros(16, np.int32), np.zeros(16, np.uint32)
+    assert L.cb_scan64_mih_plan(t, shifts.ctypes.data, masks.ctypes.data) == t
+    h, _ = synth.dct_hashes(n, seed=6, planted_frac=0.4)
+    local = _mih_lists(h, t, rank, world, shifts[:t].astype(np.uint64), masks[:t].astype(np.uint64)).astype(np.int64)
+    spans = []
+    for r in range(world):
+        b, e = C.c_int64(0), C.c_int64(0)
+        assert L.cb_comm_shard_rows(n, r, world, C.byref(b), C.byref(e)) == 0
+        spans.append((b.value, e.value))
+    per = spans[0][1] - spans[0][0]
+    dest = np.minimum(local[:, 0] // per, world - 1)
+    counts = torch.tensor([int((dest == r).sum()) for r in range(world)], dtype=torch.int64)
+    table = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(table, counts)                       # table[src][dst]
+    parts = [torch.from_numpy(local[dest == r]) for r in range(world)]
+    got = [parts[rank]]
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            continue
+        if int(table[rank][r]):
+            reqs.append(dist.isend(parts[r].contiguous(), r))
+    for r in range(world):
+        if r == rank:
+            continue
+        k = int(table[r][rank])
+        if k:
+            buf = torch.zeros((k, 4), dtype=torch.int64)
+            dist.recv(buf, r)
+            got.append(buf)
+    for q in reqs:
+        q.wait()
+    mine = torch.cat(got).numpy()
+    assert len(mine) == sum(int(table[r][rank]) for r in range(world))
+    assert mine[:, 0].min() >= spans[rank][0] and mine[:, 0].max() < spans[rank][1]
+    mine = mine[np.lexsort((mine[:, 1], mine[:, 2], mine[:, 0]))][:, :3]  # (needle, score, row): ids ascend with rows here
+    np.save(os.path.join(out_dir, "ex_%d.npy" % rank), mine)
+    np.save(os.path.join(out_dir, "span_%d.npy" % rank), np.array(spans[rank]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_needle_owner_exchange(tmp_path, po, world):
+    n, t = 1501, 5
+    mp.spawn(_worker_exchange, args=(world, _free_port(), n, t, str(tmp_path)), nprocs=world, join=True)
+    from cbird_b200 import synth
+
+    h, ids = synth.dct_hashes(n, seed=6, planted_frac=0.4)
+    want, total, _ = po.dct_find_batch(h, ids, h, t)
+    want = want.copy()
+    want[:, 1] -= 1
+    want = want[np.lexsort((want[:, 1], want[:, 2], want[:, 0]))]
+    seen = 0
+    prev_end = 0
+    for r in range(world):
+        m = np.load(tmp_path / ("ex_%d.npy" % r))
+        b, e = np.load(tmp_path / ("span_%d.npy" % r))
+        assert b == prev_end
+        prev_end = e
+        sel = want[(want[:, 0] >= b) & (want[:, 0] < e)]
+        assert np.array_equal(m, sel), r
+        seen += len(m)
+    assert prev_end == n and seen == total
+
+
+def test_comm_shard_rows_rule(cb):
+    import ctypes as C
+
+    L = cb.lib()
+    for n in (0, 1, 2, 7, 4096, 1048576, 10_000_000, 99_999_999):
+        for world in (1, 2, 3, 4, 8, 16):
+            prev = 0
+            for r in range(world):
+                b, e = C.c_int64(-1), C.c_int64(-1)
+                assert L.cb_comm_shard_rows(n, r, world, C.byref(b), C.byref(e)) == 0
+                assert b.value == min(n, prev) and b.value <= e.value <= n and (b.value % 2 == 0 or b.value == n)
+                prev = e.value if e.value > b.value or b.value == n else prev
+            assert prev == n or n == 0
+    assert L.cb_comm_shard_rows(10, 2, 2, None, None) == -3
