@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kWalkThreads) mih_walk_kernel(const WalkArgs A
 // of KB), then every bin of equal c2 value is a bucket of the plan: its pairs are tested, OR-fold first, exact
 // re-test, first-unit rule as everywhere. One thread per bin (bins of up to 8 rows out of registers), bins over
 // 128 rows are shared by the CTA.
-constexpr int kL2Threads = 512, kL2Stage = 256;
+constexpr int kL2Threads = 512, kL2Stage = 128;
 constexpr uint32_t kL2BinCap = 1u << 16;  // a bin larger than this means heavily skewed data: the pass is declined
 
 __global__ void mih2_keys_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask, uint32_t c1,
@@ -686,73 +686,100 @@ __device__ __noinline__ void l2_emit(const L2Emit& A, uint4* stage, unsigned* n_
   if (ia && pos < A.out.cap) o[pos] = ((unsigned long long)rb << A.out.needle_shift) | ((unsigned long long)d << 32) | ia;
 }
 
-// One CTA per (c1 bucket, c2). A bucket that fits the CTA's shared memory (L2Args::smem_rows) is re-ordered there:
-// 8 B of hash + 2 B of position per row; larger buckets use the global scratch (8 + 4 B per row, L2-resident).
-// After the scatter cur[b] is the END of bin b; a row at bin-ordered position p walks the rows after it up to the
-// end of its own bin, so a bin of c rows costs c (c - 1) / 2 tests spread over c threads, whatever c is.
-template <bool SMEM>
-__device__ __forceinline__ void l2_bucket(const L2Args& A, const L2Emit& E, const int* p_shift, const uint32_t* p_mask, uint32_t* cur, uint64_t* H,
-                                          void* Pv, const uint64_t* hs, uint32_t base, uint32_t s, int c1, int c2, uint4* stage,
-                                          unsigned* n_staged, unsigned long long* tests_cta) {
-  const uint32_t nb = p_mask[c2] + 1u;
-  const int sh2 = p_shift[c2];
-  const uint32_t mk2 = p_mask[c2];
-  const int T = A.threshold;
-  uint16_t* P16 = static_cast<uint16_t*>(Pv);
-  uint32_t* P32 = static_cast<uint32_t*>(Pv);
-  __shared__ uint32_t part_sum[kL2Threads];
-  for (uint32_t b = threadIdx.x; b < nb; b += kL2Threads) cur[b] = 0;
+// One CTA per (bin range, c1 bucket, c2). The CTA owns the rows of its bucket whose c2 value falls into its bin range
+// (one range = the whole bucket when the bucket is expected to fit shared memory; the host cuts larger buckets into
+// ranges, gridDim.x of them, neighbours in launch order so that the bucket is read from HBM once and from L2 after
+// that). Rows that fit the CTA's shared memory (L2Args::smem_rows) are re-ordered there, 8 B of hash + 4 B of position
+// per row; otherwise in the global scratch. After the scatter cur[b] is the END of bin b; a row at bin-ordered position
+// p walks the rows after it up to the end of its own bin, so a bin of c rows costs c (c - 1) / 2 tests spread over c
+// threads, whatever c is.
+struct L2Cta {
+  const int* p_shift;
+  const uint32_t* p_mask;
+  uint32_t* cur;      // [nb]
+  uint32_t* part_sum; // [kL2Threads]
+  const uint64_t* hs; // the bucket's rows
+  uint32_t base, s;   // first position and rows of the bucket
+  int c1, c2;
+  uint32_t bin_lo, nb;
+  uint4* stage;
+  unsigned* n_staged;
+  unsigned long long* tests_cta;
+};
+
+// histogram of this CTA's bins + exclusive scan; returns (rows in its bins, rows of the bucket in lower bins)
+__device__ __forceinline__ uint2 l2_count(const L2Cta& C, unsigned* below_smem) {
+  const int sh2 = C.p_shift[C.c2];
+  const uint32_t mk2 = C.p_mask[C.c2];
+  for (uint32_t b = threadIdx.x; b < C.nb; b += kL2Threads) C.cur[b] = 0;
   __syncthreads();
-  // histogram of the c2 values; four independent loads in flight per thread
-  for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
+  unsigned below = 0;
+  for (uint32_t i0 = threadIdx.x; i0 < C.s; i0 += 4 * kL2Threads) {  // four independent loads in flight per thread
     uint64_t h[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < s ? hs[i0 + u * kL2Threads] : 0;
+    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < C.s ? C.hs[i0 + u * kL2Threads] : ~0ull;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (i0 + u * kL2Threads < s) atomicAdd(&cur[uint32_t(h[u] >> sh2) & mk2], 1u);
-  }
-  __syncthreads();
-  {  // exclusive scan of cur[0..nb) in place: every thread sums a contiguous slice, then a block scan of the slice sums
-    const uint32_t per = (nb + kL2Threads - 1) / kL2Threads;
-    const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
-    uint32_t acc = 0;
-    for (uint32_t b = b0; b < b1; ++b) acc += cur[b];
-    part_sum[threadIdx.x] = acc;
-    __syncthreads();
-    for (int off = 1; off < kL2Threads; off <<= 1) {
-      const uint32_t v = int(threadIdx.x) >= off ? part_sum[threadIdx.x - off] : 0u;
-      __syncthreads();
-      part_sum[threadIdx.x] += v;
-      __syncthreads();
-    }
-    uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
-    for (uint32_t b = b0; b < b1; ++b) {
-      const uint32_t c = cur[b];
-      cur[b] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  // the bucket's hashes (and their positions) in bin order
-  for (uint32_t i0 = threadIdx.x; i0 < s; i0 += 4 * kL2Threads) {
-    uint64_t h[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < s ? hs[i0 + u * kL2Threads] : 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (i0 + u * kL2Threads < s) {
-        const uint32_t at = atomicAdd(&cur[uint32_t(h[u] >> sh2) & mk2], 1u);
-        H[at] = h[u];
-        if (SMEM) P16[at] = uint16_t(i0 + u * kL2Threads);
-        else P32[at] = i0 + u * kL2Threads;
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t v = uint32_t(h[u] >> sh2) & mk2;
+      if (i0 + u * kL2Threads < C.s) {
+        if (v - C.bin_lo < C.nb) atomicAdd(&C.cur[v - C.bin_lo], 1u);  // (wraps for v < bin_lo)
+        else if (v < C.bin_lo) ++below;
       }
+    }
+  }
+  if (C.bin_lo) {
+    for (int off = 16; off; off >>= 1) below += __shfl_down_sync(0xffffffffu, below, off);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(below_smem, below);
+  }
+  __syncthreads();
+  // exclusive scan of cur[0..nb) in place: every thread sums a contiguous slice, then a block scan of the slice sums
+  const uint32_t per = (C.nb + kL2Threads - 1) / kL2Threads;
+  const uint32_t b0 = threadIdx.x * per, b1 = min(C.nb, b0 + per);
+  uint32_t acc = 0;
+  for (uint32_t b = b0; b < b1; ++b) acc += C.cur[b];
+  C.part_sum[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 1; off < kL2Threads; off <<= 1) {
+    const uint32_t v = int(threadIdx.x) >= off ? C.part_sum[threadIdx.x - off] : 0u;
+    __syncthreads();
+    C.part_sum[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? C.part_sum[threadIdx.x - 1] : 0u;
+  for (uint32_t b = b0; b < b1; ++b) {
+    const uint32_t c = C.cur[b];
+    C.cur[b] = run;
+    run += c;
+  }
+  const uint32_t total = C.part_sum[kL2Threads - 1];
+  __syncthreads();
+  return make_uint2(total, *below_smem);
+}
+
+__device__ __forceinline__ void l2_scatter_walk(const L2Args& A, const L2Emit& E, const L2Cta& C, uint64_t* H, uint32_t* P, uint32_t rows) {
+  const int sh2 = C.p_shift[C.c2];
+  const uint32_t mk2 = C.p_mask[C.c2];
+  const int T = A.threshold;
+  // this CTA's rows (and their positions in the bucket) in bin order
+  for (uint32_t i0 = threadIdx.x; i0 < C.s; i0 += 4 * kL2Threads) {
+    uint64_t h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[u] = i0 + u * kL2Threads < C.s ? C.hs[i0 + u * kL2Threads] : ~0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t bin = (uint32_t(h[u] >> sh2) & mk2) - C.bin_lo;
+      if (i0 + u * kL2Threads < C.s && bin < C.nb) {
+        const uint32_t at = atomicAdd(&C.cur[bin], 1u);
+        H[at] = h[u];
+        P[at] = i0 + u * kL2Threads;
+      }
+    }
   }
   __syncthreads();
   unsigned long long tests = 0;
-  for (uint32_t p = threadIdx.x; p < s; p += kL2Threads) {
+  for (uint32_t p = threadIdx.x; p < rows; p += kL2Threads) {
     const uint64_t hp = H[p];
-    const uint32_t end = cur[uint32_t(hp >> sh2) & mk2];
+    const uint32_t end = C.cur[(uint32_t(hp >> sh2) & mk2) - C.bin_lo];
     if (end - p > kL2BinCap) {  // heavily skewed data: the caller takes the one-chunk keys
       A.info[kDeclined] = 1;
       continue;
@@ -765,28 +792,28 @@ __device__ __forceinline__ void l2_bucket(const L2Args& A, const L2Emit& E, cons
       const int d = __popc(xlo) + __popc(xhi);
       if (d >= T) continue;
       bool first = true;  // reported by the first unit in which the two hashes share a bucket
-      for (int c = 0; c < c2; ++c)
-        if (c != c1 && ((uint32_t(x >> p_shift[c])) & p_mask[c]) == 0) first = false;
+      for (int c = 0; c < C.c2; ++c)
+        if (c != C.c1 && ((uint32_t(x >> C.p_shift[c])) & C.p_mask[c]) == 0) first = false;
       if (!first) continue;
-      const uint32_t ia = SMEM ? uint32_t(P16[p]) : P32[p], ib = SMEM ? uint32_t(P16[q]) : P32[q];
-      l2_emit(E, stage, n_staged, base + ia, base + ib, uint32_t(d));
+      l2_emit(E, C.stage, C.n_staged, C.base + P[p], C.base + P[q], uint32_t(d));
     }
   }
   for (int off = 16; off; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
-  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(tests_cta, tests);
+  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(C.tests_cta, tests);
 }
 
 __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args A) {
-  extern __shared__ __align__(16) unsigned char l2_smem[];  // cur[nb_max] | hashes[smem_rows] | positions u16[smem_rows]
+  extern __shared__ __align__(16) unsigned char l2_smem[];  // cur[nb_max] | hashes[smem_rows] | positions[smem_rows]
   __shared__ uint4 stage[kL2Stage];
-  __shared__ unsigned n_staged, kept;
+  __shared__ unsigned n_staged, kept, below_rows;
   __shared__ unsigned long long g_base, tests_cta;
-  const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.y);
-  const uint32_t base = A.ofs[blockIdx.x], s = A.ofs[blockIdx.x + 1] - base;
-  if (s < 2) return;
+  __shared__ uint32_t part_sum[kL2Threads];
   __shared__ int p_shift[kMihMaxChunks + 1];  // the plan's chunk table out of the parameter space (dynamic indexing)
   __shared__ uint32_t p_mask[kMihMaxChunks + 1];
   __shared__ L2Emit E;
+  const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.z);
+  const uint32_t base = A.ofs[blockIdx.y], s = A.ofs[blockIdx.y + 1] - base;
+  if (s < 2) return;
   if (threadIdx.x == 32) {
     E.rows = A.rows;
     E.out = A.out;
@@ -799,21 +826,30 @@ __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args
     n_staged = 0;
     kept = 0;
     tests_cta = 0;
+    below_rows = 0;
   }
   __syncthreads();
-  uint32_t* cur = reinterpret_cast<uint32_t*>(l2_smem);
-  const uint64_t* hs = A.sorted + base;
-  if (s <= A.smem_rows) {
-    uint64_t* H = reinterpret_cast<uint64_t*>(l2_smem + size_t(A.nb_max) * 4);
-    uint16_t* P = reinterpret_cast<uint16_t*>(l2_smem + size_t(A.nb_max) * 4 + size_t(A.smem_rows) * 8);
-    l2_bucket<true>(A, E, p_shift, p_mask, cur, H, P, hs, base, s, c1, c2, stage, &n_staged, &tests_cta);
-  } else {
-    uint64_t* H = A.bin_hash + size_t(blockIdx.y) * A.m + base;
-    uint32_t* P = A.bin_pos + size_t(blockIdx.y) * A.m + base;
-    l2_bucket<false>(A, E, p_shift, p_mask, cur, H, P, hs, base, s, c1, c2, stage, &n_staged, &tests_cta);
+  // this CTA's bin range of the c2 value
+  const uint32_t nb_all = p_mask[c2] + 1u;
+  const uint32_t per_part = (nb_all + gridDim.x - 1) / gridDim.x;
+  const uint32_t bin_lo = blockIdx.x * per_part;
+  if (bin_lo >= nb_all) return;
+  L2Cta C{p_shift, p_mask, reinterpret_cast<uint32_t*>(l2_smem), part_sum, A.sorted + base, base, s, c1, c2, bin_lo,
+          min(per_part, nb_all - bin_lo), stage, &n_staged, &tests_cta};
+  const uint2 cnt = l2_count(C, &below_rows);
+  if (cnt.x >= 2) {
+    if (cnt.x <= A.smem_rows) {
+      uint64_t* H = reinterpret_cast<uint64_t*>(l2_smem + size_t(A.nb_max) * 4);
+      uint32_t* P = reinterpret_cast<uint32_t*>(l2_smem + size_t(A.nb_max) * 4 + size_t(A.smem_rows) * 8);
+      l2_scatter_walk(A, E, C, H, P, cnt.x);
+    } else {  // the rows of lower bin ranges come first in the bucket's scratch region
+      uint64_t* H = A.bin_hash + size_t(blockIdx.z) * A.m + base + cnt.y;
+      uint32_t* P = A.bin_pos + size_t(blockIdx.z) * A.m + base + cnt.y;
+      l2_scatter_walk(A, E, C, H, P, cnt.x);
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && tests_cta) atomicAdd(A.info + kSpread + ((blockIdx.x + blockIdx.y) & 63), tests_cta);
+  if (threadIdx.x == 0 && tests_cta) atomicAdd(A.info + kSpread + ((blockIdx.x + blockIdx.y + blockIdx.z) & 63), tests_cta);
   // flush the staged pairs: rows, ids, one global atomic per CTA
   const unsigned ns = min(n_staged, unsigned(kL2Stage));
   if (!ns) return;
@@ -1035,13 +1071,18 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     mih_bounds_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
     CB_CUDA(cudaGetLastError());
     prof_end(kProfGather, stream);
-    // two CTAs per SM: each gets half of the SM's shared memory for the bin table and the re-ordered bucket
-    const size_t smem = 108 * 1024;
-    const uint32_t smem_rows = uint32_t((smem - size_t(n_buckets_max) * 4) / 10) & ~31u;
+    // two CTAs per SM (228 KB per SM, ~7 KB static and 1 KB reserved per CTA): 104 KB each for the bin table and the
+    // re-ordered bucket
+    const size_t smem = 104 * 1024;
+    const uint32_t smem_rows = uint32_t((smem - size_t(n_buckets_max) * 4) / 12) & ~31u;
     L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.bin_hash.p, ws.perm.p, m, n_buckets_max, smem_rows, info, plan, c1, threshold, out};
     CB_CUDA(cudaFuncSetAttribute(mih2_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     prof_begin(kProfMihBucket, stream);
-    mih2_bucket_kernel<<<dim3(n_buckets, unsigned(rounds)), kL2Threads, smem, stream>>>(A);
+    // buckets expected to overflow the shared-memory budget are cut into bin ranges (25 % head room for uneven buckets)
+    const double rows_per_bucket = double(m) / double(n_buckets);
+    unsigned parts = unsigned(rows_per_bucket * 1.25 / double(smem_rows)) + 1u;
+    parts = std::min(parts, 64u);
+    mih2_bucket_kernel<<<dim3(parts, n_buckets, unsigned(rounds)), kL2Threads, smem, stream>>>(A);
     CB_CUDA(cudaGetLastError());
     prof_end(kProfMihBucket, stream);
     counters().launches += 5;
