@@ -405,6 +405,24 @@ def main():
     sort_ms_step = reduce_max((prof.ms[S["mih_sort"]] + prof.ms[S["hit_sort"]]) / args.steps)
     scan_ms_step = reduce_max(prof.ms[S["scan64_kernel"]] / args.steps)
 
+    # ---------------- the one-chunk plan's kernel (POPC-bound) on the same index, for the roofline record ----------------
+    bucket_leg = None
+    if not args.no_extras or os.environ.get("CB_BENCH_BUCKET_LEG"):
+        L.cb_scan64_mih_force(0, 1)
+        ix.similar_count(params)
+        L.cb_profile_get(C.byref(prof), 1)
+        L.cb_profile_enable(1)
+        reps = 3
+        for i in range(reps):
+            flush.fill_(i)
+            barrier()
+            kept1, issued1 = ix.similar_count(params)
+        barrier()
+        L.cb_profile_enable(0)
+        L.cb_profile_get(C.byref(prof), 1)
+        L.cb_scan64_mih_force(0, 0)
+        bucket_leg = {"kernel_ms": prof.ms[S["mih_bucket_kernel"]] / reps, "issued": float(issued1), "kept": int(kept1)}
+
     # ---------------- e2e through the public API, host buffers, the same call at every N ----------------
     def step_e2e():
         ix.load(np_ids, np_hashes)      # H2D inside the C ABI (this rank's rows + all-gather when N > 1)
@@ -497,7 +515,7 @@ def main():
         popc_frac = issued_rank0 * popc_per_test / k_s / popc_peak
         alu_frac = issued_rank0 * lop_per_test / k_s / alu_peak
         roofline = {
-            "bound": "int_pipe", "kernel": ("mih_bucket_kernel<%d>" % variant) if need == 1 else "mih_walk_kernel",
+            "bound": "int_pipe", "kernel": ("mih_bucket_kernel<%d>" % variant) if need == 1 else "mih2_bucket_kernel",
             "chunks_per_bucket_key": need,
             "achieved": issued_rank0 * popc_per_test / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
             "frac": popc_frac,
@@ -515,9 +533,28 @@ def main():
             "nominal_frac": comparisons / world / (step_ms * 1e-3) / pair_peak,
             "nominal_frac_note": "rows^2 x 2 POPC / step time / peak: NOT a hardware fraction (the index issues a small share of "
                                  "the square); kept because SURVEY 8d defines the metric on nominal comparisons",
-            "traffic": committed_traffic("mih_bucket_kernel"),
+            "traffic": committed_traffic("mih_bucket_kernel" if need == 1 else "mih2_bucket_kernel"),
+            "note": ("two-chunk bucket keys leave so few pair tests that the POPC pipe idles: this kernel is bound by the latency of "
+                     "its shared-memory histogram / scatter phases and by one pass over the bucket's rows (8 B per row per c2 round "
+                     "from L2/HBM); roofline_bucket_kernel is the POPC-bound kernel of the one-chunk plan on the same index")
+                    if need == 2 else "",
+            "hbm_frac_of_kernel": (float(n_rows) * 8.0 * (15 if DHT == 5 else DHT * (DHT + 1) / 2) / world / k_s / 1e9 / hbm_peak) if need == 2 else None,
             "peak_source": "148 SM x 16 POPC lanes/clk/SM (measured, profiles/pipe_probe_r01.json) x %.0f MHz max SM clock" % sm_max_mhz,
         }
+        if bucket_leg:
+            v1 = C.c_int(1)
+            L.cb_scan64_mih_force(0, 1)
+            L.cb_scan64_mih_config(n_rows, DHT, C.byref(v1), None)
+            L.cb_scan64_mih_force(0, 0)
+            ppt = {1: 1.0, 2: 0.5, 3: 0.5}[int(v1.value)]
+            ks = max(bucket_leg["kernel_ms"], 1e-9) * 1e-3
+            roofline["roofline_bucket_kernel"] = {
+                "kernel": "mih_bucket_kernel<%d> (one-chunk bucket keys forced: the plan below ~2e6 rows and the fallback for skewed data)" % int(v1.value),
+                "bound": "int_pipe", "kernel_ms_per_pass": bucket_leg["kernel_ms"], "issued_pair_tests_rank0": bucket_leg["issued"],
+                "achieved": bucket_leg["issued"] * ppt / ks / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
+                "frac": bucket_leg["issued"] * ppt / ks / popc_peak, "popc_per_pair_test": ppt,
+                "same_hits_as_default_plan": bool(bucket_leg["kept"] == int(n_kept)),
+                "traffic": committed_traffic("mih_bucket_kernel")}
         line = {
             "metric": "hamming_comparisons_per_sec", "value": value, "unit": "comparisons/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,

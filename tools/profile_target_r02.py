@@ -1,7 +1,10 @@
 """launches the round-2 hot kernels a few times for ncu: the -similar pass at 10^7 rows with the default (two-level,
 two-chunk keys) path and with one-chunk keys (mih_bucket_kernel), the find() queue kernel, dct_hash32."""
 import ctypes as C
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
