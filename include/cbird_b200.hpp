@@ -64,6 +64,11 @@ struct SearchParams {
   }
 };
 
+/// Multi-GPU: call once, before any index is created — where Engine::Engine makes the Index objects
+/// (src/engine.cpp:38-45). Afterwards DctHashIndex::load / similar fan out over the devices by themselves.
+inline bool init(const std::vector<int>& devices) { return ok(cb_init(devices.data(), int(devices.size())), "cbird::init"); }
+inline void shutdown() { cb_shutdown(); }
+
 /// the slice of Media the indexes read (src/media.h:243,253,300,417,536-539)
 struct Media {
   enum { TypeImage = 1, TypeVideo = 2 };
