@@ -15,9 +15,12 @@
 //     re-tested exactly.  G is chosen from the threshold so that the bound stays far above T on
 //     random descriptors (G=1 saturates at ~32, G=2 at ~60, G=4 at ~96); G=8 is the exact kernel.
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include <algorithm>
 #include <map>
+#include <memory>
+#include <thread>
 #include <unordered_set>
 
 #include "common.h"
@@ -181,50 +184,192 @@ struct KHitLess {  // (query, dist, row)
 
 }  // namespace
 
+// per-query cut of a list sorted by (query, dist, row): a record stays when fewer than k records of its query come
+// before it; rows become global (row0 = first row of the shard)
+__global__ void knn_cut_flags(cb_pair* __restrict__ pairs, unsigned long long n, int k, uint32_t row0, unsigned char* __restrict__ flags) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t q = pairs[i].b;
+  unsigned long long lo = 0, hi = i;  // first record of this query
+  while (lo < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    if (pairs[mid].b < q) lo = mid + 1; else hi = mid;
+  }
+  flags[i] = (k <= 0 || i - lo < (unsigned long long)k) ? 1 : 0;
+  pairs[i].a += row0;
+}
+
+// one device's share of the descriptor rows
+struct OrbShard {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> d_desc, d_q;
+  uint32_t row0 = 0, rows = 0;  // index rows [row0, row0 + rows) live here
+  DevBuf<cb_pair> d_pairs, d_cut;
+  DevBuf<unsigned char> d_temp, d_flags;
+  DevBuf<unsigned long long> d_counts;
+  unsigned long long* h_counts = nullptr;
+  unsigned long long n_cut = 0;
+  ~OrbShard() {
+    cudaSetDevice(device);
+    if (h_counts) cudaFreeHost(h_counts);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  int init() {
+    CB_CUDA(cudaSetDevice(device));
+    if (!stream) CB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!h_counts) CB_CUDA(cudaMallocHost(&h_counts, 4 * sizeof(unsigned long long)));
+    return d_counts.reserve(4);
+  }
+
+  // exact neighbours under the threshold of every query among this shard's rows, sorted by (query, dist, row),
+  // at most k per query, rows global; left in d_cut[0, n_cut)
+  int knn(const uint8_t* q, int64_t nq, int threshold, int k) {
+    n_cut = 0;
+    CB_CUDA(cudaSetDevice(device));
+    if (!nq || !rows || threshold <= 0) return CB_OK;
+    int rc = d_q.reserve(size_t(nq) * 32 + 32);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(d_q.p, q, size_t(nq) * 32, cudaMemcpyHostToDevice, stream));
+    // an overflow of the hit list costs a second scan: size the first guess from the needle count
+    unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, std::min<unsigned long long>(4ull * nq + (1ull << 18), 1ull << 28));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      rc = d_pairs.reserve(cap);
+      if (rc != CB_OK) return rc;
+      cap = d_pairs.cap;
+      CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 4 * sizeof(unsigned long long), stream));
+      rc = scan256_launch(d_desc.p, rows, d_q.p, uint32_t(nq), threshold, d_pairs.p, cap, d_counts.p, stream);
+      if (rc != CB_OK) return rc;
+      CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      CB_CUDA(cudaStreamSynchronize(stream));
+      if (h_counts[0] <= cap) break;
+      cap = h_counts[0] + h_counts[0] / 8 + 1024;
+      if (attempt == 2) {
+        set_error("scan256: hit list overflow persisted");
+        return CB_ERR_CUDA;
+      }
+    }
+    const unsigned long long n = h_counts[0];
+    counters().hits += n;
+    if (!n) return CB_OK;
+    return sort_and_cut(d_pairs.p, n, k, row0);
+  }
+
+  // pairs (device, this shard's) -> sorted, cut to k per query, rows + add_row0, in d_cut
+  int sort_and_cut(cb_pair* pairs, unsigned long long n, int k, uint32_t add_row0) {
+    size_t tb = 0, tb2 = 0;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)nullptr, tb, pairs, (long long)n, KHitLess(), stream));
+    int rc = d_flags.reserve(n);
+    if (rc == CB_OK) rc = d_cut.reserve(n);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cub::DeviceSelect::Flagged(nullptr, tb2, pairs, d_flags.p, d_cut.p, d_counts.p + 1, (long long)n, stream));
+    rc = d_temp.reserve(std::max(tb, tb2) + 16);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)d_temp.p, tb, pairs, (long long)n, KHitLess(), stream));
+    knn_cut_flags<<<unsigned((n + 255) / 256), 256, 0, stream>>>(pairs, n, k, add_row0, d_flags.p);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cub::DeviceSelect::Flagged(d_temp.p, tb2, pairs, d_flags.p, d_cut.p, d_counts.p + 1, (long long)n, stream));
+    CB_CUDA(cudaMemcpyAsync(h_counts + 1, d_counts.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CB_CUDA(cudaStreamSynchronize(stream));
+    n_cut = h_counts[1];
+    counters().launches += 2;
+    return CB_OK;
+  }
+};
+
 struct OrbIndex {
   std::vector<uint8_t> desc;                 // _descriptors: rows x 32
   std::vector<uint32_t> first_row, media;    // _indexMap as sorted arrays: block start -> mediaId (0 = removed)
   std::map<uint32_t, std::pair<uint32_t, uint32_t>> id_map;  // _idMap: mediaId -> (first row, rows)
   bool loaded = false;
-  int device = 0;
   std::mutex mu;
-  cudaStream_t stream = nullptr;
-  DevBuf<uint8_t> d_desc, d_q;
-  size_t d_rows = 0;
-  DevBuf<cb_pair> d_pairs;
-  DevBuf<unsigned char> d_temp;
-  DevBuf<unsigned long long> d_counts;
-  unsigned long long* h_counts = nullptr;
+  // the rows on the device(s): one shard, or one per device of cb_init (rows split evenly, needles go to all of them,
+  // per-shard top-k lists are merged on the first device)
+  std::vector<std::unique_ptr<OrbShard>> shards;
+  size_t d_rows = 0;  // rows valid on the device(s)
 
-  ~OrbIndex() {
-    if (h_counts) cudaFreeHost(h_counts);
-    if (stream) cudaStreamDestroy(stream);
-  }
   uint32_t rows() const { return uint32_t(desc.size() / 32); }
 
   int init_device() {
-    int rc = ensure_device();
-    if (rc != CB_OK) return rc;
-    if (!stream) {
-      device = current_device();
-      CB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!shards.empty()) return CB_OK;
+    const CommWorld& W = comm_world();
+    std::vector<std::unique_ptr<OrbShard>> v;
+    if (W.n_local > 1 && W.n_local == W.world) {
+      for (int i = 0; i < W.n_local; ++i) {
+        v.emplace_back(new OrbShard);
+        v.back()->device = W.local[i].device;
+      }
+    } else {
+      int rc = ensure_device();
+      if (rc != CB_OK) return rc;
+      v.emplace_back(new OrbShard);
+      v.back()->device = current_device();
     }
-    if (!h_counts) CB_CUDA(cudaMallocHost(&h_counts, 2 * sizeof(unsigned long long)));
-    return d_counts.reserve(2);
+    for (auto& sh : v) {
+      int rc = sh->init();
+      if (rc != CB_OK) return rc;
+    }
+    shards = std::move(v);
+    return CB_OK;
   }
 
-  // append rows of the device mirror (load / add)
+  template <class F>
+  int for_each_shard(F f) {
+    if (shards.size() == 1) return f(*shards[0]);
+    std::vector<int> rcs(shards.size(), CB_OK);
+    std::vector<std::string> errs(shards.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < shards.size(); ++i)
+      th.emplace_back([&, i] {
+        try {
+          rcs[i] = f(*shards[i]);
+        } catch (...) {
+          set_error("exception in a shard thread");
+          rcs[i] = CB_ERR_INVALID;
+        }
+        if (rcs[i] != CB_OK) errs[i] = cb_last_error();
+      });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < shards.size(); ++i)
+      if (rcs[i] != CB_OK) {
+        set_error("%s", errs[i].c_str());
+        return rcs[i];
+      }
+    return CB_OK;
+  }
+
+  // rows of the device mirror (load / add): one shard appends, several re-split
   int sync_to_device() {
     int rc = init_device();
     if (rc != CB_OK) return rc;
-    CB_CUDA(cudaSetDevice(device));
     const size_t n = rows();
     if (n < d_rows) d_rows = 0;
     if (n == d_rows) return CB_OK;
-    rc = d_desc.reserve(n * 32 + 32, true, stream);
-    if (rc != CB_OK) return rc;
-    CB_CUDA(cudaMemcpyAsync(d_desc.p + d_rows * 32, desc.data() + d_rows * 32, (n - d_rows) * 32, cudaMemcpyHostToDevice, stream));
-    CB_CUDA(cudaStreamSynchronize(stream));
+    if (shards.size() == 1) {
+      OrbShard& S = *shards[0];
+      CB_CUDA(cudaSetDevice(S.device));
+      rc = S.d_desc.reserve(n * 32 + 32, true, S.stream);
+      if (rc != CB_OK) return rc;
+      CB_CUDA(cudaMemcpyAsync(S.d_desc.p + d_rows * 32, desc.data() + d_rows * 32, (n - d_rows) * 32, cudaMemcpyHostToDevice, S.stream));
+      CB_CUDA(cudaStreamSynchronize(S.stream));
+      S.row0 = 0;
+      S.rows = uint32_t(n);
+    } else {
+      const size_t per = (n + shards.size() - 1) / shards.size();
+      for (size_t i = 0; i < shards.size(); ++i) {
+        shards[i]->row0 = uint32_t(std::min(n, per * i));
+        shards[i]->rows = uint32_t(std::min(n, per * (i + 1)) - shards[i]->row0);
+      }
+      rc = for_each_shard([&](OrbShard& S) -> int {
+        CB_CUDA(cudaSetDevice(S.device));
+        int r = S.d_desc.reserve(size_t(S.rows) * 32 + 32);
+        if (r != CB_OK) return r;
+        if (S.rows) CB_CUDA(cudaMemcpyAsync(S.d_desc.p, desc.data() + size_t(S.row0) * 32, size_t(S.rows) * 32, cudaMemcpyHostToDevice, S.stream));
+        CB_CUDA(cudaStreamSynchronize(S.stream));
+        return CB_OK;
+      });
+      if (rc != CB_OK) return rc;
+    }
     d_rows = n;
     return CB_OK;
   }
@@ -257,49 +402,34 @@ struct OrbIndex {
     int rc = sync_to_device();
     if (rc != CB_OK) return rc;
     if (!nq || !d_rows || threshold <= 0) return CB_OK;
-    rc = d_q.reserve(size_t(nq) * 32 + 32);
+    rc = for_each_shard([&](OrbShard& S) { return S.knn(q, nq, threshold, k); });
     if (rc != CB_OK) return rc;
-    CB_CUDA(cudaMemcpyAsync(d_q.p, q, size_t(nq) * 32, cudaMemcpyHostToDevice, stream));
-    // an overflow of the hit list costs a second scan: size the first guess from the needle count
-    unsigned long long cap = std::max<unsigned long long>(d_pairs.cap, std::min<unsigned long long>(4ull * nq + (1ull << 18), 1ull << 28));
-    for (int attempt = 0; attempt < 3; ++attempt) {
-      rc = d_pairs.reserve(cap);
+    OrbShard& S0 = *shards[0];
+    CB_CUDA(cudaSetDevice(S0.device));
+    const cb_pair* src = S0.d_cut.p;
+    unsigned long long n = S0.n_cut;
+    if (shards.size() > 1) {
+      // the per-shard lists (<= k per query each) meet on the first device: peer copies, one more sort + cut
+      unsigned long long total = 0;
+      for (auto& sh : shards) total += sh->n_cut;
+      if (!total) return CB_OK;
+      rc = S0.d_pairs.reserve(total);
       if (rc != CB_OK) return rc;
-      cap = d_pairs.cap;
-      CB_CUDA(cudaMemsetAsync(d_counts.p, 0, 2 * sizeof(unsigned long long), stream));
-      rc = scan256_launch(d_desc.p, uint32_t(d_rows), d_q.p, uint32_t(nq), threshold, d_pairs.p, cap, d_counts.p, stream);
-      if (rc != CB_OK) return rc;
-      CB_CUDA(cudaMemcpyAsync(h_counts, d_counts.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-      CB_CUDA(cudaStreamSynchronize(stream));
-      if (h_counts[0] <= cap) break;
-      cap = h_counts[0] + h_counts[0] / 8 + 1024;
-      if (attempt == 2) {
-        set_error("scan256: hit list overflow persisted");
-        return CB_ERR_CUDA;
+      unsigned long long at = 0;
+      for (auto& sh : shards) {
+        if (!sh->n_cut) continue;
+        CB_CUDA(cudaMemcpyPeerAsync(S0.d_pairs.p + at, S0.device, sh->d_cut.p, sh->device, size_t(sh->n_cut) * sizeof(cb_pair), S0.stream));
+        at += sh->n_cut;
       }
+      rc = S0.sort_and_cut(S0.d_pairs.p, total, k, 0);
+      if (rc != CB_OK) return rc;
+      src = S0.d_cut.p;
+      n = S0.n_cut;
     }
-    const unsigned long long n = h_counts[0];
-    counters().hits += n;
     if (!n) return CB_OK;
-    size_t tb = 0;
-    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)nullptr, tb, d_pairs.p, (long long)n, KHitLess(), stream));
-    rc = d_temp.reserve(tb + 16);
-    if (rc != CB_OK) return rc;
-    CB_CUDA(cub::DeviceMergeSort::SortKeys((void*)d_temp.p, tb, d_pairs.p, (long long)n, KHitLess(), stream));
-    std::vector<cb_pair> all(n);
-    CB_CUDA(cudaMemcpyAsync(all.data(), d_pairs.p, n * sizeof(cb_pair), cudaMemcpyDeviceToHost, stream));
-    CB_CUDA(cudaStreamSynchronize(stream));
-    if (k <= 0) {
-      out.swap(all);
-      return CB_OK;
-    }
-    size_t i = 0;
-    while (i < all.size()) {
-      size_t j = i;
-      while (j < all.size() && all[j].b == all[i].b) ++j;
-      for (size_t t = i; t < j && t < i + size_t(k); ++t) out.push_back(all[t]);
-      i = j;
-    }
+    out.resize(n);
+    CB_CUDA(cudaMemcpyAsync(out.data(), src, n * sizeof(cb_pair), cudaMemcpyDeviceToHost, S0.stream));
+    CB_CUDA(cudaStreamSynchronize(S0.stream));
     return CB_OK;
   }
 };
@@ -318,7 +448,6 @@ cb_orb_index* cb_orb_index_create(void) { return new (std::nothrow) cb_orb_index
 
 void cb_orb_index_destroy(cb_orb_index* ix) {
   if (!ix) return;
-  if (ix->impl.stream) cudaSetDevice(ix->impl.device);
   delete ix;
 }
 

@@ -75,10 +75,28 @@ def test_cb_init_one_process_all_devices(cb, po):
     import torch
 
     L = cb.lib()
+    # CvFeaturesIndex on one device first: the sharded index below must give the same lists
+    oids, odesc = synth.orb_descriptors(300, 100, seed=3, planted_frac=0.2)
+    rng = np.random.default_rng(4)
+    needle = np.concatenate([odesc[7], odesc[130][:40], rng.integers(0, 256, size=(60, 32), dtype=np.uint8)])
+    solo = cb.CvFeaturesIndex()
+    solo.load(oids, odesc)
+    want_knn = solo.knn(needle, k=10, threshold=40)
+    want_find = [(m.mediaId, m.score) for m in solo.find(cb.Media(descriptors=needle), cb.SearchParams(cvThresh=40))]
+    assert len(want_knn) > 100 and len(want_find) >= 2
+    del solo
     ndev = min(torch.cuda.device_count(), 4)
     devs = (C.c_int * ndev)(*range(ndev))
     assert L.cb_init(devs, ndev) == 0, L.cb_last_error()
     try:
+        ox = cb.CvFeaturesIndex()
+        ox.load(oids, odesc)
+        got_knn = ox.knn(needle, k=10, threshold=40)
+        assert np.array_equal(got_knn, want_knn)
+        assert [(m.mediaId, m.score) for m in ox.find(cb.Media(descriptors=needle), cb.SearchParams(cvThresh=40))] == want_find
+        ox.add([cb.Media(id=9001, descriptors=needle[:50])])
+        assert any(m.mediaId == 9001 and m.score == 0 for m in ox.find(cb.Media(descriptors=needle[:50]), cb.SearchParams(cvThresh=25)))
+        del ox
         n = 400_000
         h, ids = synth.dct_hashes_fast(n, seed=13, planted_frac=0.3)
         h[1000:1040] = 0
