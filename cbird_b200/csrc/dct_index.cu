@@ -699,6 +699,15 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
   unsigned long long n_keys = 0, kept = 0;
   unsigned long long* keys = nullptr;
   const unsigned post_blocks = unsigned((size_t(n_rows) + 1 + 255) / 256);
+  // CB_TRACE=1: host timestamps of the phases on stderr (each mark drains the stream: measurement aid only)
+  static const bool trace = getenv("CB_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[cb trace] rank %d %-22s %8.3f ms\n", rank, what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+  };
 
   // how the pair tests are done: two-chunk bucket keys that meet skewed buckets fall back to one-chunk keys, those to
   // the brute-force scan. The buckets are dealt to the ranks by the plan, so every rank must take the same path: with
@@ -842,7 +851,9 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
         rp[r] = S.d_keys.p + recv_off[r];
         rb[r] = size_t(recv_off[r + 1] - recv_off[r]) * 8;
       }
+      mark("  dest scatter");
       if ((rc = comm_all_to_all(S.R, sp, sb, rp, rb, st)) != CB_OK) return rc;
+      mark("  all-to-all");
       n_keys = n_recv;
       keys = S.d_keys.p;
     } else {
@@ -858,6 +869,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
       CB_CUDA(cub::DeviceRadixSort::SortKeys(S.d_temp.p, tb, db, static_cast<long long>(n_keys), 0, end_bit, st));
       prof_end(kProfHitSort, st);
       keys = db.Current();
+      mark("  hit sort");
     }
     if ((rc = S.d_post_begin.reserve(size_t(n_rows) + 1)) != CB_OK || (rc = S.d_post_kept.reserve(size_t(n_rows) + 1)) != CB_OK ||
         (rc = S.d_post_off.reserve(size_t(n_rows) + 1)) != CB_OK)
@@ -906,11 +918,13 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
   int rc = CB_OK;
   for (int round = 0;; ++round) {
     rc = phase1();
+    mark("bucket pass");
     if (rc != CB_OK) J.failed.store(rc);
     J.bar.wait();
     if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
     if (world == 1) break;
     rc = exchange_counts();
+    mark("count exchange");
     if (rc != CB_OK) J.failed.store(rc);
     J.bar.wait();
     if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
@@ -924,6 +938,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
     else use_mih = false;
   }
   rc = phase2();
+  mark("exchange+sort+post");
   if (rc != CB_OK) J.failed.store(rc);
   if (!J.want_lists) return rc;
   J.bar.wait();  // all local totals are known
@@ -942,7 +957,9 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
   }
   J.bar.wait();  // the result buffer exists
   if (J.failed.load()) return rc != CB_OK ? rc : CB_ERR_CUDA;
-  return phase3(base);
+  rc = phase3(base);
+  mark("result copy");
+  return rc;
 }
 
 }  // namespace

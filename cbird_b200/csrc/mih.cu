@@ -639,6 +639,53 @@ __global__ void mih2_count_kernel(const uint64_t* __restrict__ hash, uint32_t n,
   }
 }
 
+// ---- grouping the rows by one chunk: a two-kernel counting sort ----------------------------------------------
+// The rows only have to be GROUPED by the value of chunk c1 (10-11 bits), not sorted, and the kernels that follow want
+// the hashes themselves in group order. So instead of keys + radix sort + gather: every CTA counts its tile of rows per
+// chunk value (mih2_hist_kernel), one exclusive scan over the (value, CTA) table gives every CTA its private slice of
+// every group, and the CTA writes hash and row straight to their places (mih2_scatter_kernel). The hashes are read twice,
+// (hash, row) written once: 28 B per row and group instead of ~100 B through the sort. With several ranks a rank simply
+// skips the rows whose group is dealt to another rank: no count has to travel to the host.
+constexpr int kPartThreads = 256;
+constexpr uint32_t kPartTile = 8192;  // rows per CTA
+
+__global__ void __launch_bounds__(kPartThreads) mih2_hist_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask,
+                                                                 uint32_t c1, uint32_t part, uint32_t n_parts, uint32_t n_cta,
+                                                                 uint32_t* __restrict__ cnt) {
+  extern __shared__ uint32_t part_smem[];  // [mask + 1]
+  for (uint32_t b = threadIdx.x; b <= mask; b += kPartThreads) part_smem[b] = 0;
+  __syncthreads();
+  const uint32_t t0 = blockIdx.x * kPartTile;
+  for (uint32_t i = t0 + threadIdx.x; i < min(n, t0 + kPartTile); i += kPartThreads) {
+    const uint32_t k = uint32_t(hash[i] >> shift) & mask;
+    if (n_parts == 1 || (k + c1) % n_parts == part) atomicAdd(&part_smem[k], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b <= mask; b += kPartThreads) cnt[size_t(b) * n_cta + blockIdx.x] = part_smem[b];
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[size_t(mask + 1) * n_cta] = 0;  // the scan's closing element = total
+}
+
+__global__ void __launch_bounds__(kPartThreads) mih2_scatter_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask,
+                                                                    uint32_t c1, uint32_t part, uint32_t n_parts, uint32_t n_cta,
+                                                                    const uint32_t* __restrict__ at, uint64_t* __restrict__ out_hash,
+                                                                    uint32_t* __restrict__ out_row, uint32_t* __restrict__ ofs) {
+  extern __shared__ uint32_t part_smem[];  // [mask + 1]: next free place of every group in this CTA's slice
+  for (uint32_t b = threadIdx.x; b <= mask; b += kPartThreads) part_smem[b] = at[size_t(b) * n_cta + blockIdx.x];
+  if (blockIdx.x == 0)  // group bounds for the bucket kernel: the first CTA's slice starts the group
+    for (uint32_t b = threadIdx.x; b <= mask + 1; b += kPartThreads) ofs[b] = at[size_t(b) * n_cta];
+  __syncthreads();
+  const uint32_t t0 = blockIdx.x * kPartTile;
+  for (uint32_t i = t0 + threadIdx.x; i < min(n, t0 + kPartTile); i += kPartThreads) {
+    const uint64_t h = hash[i];
+    const uint32_t k = uint32_t(h >> shift) & mask;
+    if (n_parts == 1 || (k + c1) % n_parts == part) {
+      const uint32_t pos = atomicAdd(&part_smem[k], 1u);
+      out_hash[pos] = h;
+      out_row[pos] = i;
+    }
+  }
+}
+
 struct L2Args {
   const uint64_t* sorted;   // hashes grouped by the value of chunk c1
   const uint32_t* rows;     // position -> row
@@ -1023,9 +1070,10 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
   unsigned long long* info = ws.info.p;
   CB_CUDA(cudaMemsetAsync(info, 0, kInfoSlots * sizeof(unsigned long long), stream));
   ws.n_batches = 1;
+  static const bool use_sort = getenv("CB_MIH2_SORT") != nullptr;  // keys + cub radix sort + gather (comparison only)
   unsigned long long m_of[kMihMaxChunks];
   for (int c1 = 0; c1 < groups; ++c1) m_of[c1] = n;
-  if (n_parts > 1) {  // how many rows of every group are dealt to this rank: one kernel, one read-back
+  if (n_parts > 1 && use_sort) {  // how many rows of every group are dealt to this rank: one kernel, one read-back
     if ((rc = ws.nblk.reserve(2 * kMihMaxChunks)) != CB_OK) return rc;
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ws.nblk.p);
     CB_CUDA(cudaMemsetAsync(d_counts, 0, kMihMaxChunks * sizeof(unsigned long long), stream));
@@ -1041,16 +1089,42 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
   const size_t max_rounds = size_t(groups);
   uint32_t n_buckets_max = 0;
   for (int c = 0; c < plan.chunks; ++c) n_buckets_max = std::max(n_buckets_max, plan.mask[c] + 1u);
-  if ((rc = ws.key.reserve(m_max)) != CB_OK || (rc = ws.key2.reserve(m_max)) != CB_OK || (rc = ws.val.reserve(m_max)) != CB_OK ||
-      (rc = ws.val2.reserve(m_max)) != CB_OK || (rc = ws.sorted.reserve(m_max + 2)) != CB_OK ||
+  if (use_sort && ((rc = ws.key.reserve(m_max)) != CB_OK || (rc = ws.key2.reserve(m_max)) != CB_OK || (rc = ws.val.reserve(m_max)) != CB_OK))
+    return rc;
+  if ((rc = ws.val2.reserve(m_max)) != CB_OK || (rc = ws.sorted.reserve(m_max + 2)) != CB_OK ||
       (rc = ws.perm.reserve(m_max * max_rounds)) != CB_OK || (rc = ws.bin_hash.reserve(m_max * max_rounds)) != CB_OK ||
       (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK)
     return rc;
+  const uint32_t n_cta = (n + kPartTile - 1) / kPartTile;
+  const size_t table = size_t(n_buckets_max) * n_cta + 1;
+  size_t scan_tb = 0;
+  if (!use_sort) {
+    if ((rc = ws.nitems.reserve(table + 1)) != CB_OK || (rc = ws.item_at.reserve(table + 1)) != CB_OK) return rc;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tb, ws.nitems.p, ws.item_at.p, static_cast<long long>(table), stream));
+    if ((rc = ws.temp.reserve(scan_tb + 16)) != CB_OK) return rc;
+  }
   for (int c1 = 0; c1 < groups; ++c1) {
     const uint32_t m = uint32_t(m_of[c1]);
     if (m < 2) continue;
     const int rounds = plan.chunks - 1 - c1;
     const uint32_t n_buckets = plan.mask[c1] + 1u;
+    if (!use_sort) {
+      const size_t smem_part = size_t(n_buckets) * sizeof(uint32_t);
+      const long long items = static_cast<long long>(size_t(n_buckets) * n_cta + 1);
+      prof_begin(kProfKeys, stream);
+      mih2_hist_kernel<<<n_cta, kPartThreads, smem_part, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part,
+                                                                  n_parts, n_cta, ws.nitems.p);
+      CB_CUDA(cudaGetLastError());
+      prof_end(kProfKeys, stream);
+      prof_begin(kProfMihSort, stream);
+      CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, scan_tb, ws.nitems.p, ws.item_at.p, items, stream));
+      prof_end(kProfMihSort, stream);
+      prof_begin(kProfGather, stream);
+      mih2_scatter_kernel<<<n_cta, kPartThreads, smem_part, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part,
+                                                                     n_parts, n_cta, ws.item_at.p, ws.sorted.p, ws.val2.p, ws.ofs.p);
+      CB_CUDA(cudaGetLastError());
+      prof_end(kProfGather, stream);
+    } else {
     prof_begin(kProfKeys, stream);
     mih2_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part, n_parts,
                                                           ws.key.p, ws.val.p, info + kKept);
@@ -1071,6 +1145,7 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     mih_bounds_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, stream>>>(ws.key2.p, m, n_buckets, ws.ofs.p);
     CB_CUDA(cudaGetLastError());
     prof_end(kProfGather, stream);
+    }
     // two CTAs per SM (228 KB per SM, ~7 KB static and 1 KB reserved per CTA): 104 KB each for the bin table and the
     // re-ordered bucket
     const size_t smem = 104 * 1024;
@@ -1079,7 +1154,7 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     CB_CUDA(cudaFuncSetAttribute(mih2_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     prof_begin(kProfMihBucket, stream);
     // buckets expected to overflow the shared-memory budget are cut into bin ranges (25 % head room for uneven buckets)
-    const double rows_per_bucket = double(m) / double(n_buckets);
+    const double rows_per_bucket = double(n) / double(n_buckets);  // whole buckets are dealt to the ranks: their size is n's
     unsigned parts = unsigned(rows_per_bucket * 1.25 / double(smem_rows)) + 1u;
     parts = std::min(parts, 64u);
     mih2_bucket_kernel<<<dim3(parts, n_buckets, unsigned(rounds)), kL2Threads, smem, stream>>>(A);
