@@ -766,6 +766,8 @@ def leg_nonuniform(cb, L, torch, dev):
             t0 = time.time()
             kept, issued = ix.similar_count(params)
             res[mode] = {"ms": (time.time() - t0) * 1e3, "hits": kept, "issued_pair_tests": issued}
+            if need < 0:
+                res[mode]["scan_variant_picked_from_a_sample"] = int(L.cb_scan64_last_variant())
         L.cb_scan64_mih_force(0, 0)
         sizes = bucket_histogram(L, h)
         res.update({"rows": int(len(h)), "distinct_hashes": int(len(np.unique(h))), "bucket_sizes": sizes,

@@ -90,6 +90,7 @@ SIGNATURES = {
     "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),
+    "cb_scan64_last_variant": (C.c_int, []),
     "cb_dct_index_create": (_vp, []),
     "cb_dct_index_destroy": (None, [_vp]),
     "cb_dct_index_load": (C.c_int, [_vp, _vp, _vp, _i64]),

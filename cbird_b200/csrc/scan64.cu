@@ -208,6 +208,41 @@ __global__ void __launch_bounds__(kThreads, 3)
 }
 
 std::atomic<int> g_forced_variant{-1};
+std::atomic<int> g_last_variant{-1};
+
+// survivor rates of the two pre-filters on a sample of this job's own pairs: the thresholds in scan64_variant_for
+// come from uniformly random hashes; real dct hashes share low-frequency bits and clustered collections hold many near
+// pairs, which both push survivors of the AND-fold (then of the OR-fold) into the exact re-test
+constexpr int kSampleThreads = 8192;
+__global__ void scan64_sample_kernel(const uint64_t* __restrict__ a, uint32_t n_a, const uint64_t* __restrict__ b, uint32_t n_b,
+                                     uint32_t b_lo, int T, unsigned* __restrict__ counts) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = 0x9E3779B97F4A7C15ull * (t + 1);  // splitmix64 per thread
+  auto next = [&]() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  unsigned s2 = 0, s1 = 0;
+  const uint32_t span = n_b - b_lo;
+  for (int k = 0; k < 16; ++k) {
+    const uint64_t x = a[next() % n_a];
+    const uint32_t j = b_lo + uint32_t(next() % span);
+    const uint64_t y0 = b[j], y1 = b[j + 1 < n_b ? j + 1 : j];
+    const uint32_t x0l = uint32_t(x ^ y0), x0h = uint32_t((x ^ y0) >> 32), x1l = uint32_t(x ^ y1), x1h = uint32_t((x ^ y1) >> 32);
+    s2 += __popc((x0l & x1l) | (x0h & x1h)) < T;
+    s1 += __popc(x0l | x0h) < T;
+  }
+  for (int off = 16; off; off >>= 1) {
+    s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    s1 += __shfl_down_sync(0xffffffffu, s1, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (s2) atomicAdd(counts, s2);
+    if (s1) atomicAdd(counts + 1, s1);
+  }
+}
 
 }  // namespace
 
@@ -220,6 +255,32 @@ int scan64_variant_for(int threshold) {
   if (threshold <= 5) return 2;
   if (threshold <= 13) return 1;
   return 0;
+}
+
+// variant for one dense scan: the threshold's default, stepped down when a sample of the job's own pairs sends more
+// than 1 in 64 warp steps... i.e. more than ~1e-3 of the tested pairs (uniform data at T = 5: 2e-4) into the exact re-test.
+// Only asked for jobs of more than 2^34 pair tests (one tiny kernel and a read-back).
+static int scan64_pick_variant(const Scan64Launch& L, int threshold, cudaStream_t stream) {
+  int v = scan64_variant_for(threshold);
+  if (g_forced_variant.load() >= 0 || v == 0 || uint64_t(L.n_a) * uint64_t(L.n_b - L.b_lo) < (1ull << 34)) return v;
+  static thread_local unsigned* d_counts[16] = {nullptr};
+  static thread_local unsigned* h_counts = nullptr;
+  const int dev = current_device() & 15;
+  if (!d_counts[dev] && cudaMalloc(&d_counts[dev], 2 * sizeof(unsigned)) != cudaSuccess) return v;
+  if (!h_counts && cudaMallocHost(&h_counts, 2 * sizeof(unsigned)) != cudaSuccess) return v;
+  if (cudaMemsetAsync(d_counts[dev], 0, 2 * sizeof(unsigned), stream) != cudaSuccess) return v;
+  scan64_sample_kernel<<<kSampleThreads / 256, 256, 0, stream>>>(L.a, L.n_a, L.b, L.n_b, L.b_lo, threshold, d_counts[dev]);
+  if (cudaMemcpyAsync(h_counts, d_counts[dev], 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaGetLastError();
+    return v;
+  }
+  const double pairs = double(kSampleThreads) * 16.0;
+  const double r2 = h_counts[0] / pairs, r1 = h_counts[1] / pairs;
+  if (v == 2 && r2 > 1.5e-3) v = 1;
+  if (v == 1 && r1 > 1.5e-3) v = 0;
+  counters().launches += 1;
+  return v;
 }
 
 int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
@@ -265,8 +326,10 @@ int scan64_launch(const Scan64Launch& L, cudaStream_t stream) {
   P.slab = tiles_per_slab * kBTile;
 
   dim3 grid(a_blocks, slabs), block(kThreads);
+  const int variant = scan64_pick_variant(L, P.threshold, stream);
+  g_last_variant.store(variant);
   prof_begin(kProfScan, stream);
-  switch (scan64_variant_for(P.threshold)) {
+  switch (variant) {
     case 2: scan64_kernel<2><<<grid, block, 0, stream>>>(P); break;
     case 1: scan64_kernel<1><<<grid, block, 0, stream>>>(P); break;
     default: scan64_kernel<0><<<grid, block, 0, stream>>>(P); break;
@@ -359,6 +422,8 @@ int cb_scan64_self_dev(const uint64_t* d_hashes, uint32_t n, uint32_t row_begin,
 }
 
 int cb_scan64_variant(int threshold) { return scan64_variant_for(threshold > 65 ? 65 : threshold); }
+
+int cb_scan64_last_variant(void) { return g_last_variant.load(); }
 
 void cb_scan64_force_variant(int variant) { g_forced_variant.store(variant); }
 

@@ -227,6 +227,10 @@ int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks);
 /* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
  * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
 int cb_scan64_variant(int threshold);
+/* variant the last dense scan of this process really ran: for jobs over 2^34 pair tests the default is stepped down
+ * (2 -> 1 -> 0) when a sample of the job's own pairs shows that the cheaper pre-filter lets too many pairs through
+ * (clustered or correlated hashes); -1 before any scan */
+int cb_scan64_last_variant(void);
 /* force a variant (-1 = automatic); for measurements and parity tests */
 void cb_scan64_force_variant(int variant);
 

@@ -90,3 +90,41 @@ def test_overflow_is_reported_not_silent(cb):
     assert cb.lib().cb_scan64_dev(da.data_ptr(), 4096, da.data_ptr(), 4096, 5, 0, out.data_ptr(), 100, cnt.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert int(cnt.item()) >= 4096  # the total is always counted; only the first `cap` hits are stored
+
+
+def test_sampled_variant_choice_is_exact_on_clustered_hashes(cb):
+    # jobs over 2^34 pair tests sample their own pairs and step the pre-filter down when too many would survive it
+    # (clustered hashes); whatever it picks, the hit set is the exact variant's
+    import torch
+
+    L = cb.lib()
+    rng = np.random.default_rng(9)
+    centres = rng.integers(0, 2 ** 63, size=100, dtype=np.uint64) << np.uint64(1)
+    h = np.repeat(centres, 2000)
+    for k in range(8):
+        bits = rng.integers(1, 64, size=len(h)).astype(np.uint64)
+        h ^= np.where(rng.random(len(h)) < 0.7, np.uint64(1) << bits, np.uint64(0)).astype(np.uint64)
+    n = len(h)  # 200 000 rows: 4e10 pair tests; same-cluster pairs are ~11 bits apart: few hits, many AND-fold survivors
+    d = torch.from_numpy(h.view(np.int64)).cuda()
+    cap = 1 << 23
+    out = torch.empty((cap, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def run():
+        cnt.zero_()
+        assert L.cb_scan64_dev(d.data_ptr(), n, d.data_ptr(), n, 5, 0, out.data_ptr(), cap, cnt.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        m = int(cnt.item())
+        assert m <= cap
+        t = out[:m].cpu().numpy().astype(np.int64)[:, :3]
+        return t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))]
+
+    got = run()
+    picked = L.cb_scan64_last_variant()
+    try:
+        L.cb_scan64_force_variant(0)
+        want = run()
+    finally:
+        L.cb_scan64_force_variant(-1)
+    assert picked == 1   # 1 % of all pairs sit in one cluster: 0.5 % of the AND-fold tests would survive, 0.01 % of the OR-fold's
+    assert np.array_equal(got, want) and len(want) > n
