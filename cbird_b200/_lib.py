@@ -87,6 +87,7 @@ SIGNATURES = {
     "cb_scan64_mih_force": (None, [C.c_int, C.c_int]),
     "cb_scan64_mih_config": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cb_scan64_mih_plan": (C.c_int, [C.c_int, _vp, _vp]),
+    "cb_scan64_mih_plan2": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "cb_scan64_tiles_dev": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cb_scan64_variant": (C.c_int, [C.c_int]),
     "cb_scan64_force_variant": (None, [C.c_int]),

@@ -1372,6 +1372,23 @@ int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks) {
   CB_API_END
 }
 
+int cb_scan64_mih_plan2(int threshold, int32_t* shifts, uint32_t* masks, int32_t* unit_c1, int32_t* unit_c2) {
+  if (threshold < 1 || threshold > kMihMaxThreshold) {
+    set_error("cb_scan64_mih_plan2: threshold %d outside [1, %d]", threshold, kMihMaxThreshold);
+    return CB_ERR_UNSUPPORTED;
+  }
+  const MihPlan p = mih_plan(threshold, 2);
+  for (int c = 0; c < p.chunks; ++c) {
+    if (shifts) shifts[c] = p.shift[c];
+    if (masks) masks[c] = p.mask[c];
+  }
+  for (int u = 0; u < p.units; ++u) {
+    if (unit_c1) unit_c1[u] = p.u_c1[u];
+    if (unit_c2) unit_c2[u] = p.u_c2[u];
+  }
+  return p.units;
+}
+
 void cb_scan64_mih_force(int variant, int need) {
   g_forced_bucket_variant = variant;
   g_forced_need = need;

@@ -224,6 +224,10 @@ int cb_scan64_mih_config(uint64_t n, int threshold, int* variant, int* need);
 /* the bucket layout the self-join uses for a threshold (host only, no device needed): chunk c of a hash is
  * (h >> shifts[c]) & masks[c]; returns the number of chunks (== threshold) or a negative status */
 int cb_scan64_mih_plan(int threshold, int32_t* shifts, uint32_t* masks);
+/* the two-chunk layout (threshold + 1 chunks, a bucket = the values of a PAIR of chunks): fills the chunk table
+ * (threshold + 1 entries) and the units (pairs c1 < c2 in lexicographic order); returns the number of units
+ * (threshold + 1) * threshold / 2. Host only. */
+int cb_scan64_mih_plan2(int threshold, int32_t* shifts, uint32_t* masks, int32_t* unit_c1, int32_t* unit_c2);
 /* variant index actually used for a threshold: 0 exact (2 POPC/pair), 1 OR-fold prefilter (1 POPC/pair),
  * 2 AND-fold prefilter (0.5 POPC/pair); all three produce identical hit sets */
 int cb_scan64_variant(int threshold);
