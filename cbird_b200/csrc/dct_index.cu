@@ -399,7 +399,7 @@ struct FindSlot {
   char err[160] = "";
 };
 
-constexpr int kFindCtxMax = 8;
+constexpr int kFindCtxMax = 32;
 
 struct FindCtx {  // one batch in flight
   cudaStream_t stream = nullptr;
@@ -408,6 +408,7 @@ struct FindCtx {  // one batch in flight
   unsigned long long* d_ctr = nullptr;
   unsigned long long seq = 0;
   bool busy = false;
+  int shard = 0;  // which replica of the index (device) this context scans
 };
 
 struct FindQueue {
@@ -421,12 +422,14 @@ struct FindQueue {
   // longer than a few microseconds take the cores the shepherds need
   int n_ctx = 3;       // batches in flight at most (CB_FIND_CTX)
   int spin_us = 5;     // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
-  int device = 0;
+  int device[kFindCtxMax] = {0};
   bool ready = false;
   std::atomic<uint64_t> batches{0}, needles{0};
   ~FindQueue() {
-    if (ready) cudaSetDevice(device);
-    for (FindCtx& c : ctx) {
+    for (int i = 0; i < kFindCtxMax; ++i) {
+      FindCtx& c = ctx[i];
+      if (!c.stream && !c.h_out && !c.d_ctr) continue;
+      cudaSetDevice(device[i]);
       if (c.h_out) cudaFreeHost(c.h_out);
       if (c.d_ctr) cudaFree(c.d_ctr);
       if (c.stream) cudaStreamDestroy(c.stream);
@@ -1020,13 +1023,16 @@ int run_find_batch(DctIndex& I, const uint64_t* needles, int64_t nq, int thresho
 int fq_init(DctIndex& I) {
   FindQueue& Q = I.fq;
   if (Q.ready) return CB_OK;
-  DctShard& S = I.s0();
-  Q.device = S.R.device;
-  if (const char* e = getenv("CB_FIND_CTX")) Q.n_ctx = std::max(1, std::min(kFindCtxMax, atoi(e)));
+  if (const char* e = getenv("CB_FIND_CTX")) Q.n_ctx = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("CB_FIND_SPIN_US")) Q.spin_us = std::max(0, atoi(e));
-  CB_CUDA(cudaSetDevice(Q.device));
+  // every replica of the index (cb_init: one per device) serves batches: contexts are dealt round-robin to the devices
+  const int per_dev = Q.n_ctx;
+  Q.n_ctx = std::min<int>(kFindCtxMax, per_dev * int(I.shards.size()));
   for (int i = 0; i < Q.n_ctx; ++i) {
     FindCtx& c = Q.ctx[i];
+    c.shard = i % int(I.shards.size());
+    Q.device[i] = I.shards[size_t(c.shard)]->R.device;
+    CB_CUDA(cudaSetDevice(Q.device[i]));
     CB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CB_CUDA(cudaHostAlloc(&c.h_out, sizeof(FindOut), cudaHostAllocMapped | cudaHostAllocPortable));
     memset(c.h_out, 0, sizeof(FindOut));
@@ -1049,7 +1055,7 @@ void fq_run_batch(DctIndex& I, FindCtx& c, FindSlot** batch, int nb, int thresho
   int rc = CB_OK;
   {
     std::shared_lock<std::shared_mutex> rd(I.rw);
-    DctShard& S = I.s0();
+    DctShard& S = *I.shards[size_t(c.shard)];
     const uint32_t n = uint32_t(I.n);
     auto launch = [&]() -> int {
       if (!I.loaded) {
@@ -1057,7 +1063,7 @@ void fq_run_batch(DctIndex& I, FindCtx& c, FindSlot** batch, int nb, int thresho
         return CB_ERR_NOT_LOADED;
       }
       if (!n || threshold <= 0) return CB_OK;
-      CB_CUDA(cudaSetDevice(Q.device));
+      CB_CUDA(cudaSetDevice(S.R.device));
       FindNeedles N;
       for (int i = 0; i < nb; ++i) N.h[i] = batch[i]->hash;
       const int T = std::min(threshold, 65);

@@ -117,6 +117,17 @@ def test_cb_init_one_process_all_devices(cb, po):
                 g = hits[off[row]:off[row + 1]]
                 assert g["score"].tolist() == os_[:k].tolist(), row
                 assert g["mediaId"].tolist() == oi[:k].tolist(), row
+        # find() batches are served by every replica in turn
+        from concurrent.futures import ThreadPoolExecutor
+
+        rows = [int(r) for r in np.random.default_rng(3).integers(0, n, 64) if ids[int(r)] != 0]
+        with ThreadPoolExecutor(8) as ex:
+            res = list(ex.map(lambda r: ix.find(cb.Media(dctHash=int(h[r])), cb.SearchParams(dctThresh=5)), rows))
+        O = po.oracle()
+        oi, os_ = np.zeros(4096, np.uint32), np.zeros(4096, np.int32)
+        for r, m in zip(rows, res):
+            k = O.orc_dct_find(h, ids, n, int(h[r]), 5, oi, os_, 4096)
+            assert sorted((x.score, x.mediaId) for x in m) == sorted(zip(os_[:k].tolist(), oi[:k].tolist())), r
         # add / remove reach every replica
         ix.add([cb.Media(id=n + 7, dctHash=int(h[5]))])
         ix.remove([int(ids[6])])
