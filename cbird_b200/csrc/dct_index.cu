@@ -407,15 +407,15 @@ struct FindCtx {  // one batch in flight
   FindOut* d_out = nullptr;  // the same memory as the device sees it
   unsigned long long* d_ctr = nullptr;
   unsigned long long seq = 0;
-  bool busy = false;
+  std::atomic<int> busy{0};  // taken by the leader under the queue mutex, released by the shepherd without it
   int shard = 0;  // which replica of the index (device) this context scans
 };
 
 struct FindQueue {
   std::mutex mu;
   std::deque<FindSlot*> waiting;
-  std::vector<FindSlot*> free_slots;
-  std::vector<std::unique_ptr<FindSlot>> all_slots;
+  std::vector<std::unique_ptr<FindSlot>> all_slots;  // one per (calling thread, index): cached by the thread, freed with the index
+  uint64_t serial = 0;                               // identifies this queue in the threads' slot caches
   bool leader_active = false;
   FindCtx ctx[kFindCtxMax];
   // measured with tools/find_bench.cpp on a 16-core host (profiles/find_bench_r02.txt): waiting callers that spin
@@ -1121,10 +1121,7 @@ void fq_run_batch(DctIndex& I, FindCtx& c, FindSlot** batch, int nb, int thresho
         for (const cb_hit& h : all) batch[h.needle]->hits.push_back(h);
     }
   }
-  {
-    std::lock_guard<std::mutex> lock(Q.mu);
-    c.busy = false;  // the next batch may use this context while the owners are being woken
-  }
+  c.busy.store(0);  // the next batch may use this context while the owners are being woken
   Q.batches.fetch_add(1, std::memory_order_relaxed);
   Q.needles.fetch_add(uint64_t(nb), std::memory_order_relaxed);
   // done: states are published last slot first, so that whoever sees its own request done also sees the requests
@@ -1143,20 +1140,33 @@ void fq_run_batch(DctIndex& I, FindCtx& c, FindSlot** batch, int nb, int thresho
 
 int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit>& out) {
   FindQueue& Q = I.fq;
+  // the calling thread's request slot for this index: found in a small thread-local cache (no lock), made on first use.
+  // Slots live as long as the index, so a late wake-up from another thread never touches freed memory.
+  struct SlotCache {
+    uint64_t serial[8] = {0};
+    FindSlot* slot[8] = {nullptr};
+    unsigned next = 0;
+  };
+  static thread_local SlotCache cache;
+  static std::atomic<uint64_t> g_serial{0};
   FindSlot* me = nullptr;
   bool lead = false;
+  if (Q.ready)
+    for (int i = 0; i < 8; ++i)
+      if (cache.serial[i] == Q.serial && cache.slot[i]) me = cache.slot[i];
   {
     std::lock_guard<std::mutex> lock(Q.mu);
     if (!Q.ready) {
       int rc = fq_init(I);
       if (rc != CB_OK) return rc;
+      Q.serial = ++g_serial;
     }
-    if (Q.free_slots.empty()) {
+    if (!me) {
       Q.all_slots.emplace_back(new FindSlot);
       me = Q.all_slots.back().get();
-    } else {
-      me = Q.free_slots.back();
-      Q.free_slots.pop_back();
+      cache.serial[cache.next & 7] = Q.serial;
+      cache.slot[cache.next & 7] = me;
+      ++cache.next;
     }
     me->hash = hash;
     me->threshold = threshold;
@@ -1197,7 +1207,7 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
     for (unsigned spin = 0; !c; ++spin) {
       std::unique_lock<std::mutex> lock(Q.mu);
       for (int i = 0; i < Q.n_ctx && !c; ++i)
-        if (!Q.ctx[i].busy) c = &Q.ctx[i];
+        if (!Q.ctx[i].busy.load()) c = &Q.ctx[i];
       if (!c) {
         lock.unlock();
         _mm_pause();
@@ -1215,7 +1225,7 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
           }
         }
       }
-      if (nb) c->busy = true;
+      if (nb) c->busy.store(1);
       if (Q.waiting.empty()) {
         Q.leader_active = false;
       } else {  // the oldest request left behind leads the next batch
@@ -1237,10 +1247,6 @@ int find_via_queue(DctIndex& I, uint64_t hash, int threshold, std::vector<cb_hit
   int rc = me->rc;
   if (rc != CB_OK) set_error("%s", me->err);
   out.swap(me->hits);
-  {
-    std::lock_guard<std::mutex> lock(Q.mu);
-    Q.free_slots.push_back(me);
-  }
   return rc;
 }
 

@@ -649,92 +649,124 @@ __global__ void mih2_count_kernel(const uint64_t* __restrict__ hash, uint32_t n,
 constexpr int kPartThreads = 256;
 constexpr uint32_t kPartTile = 7680;  // rows per CTA: 15 per thread of the scatter kernel, two of its CTAs per SM
 
-__global__ void __launch_bounds__(kPartThreads) mih2_hist_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask,
-                                                                 uint32_t c1, uint32_t part, uint32_t n_parts, uint32_t n_cta,
-                                                                 uint32_t* __restrict__ cnt) {
-  extern __shared__ uint32_t part_smem[];  // [mask + 1]
-  for (uint32_t b = threadIdx.x; b <= mask; b += kPartThreads) part_smem[b] = 0;
+// All groups in one pass over the hashes: the tile's rows are read once (histogram kernel) / held in registers (scatter
+// kernel) while the CTA goes through the chunk groups one after the other. With N ranks every rank has to look at every
+// row of every group to find its own, so what does not shrink with N is this read: one pass instead of one per group.
+constexpr int kScatThreads = 512;
+
+struct PartGroups {
+  int groups;
+  int shift[kMihMaxChunks];
+  uint32_t mask[kMihMaxChunks];
+  uint32_t bin_at[kMihMaxChunks + 1];   // start of group g's bins in the histogram kernel's shared memory
+  size_t table_at[kMihMaxChunks + 1];   // start of group g's (value, CTA) table (nb_g * n_cta + 1 entries)
+};
+
+__global__ void __launch_bounds__(kPartThreads) mih2_hist_all_kernel(const uint64_t* __restrict__ hash, uint32_t n, const PartGroups G,
+                                                                     uint32_t part, uint32_t n_parts, uint32_t n_cta,
+                                                                     uint32_t* __restrict__ cnt) {
+  extern __shared__ uint32_t part_smem[];  // [bin_at[groups]]
+  const uint32_t bins = G.bin_at[G.groups];
+  for (uint32_t b = threadIdx.x; b < bins; b += kPartThreads) part_smem[b] = 0;
   __syncthreads();
   const uint32_t t0 = blockIdx.x * kPartTile;
   for (uint32_t i = t0 + threadIdx.x; i < min(n, t0 + kPartTile); i += kPartThreads) {
-    const uint32_t k = uint32_t(hash[i] >> shift) & mask;
-    if (n_parts == 1 || (k + c1) % n_parts == part) atomicAdd(&part_smem[k], 1u);
+    const uint64_t h = hash[i];
+#pragma unroll
+    for (int g = 0; g < kMihMaxChunks; ++g)
+      if (g < G.groups) {
+        const uint32_t k = uint32_t(h >> G.shift[g]) & G.mask[g];
+        if (n_parts == 1 || (k + uint32_t(g)) % n_parts == part) atomicAdd(&part_smem[G.bin_at[g] + k], 1u);
+      }
   }
   __syncthreads();
-  for (uint32_t b = threadIdx.x; b <= mask; b += kPartThreads) cnt[size_t(b) * n_cta + blockIdx.x] = part_smem[b];
-  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[size_t(mask + 1) * n_cta] = 0;  // the scan's closing element = total
+#pragma unroll
+  for (int g = 0; g < kMihMaxChunks; ++g)
+    if (g < G.groups) {
+      const uint32_t nb = G.mask[g] + 1u;
+      uint32_t* t = cnt + G.table_at[g];
+      for (uint32_t b = threadIdx.x; b < nb; b += kPartThreads) t[size_t(b) * n_cta + blockIdx.x] = part_smem[G.bin_at[g] + b];
+      if (blockIdx.x == 0 && threadIdx.x == 0) t[size_t(nb) * n_cta] = 0;  // the scan's closing element = the group's total
+    }
 }
 
-// The tile is first put in group order in shared memory, then written out: neighbouring threads then write neighbouring
-// rows of one group, so a group's few rows from this tile leave as one or two sectors instead of one partial write per
-// row (ncu on the direct scatter: 2x the algorithmic DRAM bytes and 22 % DRAM throughput at 2 % issue activity).
-constexpr int kScatThreads = 512;
 __global__ void __launch_bounds__(kScatThreads, 2)
-    mih2_scatter_kernel(const uint64_t* __restrict__ hash, uint32_t n, int shift, uint32_t mask, uint32_t c1, uint32_t part,
-                        uint32_t n_parts, uint32_t n_cta, const uint32_t* __restrict__ at, uint64_t* __restrict__ out_hash,
-                        uint32_t* __restrict__ out_row, uint32_t* __restrict__ ofs) {
-  extern __shared__ __align__(16) unsigned char scat_smem[];  // H[tile] u64 | R[tile] u32 | cur[nb] | gofs[nb]
+    mih2_scatter_all_kernel(const uint64_t* __restrict__ hash, uint32_t n, const PartGroups G, uint32_t part, uint32_t n_parts,
+                            uint32_t n_cta, const uint32_t* __restrict__ at_all, uint64_t* __restrict__ out_hash,
+                            uint32_t* __restrict__ out_row, uint32_t* __restrict__ ofs_all, uint32_t ofs_stride) {
+  extern __shared__ __align__(16) unsigned char scat_smem[];  // H[tile] u64 | R[tile] u32 | cur[nb_max] | gofs[nb_max]
   uint64_t* H = reinterpret_cast<uint64_t*>(scat_smem);
   uint32_t* R = reinterpret_cast<uint32_t*>(scat_smem + size_t(kPartTile) * 8);
   uint32_t* cur = R + kPartTile;
-  uint32_t* gofs = cur + (mask + 1);
   __shared__ uint32_t part_sum[kScatThreads];
-  const uint32_t nb = mask + 1;
-  for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) cur[b] = 0;
-  if (blockIdx.x == 0)  // group bounds for the bucket kernel: the first CTA's slice starts the group
-    for (uint32_t b = threadIdx.x; b <= nb; b += kScatThreads) ofs[b] = at[size_t(b) * n_cta];
-  __syncthreads();
   constexpr int kPer = kPartTile / kScatThreads;  // rows per thread
   const uint32_t t0 = blockIdx.x * kPartTile;
   uint64_t h[kPer];
-  uint32_t bin[kPer];
 #pragma unroll
   for (int k = 0; k < kPer; ++k) {
     const uint32_t i = t0 + threadIdx.x + k * kScatThreads;
     h[k] = i < n ? hash[i] : 0;
-    const uint32_t v = uint32_t(h[k] >> shift) & mask;
-    bin[k] = (i < n && (n_parts == 1 || (v + c1) % n_parts == part)) ? v : 0xFFFFFFFFu;
-    if (bin[k] != 0xFFFFFFFFu) atomicAdd(&cur[v], 1u);
   }
-  __syncthreads();
-  {  // exclusive scan of cur[0..nb) in place
-    const uint32_t per = (nb + kScatThreads - 1) / kScatThreads;
-    const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
-    uint32_t acc = 0;
-    for (uint32_t b = b0; b < b1; ++b) acc += cur[b];
-    part_sum[threadIdx.x] = acc;
+  for (int g = 0; g < G.groups; ++g) {
+    const int shift = G.shift[g];
+    const uint32_t mask = G.mask[g], nb = mask + 1u;
+    uint32_t* gofs = cur + nb;
+    const uint32_t* at = at_all + G.table_at[g];
+    uint64_t* oh = out_hash + size_t(g) * n;
+    uint32_t* orow = out_row + size_t(g) * n;
+    __syncthreads();  // the previous group's write-out is done with H / R / cur
+    for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) cur[b] = 0;
+    if (blockIdx.x == 0)  // group bounds for the bucket kernel: the first CTA's slice starts the group
+      for (uint32_t b = threadIdx.x; b <= nb; b += kScatThreads) ofs_all[size_t(g) * ofs_stride + b] = at[size_t(b) * n_cta];
     __syncthreads();
-    for (int off = 1; off < kScatThreads; off <<= 1) {
-      const uint32_t v = int(threadIdx.x) >= off ? part_sum[threadIdx.x - off] : 0u;
-      __syncthreads();
-      part_sum[threadIdx.x] += v;
-      __syncthreads();
-    }
-    uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
-    for (uint32_t b = b0; b < b1; ++b) {
-      const uint32_t c = cur[b];
-      cur[b] = run;
-      run += c;
-    }
-  }
-  const uint32_t total = part_sum[kScatThreads - 1];
-  __syncthreads();
-  // where this CTA's slice of group b starts in the output, minus where the group starts in the tile
-  for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) gofs[b] = at[size_t(b) * n_cta + blockIdx.x] - cur[b];
-  __syncthreads();
+    uint32_t bin[kPer];
 #pragma unroll
-  for (int k = 0; k < kPer; ++k)
-    if (bin[k] != 0xFFFFFFFFu) {
-      const uint32_t pos = atomicAdd(&cur[bin[k]], 1u);
-      H[pos] = h[k];
-      R[pos] = t0 + threadIdx.x + k * kScatThreads;
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t i = t0 + threadIdx.x + k * kScatThreads;
+      const uint32_t v = uint32_t(h[k] >> shift) & mask;
+      bin[k] = (i < n && (n_parts == 1 || (v + uint32_t(g)) % n_parts == part)) ? v : 0xFFFFFFFFu;
+      if (bin[k] != 0xFFFFFFFFu) atomicAdd(&cur[v], 1u);
     }
-  __syncthreads();
-  for (uint32_t j = threadIdx.x; j < total; j += kScatThreads) {
-    const uint64_t v = H[j];
-    const uint32_t dst = gofs[uint32_t(v >> shift) & mask] + j;
-    out_hash[dst] = v;
-    out_row[dst] = R[j];
+    __syncthreads();
+    {  // exclusive scan of cur[0..nb) in place
+      const uint32_t per = (nb + kScatThreads - 1) / kScatThreads;
+      const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+      uint32_t acc = 0;
+      for (uint32_t b = b0; b < b1; ++b) acc += cur[b];
+      part_sum[threadIdx.x] = acc;
+      __syncthreads();
+      for (int off = 1; off < kScatThreads; off <<= 1) {
+        const uint32_t v = int(threadIdx.x) >= off ? part_sum[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part_sum[threadIdx.x] += v;
+        __syncthreads();
+      }
+      uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
+      for (uint32_t b = b0; b < b1; ++b) {
+        const uint32_t c = cur[b];
+        cur[b] = run;
+        run += c;
+      }
+    }
+    const uint32_t total = part_sum[kScatThreads - 1];
+    __syncthreads();
+    // where this CTA's slice of group value b starts in the output, minus where that value starts in the tile
+    for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) gofs[b] = at[size_t(b) * n_cta + blockIdx.x] - cur[b];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (bin[k] != 0xFFFFFFFFu) {
+        const uint32_t pos = atomicAdd(&cur[bin[k]], 1u);
+        H[pos] = h[k];
+        R[pos] = t0 + threadIdx.x + k * kScatThreads;
+      }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < total; j += kScatThreads) {
+      const uint64_t v = H[j];
+      const uint32_t dst = gofs[uint32_t(v >> shift) & mask] + j;
+      oh[dst] = v;
+      orow[dst] = R[j];
+    }
   }
 }
 
@@ -1148,37 +1180,60 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
       (rc = ws.ofs.reserve(n_buckets_max + 2)) != CB_OK)
     return rc;
   const uint32_t n_cta = (n + kPartTile - 1) / kPartTile;
-  const size_t table = size_t(n_buckets_max) * n_cta + 1;
-  size_t scan_tb = 0;
+  const uint32_t ofs_stride = n_buckets_max + 2;
+  PartGroups PG;
+  memset(&PG, 0, sizeof(PG));
   if (!use_sort) {
-    if ((rc = ws.nitems.reserve(table + 1)) != CB_OK || (rc = ws.item_at.reserve(table + 1)) != CB_OK) return rc;
-    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tb, ws.nitems.p, ws.item_at.p, static_cast<long long>(table), stream));
+    // one (value, CTA) count table per group, one pass over the hashes for all of them, one scan per group, one more
+    // pass that writes every group's (hash, row) arrays
+    PG.groups = groups;
+    size_t table_total = 0;
+    uint32_t bins_total = 0;
+    for (int g = 0; g < groups; ++g) {
+      PG.shift[g] = plan.shift[g];
+      PG.mask[g] = plan.mask[g];
+      PG.bin_at[g] = bins_total;
+      PG.table_at[g] = table_total;
+      bins_total += plan.mask[g] + 1u;
+      table_total += size_t(plan.mask[g] + 1u) * n_cta + 1;
+    }
+    PG.bin_at[groups] = bins_total;
+    PG.table_at[groups] = table_total;
+    if ((rc = ws.nitems.reserve(table_total + 1)) != CB_OK || (rc = ws.item_at.reserve(table_total + 1)) != CB_OK ||
+        (rc = ws.sorted.reserve(size_t(n) * groups + 2)) != CB_OK || (rc = ws.val2.reserve(size_t(n) * groups)) != CB_OK ||
+        (rc = ws.ofs.reserve(size_t(ofs_stride) * groups)) != CB_OK)
+      return rc;
+    size_t scan_tb = 0;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tb, ws.nitems.p, ws.item_at.p, static_cast<long long>(size_t(n_buckets_max) * n_cta + 1), stream));
     if ((rc = ws.temp.reserve(scan_tb + 16)) != CB_OK) return rc;
+    CB_CUDA(cudaFuncSetAttribute(mih2_hist_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(bins_total) * sizeof(uint32_t))));
+    prof_begin(kProfKeys, stream);
+    mih2_hist_all_kernel<<<n_cta, kPartThreads, size_t(bins_total) * sizeof(uint32_t), stream>>>(d_hashes, n, PG, part, n_parts, n_cta,
+                                                                                                  ws.nitems.p);
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfKeys, stream);
+    prof_begin(kProfMihSort, stream);
+    for (int g = 0; g < groups; ++g) {
+      size_t tb = scan_tb;
+      CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, tb, ws.nitems.p + PG.table_at[g], ws.item_at.p + PG.table_at[g],
+                                            static_cast<long long>(size_t(plan.mask[g] + 1u) * n_cta + 1), stream));
+    }
+    prof_end(kProfMihSort, stream);
+    prof_begin(kProfGather, stream);
+    const size_t smem_scat = size_t(kPartTile) * 12 + size_t(n_buckets_max) * 8;
+    CB_CUDA(cudaFuncSetAttribute(mih2_scatter_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_scat)));
+    mih2_scatter_all_kernel<<<n_cta, kScatThreads, smem_scat, stream>>>(d_hashes, n, PG, part, n_parts, n_cta, ws.item_at.p, ws.sorted.p,
+                                                                       ws.val2.p, ws.ofs.p, ofs_stride);
+    CB_CUDA(cudaGetLastError());
+    prof_end(kProfGather, stream);
+    counters().launches += 2 + groups;
   }
   for (int c1 = 0; c1 < groups; ++c1) {
     const uint32_t m = uint32_t(m_of[c1]);
     if (m < 2) continue;
     const int rounds = plan.chunks - 1 - c1;
     const uint32_t n_buckets = plan.mask[c1] + 1u;
-    if (!use_sort) {
-      const size_t smem_part = size_t(n_buckets) * sizeof(uint32_t);
-      const long long items = static_cast<long long>(size_t(n_buckets) * n_cta + 1);
-      prof_begin(kProfKeys, stream);
-      mih2_hist_kernel<<<n_cta, kPartThreads, smem_part, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part,
-                                                                  n_parts, n_cta, ws.nitems.p);
-      CB_CUDA(cudaGetLastError());
-      prof_end(kProfKeys, stream);
-      prof_begin(kProfMihSort, stream);
-      CB_CUDA(cub::DeviceScan::ExclusiveSum(ws.temp.p, scan_tb, ws.nitems.p, ws.item_at.p, items, stream));
-      prof_end(kProfMihSort, stream);
-      prof_begin(kProfGather, stream);
-      const size_t smem_scat = size_t(kPartTile) * 12 + size_t(n_buckets) * 8;
-      CB_CUDA(cudaFuncSetAttribute(mih2_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_scat)));
-      mih2_scatter_kernel<<<n_cta, kScatThreads, smem_scat, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part,
-                                                                     n_parts, n_cta, ws.item_at.p, ws.sorted.p, ws.val2.p, ws.ofs.p);
-      CB_CUDA(cudaGetLastError());
-      prof_end(kProfGather, stream);
-    } else {
+    if (use_sort) {
     prof_begin(kProfKeys, stream);
     mih2_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, n, plan.shift[c1], plan.mask[c1], uint32_t(c1), part, n_parts,
                                                           ws.key.p, ws.val.p, info + kKept);
@@ -1204,7 +1259,9 @@ static int scan64_self_mih2(const uint64_t* d_hashes, uint32_t n, int threshold,
     // re-ordered bucket
     const size_t smem = 104 * 1024;
     const uint32_t smem_rows = uint32_t((smem - size_t(n_buckets_max) * 4) / 12) & ~31u;
-    L2Args A{ws.sorted.p, ws.val2.p, ws.ofs.p, ws.bin_hash.p, ws.perm.p, m, n_buckets_max, smem_rows, info, plan, c1, threshold, out};
+    const size_t goff = use_sort ? 0 : size_t(c1);  // the fused partition keeps one set of arrays per group
+    L2Args A{ws.sorted.p + goff * n, ws.val2.p + goff * n, ws.ofs.p + goff * ofs_stride, ws.bin_hash.p, ws.perm.p, m, n_buckets_max, smem_rows,
+             info, plan, c1, threshold, out};
     CB_CUDA(cudaFuncSetAttribute(mih2_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     prof_begin(kProfMihBucket, stream);
     // buckets expected to overflow the shared-memory budget are cut into bin ranges (25 % head room for uneven buckets)
