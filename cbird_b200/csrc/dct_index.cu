@@ -143,9 +143,20 @@ struct SimilarPost {
   int dht, max_thresh, min_matches, max_matches, filter_self, escalate;
 };
 
+// first key of every needle row of this rank: one thread per key marks the heads of the runs (keys are sorted by needle,
+// score, id). Rows without any key keep the memset's 0, which the post step treats as "no run" (the needle test fails).
+__global__ void similar_run_heads(const unsigned long long* __restrict__ keys, unsigned long long n_keys, int needle_shift,
+                                  uint32_t row0, uint32_t n_rows, unsigned long long* __restrict__ begin) {
+  const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (j >= n_keys) return;
+  const uint32_t needle = uint32_t(keys[j] >> needle_shift);
+  if (j && uint32_t(keys[j - 1] >> needle_shift) == needle) return;
+  if (needle >= row0 && needle - row0 < n_rows) begin[needle - row0] = j;
+}
+
 __global__ void similar_post_count(const unsigned long long* __restrict__ keys, unsigned long long n_keys, KeyLayout L,
                                    const uint64_t* __restrict__ row_hash, const uint32_t* __restrict__ row_id, uint32_t row0,
-                                   uint32_t n_rows, SimilarPost P, unsigned long long* __restrict__ begin,
+                                   uint32_t n_rows, SimilarPost P, const unsigned long long* __restrict__ begin,
                                    long long* __restrict__ kept) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n_rows) return;
@@ -154,13 +165,7 @@ __global__ void similar_post_count(const unsigned long long* __restrict__ keys, 
     return;
   }
   const uint32_t row = row0 + i;
-  const unsigned long long first = (unsigned long long)row << L.needle_shift;
-  unsigned long long lo = 0, hi = n_keys;  // first key of this needle (keys are sorted by needle, score, id)
-  while (lo < hi) {
-    const unsigned long long mid = lo + ((hi - lo) >> 1);
-    if (keys[mid] < first) lo = mid + 1; else hi = mid;
-  }
-  begin[i] = lo;
+  const unsigned long long lo = begin[i];
   int t = P.dht;
   long long k = 0;
   if (row_hash[row] != 0) {  // needles without hash find nothing (dcthashindex.cpp:196-200)
@@ -420,8 +425,8 @@ struct FindQueue {
   FindCtx ctx[kFindCtxMax];
   // measured with tools/find_bench.cpp on a 16-core host (profiles/find_bench_r02.txt): waiting callers that spin
   // longer than a few microseconds take the cores the shepherds need
-  int n_ctx = 3;       // batches in flight at most (CB_FIND_CTX)
-  int spin_us = 5;     // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
+  int n_ctx = 4;       // batches in flight at most, per device (CB_FIND_CTX)
+  int spin_us = 2;     // a waiting caller spins this long before it sleeps (CB_FIND_SPIN_US)
   int device[kFindCtxMax] = {0};
   bool ready = false;
   std::atomic<uint64_t> batches{0}, needles{0};
@@ -878,6 +883,11 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
         (rc = S.d_post_off.reserve(size_t(n_rows) + 1)) != CB_OK)
       return rc;
     prof_begin(kProfPost, st);
+    CB_CUDA(cudaMemsetAsync(S.d_post_begin.p, 0, (size_t(n_rows) + 1) * sizeof(unsigned long long), st));
+    if (n_keys) {
+      similar_run_heads<<<unsigned((n_keys + 255) / 256), 256, 0, st>>>(keys, n_keys, J.L.needle_shift, r0, n_rows, S.d_post_begin.p);
+      CB_CUDA(cudaGetLastError());
+    }
     similar_post_count<<<post_blocks, 256, 0, st>>>(keys, n_keys, J.L, S.d_hashes.p, S.d_ids.p, r0, n_rows, J.P, S.d_post_begin.p,
                                                    S.d_post_kept.p);
     CB_CUDA(cudaGetLastError());
