@@ -56,17 +56,22 @@ def load_peaks():
         return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full summaries (profiles/ncu_*_r02.json)."""
+def committed_ncu(kernel, field="dram_bytes_per_launch"):
+    """a metric of `kernel` from the committed ncu --set full summaries (profiles/ncu_full_r02.json; capture sizes are
+    stated in profiles/README.md), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_full_r02.json")) as f:
             prof = json.load(f)
         for k in prof["kernels"]:
-            if kernel in k["kernel"]:
-                return float(k["dram_bytes_per_launch"])
+            if kernel in k["kernel"] and field in k:
+                return float(k[field])
     except Exception:
         pass
     return None
+
+
+def committed_traffic(kernel):
+    return committed_ncu(kernel)
 
 
 class ClockSampler(threading.Thread):
@@ -534,10 +539,14 @@ def main():
             "nominal_frac_note": "rows^2 x 2 POPC / step time / peak: NOT a hardware fraction (the index issues a small share of "
                                  "the square); kept because SURVEY 8d defines the metric on nominal comparisons",
             "traffic": committed_traffic("mih_bucket_kernel" if need == 1 else "mih2_bucket_kernel"),
-            "note": ("two-chunk bucket keys leave so few pair tests that the POPC pipe idles: this kernel is bound by the latency of "
-                     "its shared-memory histogram / scatter phases and by one pass over the bucket's rows (8 B per row per c2 round "
-                     "from L2/HBM); roofline_bucket_kernel is the POPC-bound kernel of the one-chunk plan on the same index")
+            "note": ("two-chunk bucket keys leave so few pair tests (issued_share_of_nominal) that the POPC pipe idles by design: this "
+                     "kernel is bound by instruction issue across its histogram / scatter / walk phases (ncu_issue_active_pct, "
+                     "ncu_active_lanes_per_instruction from the committed capture) and reads the bucket's rows once per c2 round "
+                     "(hbm_frac_of_kernel). roofline_bucket_kernel is the POPC-bound kernel of the one-chunk plan on the same index: "
+                     "same hits, ~0.9 of the pipe, ~3x the time")
                     if need == 2 else "",
+            "ncu_issue_active_pct": committed_ncu("mih2_bucket_kernel" if need == 2 else "mih_bucket_kernel", "issue_active_pct"),
+            "ncu_active_lanes_per_instruction": committed_ncu("mih2_bucket_kernel" if need == 2 else "mih_bucket_kernel", "active_lanes_per_inst"),
             "hbm_frac_of_kernel": (float(n_rows) * 8.0 * (15 if DHT == 5 else DHT * (DHT + 1) / 2) / world / k_s / 1e9 / hbm_peak) if need == 2 else None,
             "peak_source": "148 SM x 16 POPC lanes/clk/SM (measured, profiles/pipe_probe_r01.json) x %.0f MHz max SM clock" % sm_max_mhz,
         }
@@ -616,6 +625,7 @@ def leg_dct_hash(cb, L, torch, dev, flush, hbm_peak, peak_src):
 
     out = {}
     frames = synth.luma_frames(HASH_FRAMES, seed=2)
+    assert frames.flags.c_contiguous  # the ABI takes raw pointers + strides: 32 / 1024 below must be the real layout
     h_frames = torch.from_numpy(frames).pin_memory()
     d_frames = h_frames.to(dev)
     d_out = torch.empty(HASH_FRAMES, dtype=torch.int64, device=dev)
@@ -689,11 +699,13 @@ def leg_dct_hash(cb, L, torch, dev, flush, hbm_peak, peak_src):
         cvh = np.array([dc.hash_from_tile32_cv2(f) for f in frames[:ncv]], dtype=np.uint64)
         cv_s = time.time() - t0
         x = cvh ^ out_np[:ncv]
+        orc, _ = po.dct_hash64_batch(frames[:ncv], threads=threads)
         flipped = int(sum(POP16[((x >> np.uint64(s)) & np.uint64(0xFFFF)).astype(np.int64)].sum() for s in range(0, 64, 16)))
         out["dct_hash"]["cpu_cv2_single_core"] = {"value": ncv / cv_s, "unit": "frames/s",
                                                   "sample": "%d frames through python cv2 (cv2.dct etc., call overhead included)" % ncv}
         out["dct_hash"]["flip_vs_cv2"] = {"hashes_compared": ncv, "hashes_differ": int((x != 0).sum()), "bits_flipped": flipped,
-                                          "bits_total": 63 * ncv, "cv2_version": __import__("cv2").__version__,
+                                          "bits_total": 63 * ncv, "gpu_equals_oracle": bool(np.array_equal(orc, out_np[:ncv])),
+                                          "cv2_version": __import__("cv2").__version__,
                                           "note": "GPU hashes of this run vs OpenCV's own f32 DCT on the same frames; flips are "
                                                   "coefficients tied with the mean (north_star: stated, measured rate)"}
     except Exception as e:  # cv2 missing on the box: not fatal for the bench line

@@ -70,7 +70,8 @@ def luma_frames(n, seed, w=32, h=32, dup_frac=0.01, lsb_frac=0.01):
     Wy, Wx = weights(h), weights(w)
     up = np.einsum("yi,nij,xj->nyx", Wy, small, Wx, optimize=True)
     up += rng.normal(0, 8, size=up.shape).astype(np.float32)
-    frames = np.clip(np.rint(up), 0, 255).astype(np.uint8)
+    # einsum hands back a permuted-stride array and astype keeps that order: callers pass raw pointers, so force C order
+    frames = np.ascontiguousarray(np.clip(np.rint(up), 0, 255).astype(np.uint8))
     nd, nl = int(n * dup_frac), int(n * lsb_frac)
     if nd and n > 1:
         dst = rng.choice(np.arange(1, n), size=nd, replace=False)

@@ -31,4 +31,9 @@ s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(2):
     assert L.cb_hash_batch_dev(fr.data_ptr(), nf, 32, 32, 32, 1024, ho.data_ptr(), s) == 0
     torch.cuda.synchronize()
+vf = torch.from_numpy(np.tile(synth.video_frames(256, seed=3, letterbox=(12, 0)), (32, 1, 1))).cuda()  # 8192 x 128x128
+vo = torch.empty(len(vf), dtype=torch.int64, device="cuda")
+for _ in range(2):
+    assert L.cb_hash_batch_dev(vf.data_ptr(), len(vf), 128, 128, 128, 128 * 128, vo.data_ptr(), s) == 0
+    torch.cuda.synchronize()
 print("done")
