@@ -646,6 +646,37 @@ __global__ void mih2_count_kernel(const uint64_t* __restrict__ hash, uint32_t n,
 // every group, and the CTA writes hash and row straight to their places (mih2_scatter_kernel). The hashes are read twice,
 // (hash, row) written once: 28 B per row and group instead of ~100 B through the sort. With several ranks a rank simply
 // skips the rows whose group is dealt to another rank: no count has to travel to the host.
+// exclusive scan of one value per thread over the CTA: shuffles inside the warps, one warp for the warp totals, two
+// barriers in all. ws[0..32] is scratch (33 words); returns this thread's exclusive prefix, *total the CTA's sum. The
+// caller synchronises before it uses ws again.
+template <int kThreads>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t acc, uint32_t* ws, uint32_t* total) {
+  static_assert(kThreads % 32 == 0 && kThreads <= 1024, "whole warps, one warp of warp totals");
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = acc;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, off);
+    if (int(lane) >= off) inc += v;
+  }
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < unsigned(kThreads / 32) ? ws[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, off);
+      if (int(lane) >= off) winc += v;
+    }
+    ws[lane] = winc - w;
+    if (lane == 31) ws[32] = winc;
+  }
+  __syncthreads();
+  *total = ws[32];
+  return ws[warp] + inc - acc;
+}
+
 constexpr int kPartThreads = 256;
 constexpr uint32_t kPartTile = 7680;  // rows per CTA: 15 per thread of the scatter kernel, two of its CTAs per SM
 
@@ -653,6 +684,7 @@ constexpr uint32_t kPartTile = 7680;  // rows per CTA: 15 per thread of the scat
 // kernel) while the CTA goes through the chunk groups one after the other. With N ranks every rank has to look at every
 // row of every group to find its own, so what does not shrink with N is this read: one pass instead of one per group.
 constexpr int kScatThreads = 512;
+static_assert(kPartTile < (1u << 16), "the scatter kernel packs a row's rank in its tile into 16 bits");
 
 struct PartGroups {
   int groups;
@@ -698,7 +730,7 @@ __global__ void __launch_bounds__(kScatThreads, 2)
   uint64_t* H = reinterpret_cast<uint64_t*>(scat_smem);
   uint32_t* R = reinterpret_cast<uint32_t*>(scat_smem + size_t(kPartTile) * 8);
   uint32_t* cur = R + kPartTile;
-  __shared__ uint32_t part_sum[kScatThreads];
+  __shared__ uint32_t part_sum[33];
   constexpr int kPer = kPartTile / kScatThreads;  // rows per thread
   const uint32_t t0 = blockIdx.x * kPartTile;
   uint64_t h[kPer];
@@ -714,49 +746,63 @@ __global__ void __launch_bounds__(kScatThreads, 2)
     const uint32_t* at = at_all + G.table_at[g];
     uint64_t* oh = out_hash + size_t(g) * n;
     uint32_t* orow = out_row + size_t(g) * n;
-    __syncthreads();  // the previous group's write-out is done with H / R / cur
+    __syncthreads();  // the previous group's write-out is done with H / R / cur / gofs
+    // where this CTA's slices start in the output: strided reads of the (value, CTA) table, issued now and used after
+    // the count phase so that their latency is covered (up to 2048 values: 10^6..10^8 rows at T = 5; wider chunks read late)
+    constexpr int kAtRegs = 4;
+    uint32_t atv[kAtRegs];
+    const bool at_in_regs = nb <= uint32_t(kAtRegs * kScatThreads);
+    if (at_in_regs) {
+#pragma unroll
+      for (int j = 0; j < kAtRegs; ++j) {
+        const uint32_t b = threadIdx.x + j * kScatThreads;
+        atv[j] = b < nb ? at[size_t(b) * n_cta + blockIdx.x] : 0u;
+      }
+    }
     for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) cur[b] = 0;
     if (blockIdx.x == 0)  // group bounds for the bucket kernel: the first CTA's slice starts the group
       for (uint32_t b = threadIdx.x; b <= nb; b += kScatThreads) ofs_all[size_t(g) * ofs_stride + b] = at[size_t(b) * n_cta];
     __syncthreads();
+    // one atomic per row: its return value is the row's rank inside its group value in this tile (value in the low 16
+    // bits, rank above: plans keep values below 2^12, a tile has 7680 rows)
     uint32_t bin[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const uint32_t i = t0 + threadIdx.x + k * kScatThreads;
       const uint32_t v = uint32_t(h[k] >> shift) & mask;
-      bin[k] = (i < n && (n_parts == 1 || (v + uint32_t(g)) % n_parts == part)) ? v : 0xFFFFFFFFu;
-      if (bin[k] != 0xFFFFFFFFu) atomicAdd(&cur[v], 1u);
+      bin[k] = 0xFFFFFFFFu;
+      if (i < n && (n_parts == 1 || (v + uint32_t(g)) % n_parts == part)) bin[k] = v | (atomicAdd(&cur[v], 1u) << 16);
     }
     __syncthreads();
+    uint32_t total;
     {  // exclusive scan of cur[0..nb) in place
       const uint32_t per = (nb + kScatThreads - 1) / kScatThreads;
       const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
       uint32_t acc = 0;
       for (uint32_t b = b0; b < b1; ++b) acc += cur[b];
-      part_sum[threadIdx.x] = acc;
-      __syncthreads();
-      for (int off = 1; off < kScatThreads; off <<= 1) {
-        const uint32_t v = int(threadIdx.x) >= off ? part_sum[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part_sum[threadIdx.x] += v;
-        __syncthreads();
-      }
-      uint32_t run = threadIdx.x ? part_sum[threadIdx.x - 1] : 0u;
+      uint32_t run = block_excl_scan<kScatThreads>(acc, part_sum, &total);
       for (uint32_t b = b0; b < b1; ++b) {
         const uint32_t c = cur[b];
         cur[b] = run;
         run += c;
       }
     }
-    const uint32_t total = part_sum[kScatThreads - 1];
     __syncthreads();
-    // where this CTA's slice of group value b starts in the output, minus where that value starts in the tile
-    for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) gofs[b] = at[size_t(b) * n_cta + blockIdx.x] - cur[b];
-    __syncthreads();
+    // the tile in group order in shared memory; gofs = where this CTA's slice of value b starts in the output minus
+    // where that value starts in the tile
+    if (at_in_regs) {
+#pragma unroll
+      for (int j = 0; j < kAtRegs; ++j) {
+        const uint32_t b = threadIdx.x + j * kScatThreads;
+        if (b < nb) gofs[b] = atv[j] - cur[b];
+      }
+    } else {
+      for (uint32_t b = threadIdx.x; b < nb; b += kScatThreads) gofs[b] = at[size_t(b) * n_cta + blockIdx.x] - cur[b];
+    }
 #pragma unroll
     for (int k = 0; k < kPer; ++k)
       if (bin[k] != 0xFFFFFFFFu) {
-        const uint32_t pos = atomicAdd(&cur[bin[k]], 1u);
+        const uint32_t pos = cur[bin[k] & 0xFFFFu] + (bin[k] >> 16);
         H[pos] = h[k];
         R[pos] = t0 + threadIdx.x + k * kScatThreads;
       }
@@ -828,7 +874,7 @@ struct L2Cta {
   const int* p_shift;
   const uint32_t* p_mask;
   uint32_t* cur;      // [nb]
-  uint32_t* part_sum; // [kL2Threads]
+  uint32_t* part_sum; // [33]: scratch of the block scan
   const uint64_t* hs; // the bucket's rows
   uint32_t base, s;   // first position and rows of the bucket
   int c1, c2;
@@ -868,21 +914,13 @@ __device__ __forceinline__ uint2 l2_count(const L2Cta& C, unsigned* below_smem) 
   const uint32_t b0 = threadIdx.x * per, b1 = min(C.nb, b0 + per);
   uint32_t acc = 0;
   for (uint32_t b = b0; b < b1; ++b) acc += C.cur[b];
-  C.part_sum[threadIdx.x] = acc;
-  __syncthreads();
-  for (int off = 1; off < kL2Threads; off <<= 1) {
-    const uint32_t v = int(threadIdx.x) >= off ? C.part_sum[threadIdx.x - off] : 0u;
-    __syncthreads();
-    C.part_sum[threadIdx.x] += v;
-    __syncthreads();
-  }
-  uint32_t run = threadIdx.x ? C.part_sum[threadIdx.x - 1] : 0u;
+  uint32_t total;
+  uint32_t run = block_excl_scan<kL2Threads>(acc, C.part_sum, &total);
   for (uint32_t b = b0; b < b1; ++b) {
     const uint32_t c = C.cur[b];
     C.cur[b] = run;
     run += c;
   }
-  const uint32_t total = C.part_sum[kL2Threads - 1];
   __syncthreads();
   return make_uint2(total, *below_smem);
 }
@@ -938,7 +976,7 @@ __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args
   __shared__ uint4 stage[kL2Stage];
   __shared__ unsigned n_staged, kept, below_rows;
   __shared__ unsigned long long g_base, tests_cta;
-  __shared__ uint32_t part_sum[kL2Threads];
+  __shared__ uint32_t part_sum[33];
   __shared__ int p_shift[kMihMaxChunks + 1];  // the plan's chunk table out of the parameter space (dynamic indexing)
   __shared__ uint32_t p_mask[kMihMaxChunks + 1];
   __shared__ L2Emit E;
@@ -1120,6 +1158,12 @@ int mih_need_for(uint64_t n, int threshold) {
   if (g_forced_need == 1 || g_forced_need == 2) return g_forced_need;
   static const int env = getenv("CB_MIH_NEED") ? atoi(getenv("CB_MIH_NEED")) : 0;
   if (env == 1 || env == 2) return env;
+  // Costs in units of one pair test of mih_bucket_kernel (4.2e12/s), fitted to tools/mih_bench.py at T = 3, 5, 8 and
+  // 2^20 .. 10^7 rows (profiles/mih_bench_r02.jsonl):
+  //   one-chunk keys: ~0.3 ms of fixed launches + 60 per sorted (row, unit) item + the bucket tests, a block of 256 rows
+  //                   padding every bucket (s + 256), at 0.8 of the kernel's best rate
+  //   two-chunk keys: ~0.4 ms fixed + 62 per row and chunk group (histogram, scans, ordered scatter) + 58 per row and
+  //                   unit (bin histogram, re-order, walk set-up) + the walk's tests, which diverge: 3 each
   double best = 0;
   int best_need = 1;
   for (int need = 1; need <= 2; ++need) {
@@ -1127,10 +1171,11 @@ int mih_need_for(uint64_t n, int threshold) {
     double tests = 0;
     for (int u = 0; u < p.units; ++u) {
       const int bits = need == 1 ? p.bits[p.u_c1[u]] : p.bits[p.u_c1[u]] + p.bits[p.u_c2[u]];
-      const double s = double(n) / double(1u << bits);  // rows per bucket on uniformly random hashes
-      tests += double(n) * (s + 256.0) / 2.0;
+      const double s = double(n) / double(1ull << bits);  // rows per bucket on uniformly random hashes
+      tests += need == 1 ? double(n) * (s + 256.0) / 2.0 : double(n) * s / 2.0;
     }
-    const double cost = double(n) * p.units * 60.0 + tests;  // one sorted item ~ 60 pair tests
+    const double cost = need == 1 ? 1.2e9 + double(n) * p.units * 60.0 + 1.25 * tests
+                                  : 1.7e9 + double(n) * ((p.chunks - 1) * 62.0 + p.units * 58.0) + 3.0 * tests;
     if (need == 1 || cost < best) {
       best = cost;
       best_need = need;

@@ -128,8 +128,8 @@ def test_every_prefilter_and_key_width(cb, variant, need):
     np.random.default_rng(1).shuffle(h)
     try:
         L.cb_scan64_mih_force(variant, need)
-        for thr in (3, 5, 8):
-            want, got, _ = both(cb, h, thr, cap=1 << 23)
+        for thr in ((1, 2, 3, 5, 8, 10) if need == 2 else (3, 5, 8)):  # the plan model picks two-chunk keys at every T
+            want, got, _ = both(cb, h, thr, cap=1 << 24)
             assert np.array_equal(got, want), (variant, need, thr)
         want, got, per_part = both(cb, h, 5, parts=3, cap=1 << 23)
         assert np.array_equal(got, want) and sum(len(p) for p in per_part) == len(want)
