@@ -867,12 +867,13 @@ __device__ __noinline__ void l2_emit(const L2Emit& A, uint4* stage, unsigned* n_
 // (one range = the whole bucket when the bucket is expected to fit shared memory; the host cuts larger buckets into
 // ranges, gridDim.x of them, neighbours in launch order so that the bucket is read from HBM once and from L2 after
 // that). Rows that fit the CTA's shared memory (L2Args::smem_rows) are re-ordered there, 8 B of hash + 4 B of position
-// per row; otherwise in the global scratch. After the scatter cur[b] is the END of bin b; a row at bin-ordered position
-// p walks the rows after it up to the end of its own bin, so a bin of c rows costs c (c - 1) / 2 tests spread over c
-// threads, whatever c is.
+// per row; otherwise in the global scratch. After the scatter cur[b] is the END of bin b (and the start of bin b + 1); the row
+// at bin-ordered position p is compared with the half of its bin that follows it cyclically, so a bin of c rows costs
+// c (c - 1) / 2 tests spread evenly over its c threads.
 struct L2Cta {
   const int* p_shift;
   const uint32_t* p_mask;
+  const uint64_t* p_cmask;  // chunk c's bits in place
   uint32_t* cur;      // [nb]
   uint32_t* part_sum; // [33]: scratch of the block scan
   const uint64_t* hs; // the bucket's rows
@@ -945,24 +946,33 @@ __device__ __forceinline__ void l2_scatter_walk(const L2Args& A, const L2Emit& E
     }
   }
   __syncthreads();
+  // Every unordered pair of a bin once, the same number of tests for every row of the bin: row i of a bin of c rows takes
+  // the (c - 1) / 2 rows after it, cyclically, and for even c the rows of the first half take the opposite row too. (A
+  // walk to the end of the bin gives the rows of one bin c - 1, c - 2, ... 0 tests: half of the lanes of a warp idle.)
   unsigned long long tests = 0;
   for (uint32_t p = threadIdx.x; p < rows; p += kL2Threads) {
     const uint64_t hp = H[p];
-    const uint32_t end = C.cur[(uint32_t(hp >> sh2) & mk2) - C.bin_lo];
-    if (end - p > kL2BinCap) {  // heavily skewed data: the caller takes the one-chunk keys
+    const uint32_t bin = (uint32_t(hp >> sh2) & mk2) - C.bin_lo;
+    const uint32_t end = C.cur[bin], beg = bin ? C.cur[bin - 1] : 0u;
+    const uint32_t c = end - beg;
+    if (c > kL2BinCap) {  // heavily skewed data: the caller takes the one-chunk keys
       A.info[kDeclined] = 1;
       continue;
     }
-    tests += end - p - 1;
-    for (uint32_t q = p + 1; q < end; ++q) {
+    uint32_t trips = (c - 1) >> 1;
+    if (!(c & 1u) && p - beg < (c >> 1)) ++trips;
+    tests += trips;
+    uint32_t q = p;
+    for (uint32_t t = 0; t < trips; ++t) {
+      if (++q == end) q = beg;
       const uint64_t x = hp ^ H[q];
       const uint32_t xlo = uint32_t(x), xhi = uint32_t(x >> 32);
       if (__popc(xlo | xhi) >= T) continue;
       const int d = __popc(xlo) + __popc(xhi);
       if (d >= T) continue;
       bool first = true;  // reported by the first unit in which the two hashes share a bucket
-      for (int c = 0; c < C.c2; ++c)
-        if (c != C.c1 && ((uint32_t(x >> C.p_shift[c])) & C.p_mask[c]) == 0) first = false;
+      for (int c0 = 0; c0 < C.c2; ++c0)
+        if (c0 != C.c1 && (x & C.p_cmask[c0]) == 0) first = false;
       if (!first) continue;
       l2_emit(E, C.stage, C.n_staged, C.base + P[p], C.base + P[q], uint32_t(d));
     }
@@ -979,6 +989,7 @@ __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args
   __shared__ uint32_t part_sum[33];
   __shared__ int p_shift[kMihMaxChunks + 1];  // the plan's chunk table out of the parameter space (dynamic indexing)
   __shared__ uint32_t p_mask[kMihMaxChunks + 1];
+  __shared__ uint64_t p_cmask[kMihMaxChunks + 1];
   __shared__ L2Emit E;
   const int c1 = A.c1, c2 = A.c1 + 1 + int(blockIdx.z);
   const uint32_t base = A.ofs[blockIdx.y], s = A.ofs[blockIdx.y + 1] - base;
@@ -990,6 +1001,7 @@ __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args
   if (threadIdx.x <= kMihMaxChunks) {
     p_shift[threadIdx.x] = A.plan.shift[threadIdx.x];
     p_mask[threadIdx.x] = A.plan.mask[threadIdx.x];
+    p_cmask[threadIdx.x] = uint64_t(A.plan.mask[threadIdx.x]) << A.plan.shift[threadIdx.x];
   }
   if (threadIdx.x == 0) {
     n_staged = 0;
@@ -1003,7 +1015,7 @@ __global__ void __launch_bounds__(kL2Threads, 2) mih2_bucket_kernel(const L2Args
   const uint32_t per_part = (nb_all + gridDim.x - 1) / gridDim.x;
   const uint32_t bin_lo = blockIdx.x * per_part;
   if (bin_lo >= nb_all) return;
-  L2Cta C{p_shift, p_mask, reinterpret_cast<uint32_t*>(l2_smem), part_sum, A.sorted + base, base, s, c1, c2, bin_lo,
+  L2Cta C{p_shift, p_mask, p_cmask, reinterpret_cast<uint32_t*>(l2_smem), part_sum, A.sorted + base, base, s, c1, c2, bin_lo,
           min(per_part, nb_all - bin_lo), stage, &n_staged, &tests_cta};
   const uint2 cnt = l2_count(C, &below_rows);
   if (cnt.x >= 2) {
