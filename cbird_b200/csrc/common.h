@@ -154,6 +154,7 @@ struct MihOut {  // where the self-join reports
   unsigned long long* count;  // total, also beyond cap
   const uint32_t* ids;        // mode 1: row -> mediaId (0 = removed row: dropped)
   int needle_shift;           // mode 1
+  int no_self;                // 1: the (row, row, 0) matches are left out (the caller adds them: -similar's post step)
 };
 struct MihWorkspace {
   DevBuf<uint32_t> key, key2, val, val2, ofs, nblk, blk_at, nitems, item_at, perm;

@@ -81,7 +81,7 @@ struct KeyLayout {
   uint32_t score_mask;
 };
 
-// brute-force scan hits (needle = a, matched row = b) -> keys; rows without id are dropped
+// brute-force scan hits (needle = a, matched row = b) -> keys; rows without id and the (a, a) matches are dropped
 __global__ void pairs_to_keys(const cb_pair* __restrict__ pairs, unsigned long long n, const uint32_t* __restrict__ ids,
                               KeyLayout L, unsigned long long* __restrict__ keys, unsigned long long cap,
                               unsigned long long* __restrict__ count) {
@@ -90,7 +90,7 @@ __global__ void pairs_to_keys(const cb_pair* __restrict__ pairs, unsigned long l
   cb_pair p{0, 0, 0, 0};
   if (i < n) {
     p = pairs[i];
-    id = ids[p.b];
+    id = p.a != p.b ? ids[p.b] : 0u;  // a row's match with itself is added by the post step
   }
   const unsigned m = __ballot_sync(0xffffffffu, id != 0);
   if (!m) return;
@@ -169,6 +169,11 @@ __global__ void similar_post_count(const unsigned long long* __restrict__ keys, 
   int t = P.dht;
   long long k = 0;
   if (row_hash[row] != 0) {  // needles without hash find nothing (dcthashindex.cpp:196-200)
+    // The key list holds the matches with OTHER rows. Every row with an id also matches itself at distance 0 (nine
+    // tenths of all matches of a typical index): that one is added here instead of travelling through the exchange
+    // and the sort. It sorts as (score 0, own id).
+    const uint32_t self = row_id[row];
+    const bool has_self = self != 0;
     unsigned long long j = lo;
     if (P.escalate) {
       // the reference re-runs find() with dht+1, dht+2, ... while the needle has <= minMatches matches (self
@@ -176,36 +181,56 @@ __global__ void similar_post_count(const unsigned long long* __restrict__ keys, 
       long long cnt = 0;
       for (;;) {
         while (j < n_keys && uint32_t(keys[j] >> L.needle_shift) == row && int((keys[j] >> 32) & L.score_mask) < t) ++j, ++cnt;
-        if (cnt > P.min_matches || t + 1 > P.max_thresh) break;
+        if (cnt + (has_self && t > 0 ? 1 : 0) > P.min_matches || t + 1 > P.max_thresh) break;
         ++t;
       }
     }
-    const uint32_t self = row_id[row];
     for (j = lo; j < n_keys && k < P.max_matches; ++j) {
       const unsigned long long key = keys[j];
       if (uint32_t(key >> L.needle_shift) != row || int((key >> 32) & L.score_mask) >= t) break;
       if (P.filter_self && uint32_t(key) == self) continue;
       ++k;
     }
+    if (has_self && t > 0 && !P.filter_self && k < P.max_matches) ++k;
   }
   kept[i] = k;
 }
 
-__global__ void similar_post_scatter(const unsigned long long* __restrict__ keys, KeyLayout L, const uint32_t* __restrict__ row_id,
-                                     uint32_t row0, uint32_t n_rows, SimilarPost P, const unsigned long long* __restrict__ begin,
-                                     const long long* __restrict__ kept, const long long* __restrict__ offsets,
-                                     cb_hit* __restrict__ out) {
+__global__ void similar_post_scatter(const unsigned long long* __restrict__ keys, unsigned long long n_keys, KeyLayout L,
+                                     const uint32_t* __restrict__ row_id, uint32_t row0, uint32_t n_rows, SimilarPost P,
+                                     const unsigned long long* __restrict__ begin, const long long* __restrict__ kept,
+                                     const long long* __restrict__ offsets, cb_hit* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   const long long want = kept[i];
   if (!want) return;
   const uint32_t row = row0 + i, self = row_id[row];
   cb_hit* dst = out + offsets[i];
+  // the first `want` entries of the needle's keys merged with its self match (score 0, own id); all of them are below
+  // the threshold the count pass settled on
+  bool self_pending = self != 0 && !P.filter_self;
   long long k = 0;
-  for (unsigned long long j = begin[i]; k < want; ++j) {
-    const unsigned long long key = keys[j];
-    if (P.filter_self && uint32_t(key) == self) continue;
-    dst[k++] = cb_hit{row, uint32_t(key), int32_t((key >> 32) & L.score_mask)};
+  unsigned long long j = begin[i];
+  while (k < want) {
+    if (j < n_keys && uint32_t(keys[j] >> L.needle_shift) == row) {
+      const unsigned long long key = keys[j];
+      if (P.filter_self && uint32_t(key) == self) {
+        ++j;
+        continue;
+      }
+      const int score = int((key >> 32) & L.score_mask);
+      if (self_pending && (score != 0 || uint32_t(key) > self)) {
+        dst[k++] = cb_hit{row, self, 0};
+        self_pending = false;
+        continue;
+      }
+      dst[k++] = cb_hit{row, uint32_t(key), score};
+      ++j;
+    } else {
+      if (!self_pending) break;  // (cannot happen: the count pass saw the same keys)
+      dst[k++] = cb_hit{row, self, 0};
+      self_pending = false;
+    }
   }
 }
 
@@ -579,7 +604,7 @@ struct DctIndex {
       if (symmetric_self && !mih_declined && mih_applicable(n_rows, threshold)) {
         // small thresholds: multi-index self-join (same hit set from a fraction of the pair tests); declined
         // when the buckets are so skewed that it would cost more than half of the symmetric brute-force scan
-        MihOut out{0, S.d_pairs.p, cap, S.d_counts.p, nullptr, 0};
+        MihOut out{0, S.d_pairs.p, cap, S.d_counts.p, nullptr, 0, 0};
         rc = scan64_self_mih(S.d_hashes.p, n_rows, threshold, 0, 1, out, S.mih, (unsigned long long)n_rows * n_rows / 4, stream,
                              mih_need);
         if (rc != CB_OK) return rc;
@@ -743,7 +768,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
       cap = S.d_keys.cap;
       CB_CUDA(cudaMemsetAsync(S.d_counts.p, 0, 64 * sizeof(unsigned long long), st));
       if (use_mih) {
-        MihOut out{1, S.d_keys.p, cap, S.d_counts.p, S.d_ids.p, J.L.needle_shift};
+        MihOut out{1, S.d_keys.p, cap, S.d_counts.p, S.d_ids.p, J.L.needle_shift, 1};  // self matches: the post step's
         // declined when the buckets are so skewed that the pass would cost more than half the symmetric scan
         rc = scan64_self_mih(S.d_hashes.p, n, J.scan_thresh, uint32_t(rank), uint32_t(world), out, S.mih,
                              (unsigned long long)n * n / 4 / world, st, mih_need);
@@ -904,7 +929,7 @@ int similar_rank(SimilarJob& J, DctShard& S, int local_index) {
     if (!J.want_lists) return CB_OK;
     if ((rc = S.d_post_out.reserve(std::max<unsigned long long>(kept, 1))) != CB_OK) return rc;
     if (kept) {
-      similar_post_scatter<<<post_blocks, 256, 0, st>>>(keys, J.L, S.d_ids.p, r0, n_rows, J.P, S.d_post_begin.p, S.d_post_kept.p,
+      similar_post_scatter<<<post_blocks, 256, 0, st>>>(keys, n_keys, J.L, S.d_ids.p, r0, n_rows, J.P, S.d_post_begin.p, S.d_post_kept.p,
                                                        S.d_post_off.p, S.d_post_out.p);
       CB_CUDA(cudaGetLastError());
       counters().launches += 1;

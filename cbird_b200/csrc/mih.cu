@@ -1352,9 +1352,11 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
   if (plan.need == 2 && !walk) {
     int rc2 = scan64_self_mih2(d_hashes, n, threshold, part, n_parts, out, ws, plan, stream);
     if (rc2 != CB_OK) return rc2;
-    mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
-    CB_CUDA(cudaGetLastError());
-    counters().launches += 1;
+    if (!out.no_self) {
+      mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
+      CB_CUDA(cudaGetLastError());
+      counters().launches += 1;
+    }
     return CB_OK;
   }
   // units are processed in batches that keep the sort below 2^29 items
@@ -1463,9 +1465,11 @@ int scan64_self_mih(const uint64_t* d_hashes, uint32_t n, int threshold, uint32_
     ws.n_batches = batch_no + 1;  // the next batch reuses the sort buffers: stream order keeps that safe
   }
   // self pairs: rows [0, n) (dealt by their unit-0 bucket when the buckets are dealt)
-  mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
-  CB_CUDA(cudaGetLastError());
-  counters().launches += 1;
+  if (!out.no_self) {
+    mih_self_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_hashes, 0, n, plan, part, n_parts, out);
+    CB_CUDA(cudaGetLastError());
+    counters().launches += 1;
+  }
   return CB_OK;
 }
 
