@@ -58,13 +58,13 @@ def load_peaks():
 
 def committed_ncu(kernel, field="dram_bytes_per_launch"):
     """a metric of `kernel` from the committed ncu --set full summaries (profiles/ncu_full_r02.json; capture sizes are
-    stated in profiles/README.md), or None."""
+    stated in profiles/README.md): the mean over the kernel's launches in the capture (one whole pass), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_full_r02.json")) as f:
             prof = json.load(f)
-        for k in prof["kernels"]:
-            if kernel in k["kernel"] and field in k:
-                return float(k[field])
+        vals = [float(k[field]) for k in prof["kernels"] if kernel in k["kernel"] and field in k]
+        if vals:
+            return sum(vals) / len(vals)
     except Exception:
         pass
     return None
