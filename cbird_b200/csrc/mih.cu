@@ -1174,7 +1174,7 @@ int mih_need_for(uint64_t n, int threshold) {
   // 2^20 .. 10^7 rows (profiles/mih_bench_r02.jsonl):
   //   one-chunk keys: ~0.3 ms of fixed launches + 60 per sorted (row, unit) item + the bucket tests, a block of 256 rows
   //                   padding every bucket (s + 256), at 0.8 of the kernel's best rate
-  //   two-chunk keys: ~0.4 ms fixed + 62 per row and chunk group (histogram, scans, ordered scatter) + 58 per row and
+  //   two-chunk keys: ~0.5 ms fixed + 62 per row and chunk group (histogram, scans, ordered scatter) + 58 per row and
   //                   unit (bin histogram, re-order, walk set-up) + the walk's tests, which diverge: 3 each
   double best = 0;
   int best_need = 1;
@@ -1187,7 +1187,7 @@ int mih_need_for(uint64_t n, int threshold) {
       tests += need == 1 ? double(n) * (s + 256.0) / 2.0 : double(n) * s / 2.0;
     }
     const double cost = need == 1 ? 1.2e9 + double(n) * p.units * 60.0 + 1.25 * tests
-                                  : 1.7e9 + double(n) * ((p.chunks - 1) * 62.0 + p.units * 58.0) + 3.0 * tests;
+                                  : 2.0e9 + double(n) * ((p.chunks - 1) * 62.0 + p.units * 58.0) + 3.0 * tests;
     if (need == 1 || cost < best) {
       best = cost;
       best_need = need;
