@@ -156,7 +156,8 @@ def test_bucket_dealt_multi_index_merge(tmp_path, po):
 def _worker_exchange(rank, world, port, n, t, out_dir):
     """the sharded -similar protocol of cbird_b200/csrc/dct_index.cu on the host: this rank's share of the bucket scans
     (numpy), every hit routed to the rank that owns its needle row (cb_comm_shard_rows), exact counts exchanged first,
-    point-to-point transfers, then sort by (needle, score, id) — gloo stands in for the NCCL all-to-all."""
+    point-to-point transfers, then sort by (needle, score, id) with every row's match with itself merged in by its
+    owner — gloo stands in for the NCCL all-to-all."""
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -171,6 +172,7 @@ def _worker_exchange(rank, world, port, n, t, out_dir):
     assert L.cb_scan64_mih_plan(t, shifts.ctypes.data, masks.ctypes.data) == t
     h, _ = synth.dct_hashes(n, seed=6, planted_frac=0.4)
     local = _mih_lists(h, t, rank, world, shifts[:t].astype(np.uint64), masks[:t].astype(np.uint64)).astype(np.int64)
+    local = local[local[:, 0] != local[:, 1]]  # a row's match with itself never travels: the owner's post step adds it
     spans = []
     for r in range(world):
         b, e = C.c_int64(0), C.c_int64(0)
@@ -202,6 +204,8 @@ def _worker_exchange(rank, world, port, n, t, out_dir):
     mine = torch.cat(got).numpy()
     assert len(mine) == sum(int(table[r][rank]) for r in range(world))
     assert mine[:, 0].min() >= spans[rank][0] and mine[:, 0].max() < spans[rank][1]
+    own = np.arange(spans[rank][0], spans[rank][1], dtype=np.int64)  # post step: (row, row, distance 0) for the rank's rows
+    mine = np.concatenate([mine, np.stack([own, own, np.zeros_like(own), np.zeros_like(own)], 1)])
     mine = mine[np.lexsort((mine[:, 1], mine[:, 2], mine[:, 0]))][:, :3]  # (needle, score, row): ids ascend with rows here
     np.save(os.path.join(out_dir, "ex_%d.npy" % rank), mine)
     np.save(os.path.join(out_dir, "span_%d.npy" % rank), np.array(spans[rank]))
