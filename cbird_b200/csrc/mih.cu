@@ -11,6 +11,7 @@
 // several units is reported by the first of them only, and every unordered pair is tested once and
 // reported in both orders, so the hit set is exactly the brute-force one.
 //
+// j = 1 (one-chunk bucket keys; below ~1.3e6 rows at T = 5 and the fallback for skewed data):
 //   keys    (unit << bucket bits | bucket, row) for every unit of every row            mih_keys_kernel
 //   sort    one stable LSD radix sort over all units of a batch                         cub::DeviceRadixSort
 //   gather  hashes in bucket order (bucket-contiguous, like the video index)             mih_gather_kernel
@@ -22,10 +23,16 @@
 //           segment streamed through the warp's own 2 KB of shared memory and read with broadcast
 //           LDS.128; a cheap lower bound of the distance first (1 POPC per two pairs), exact re-test of
 //           the survivors; hits staged in shared memory, one global atomic per flush       mih_bucket_kernel
-//   self    every row matches itself                                                      mih_self_kernel
+// j = 2 (two-chunk bucket keys; the default above that):
+//   group   rows grouped by the value of chunk c1, once for all units (c1, c2 > c1): a counting sort over
+//           all k - 1 groups in one pass (per-CTA counts, one exclusive scan per group, ordered scatter
+//           through shared memory)                            mih2_hist_all_kernel, mih2_scatter_all_kernel
+//   scan    one CTA per (c1 bucket, c2): the bucket re-binned by chunk c2 in shared memory, every row
+//           compared with the half of its bin that follows it cyclically                mih2_bucket_kernel
+//   self    every row matches itself (left out when the caller adds those itself)         mih_self_kernel
 //
-// Multi-GPU: buckets are dealt to ranks ((bucket + unit) % n_parts); every rank sorts and scans only its
-// own buckets, and the per-rank hit lists are disjoint by construction.
+// Multi-GPU: buckets are dealt to ranks ((bucket + unit) % n_parts, resp. (c1 value + c1) % n_parts); every
+// rank groups and scans only its own buckets, and the per-rank hit lists are disjoint by construction.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -642,8 +649,8 @@ __global__ void mih2_count_kernel(const uint64_t* __restrict__ hash, uint32_t n,
 // ---- grouping the rows by one chunk: a two-kernel counting sort ----------------------------------------------
 // The rows only have to be GROUPED by the value of chunk c1 (10-11 bits), not sorted, and the kernels that follow want
 // the hashes themselves in group order. So instead of keys + radix sort + gather: every CTA counts its tile of rows per
-// chunk value (mih2_hist_kernel), one exclusive scan over the (value, CTA) table gives every CTA its private slice of
-// every group, and the CTA writes hash and row straight to their places (mih2_scatter_kernel). The hashes are read twice,
+// chunk value (mih2_hist_all_kernel), one exclusive scan over the (value, CTA) table gives every CTA its private slice of
+// every group, and the CTA writes hash and row straight to their places (mih2_scatter_all_kernel). The hashes are read twice,
 // (hash, row) written once: 28 B per row and group instead of ~100 B through the sort. With several ranks a rank simply
 // skips the rows whose group is dealt to another rank: no count has to travel to the host.
 // exclusive scan of one value per thread over the CTA: shuffles inside the warps, one warp for the warp totals, two
